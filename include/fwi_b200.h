@@ -1,0 +1,152 @@
+/*
+ * fwi_b200.h -- C ABI of the B200-native FWI hot path (libfwi_b200.so).
+ *
+ * Drop-in boundary of the reference's 2-D elastic FWI operator.  Every entry
+ * point below replaces one interface of lidongzh/FwiFlow.jl (paths relative to
+ * the reference root):
+ *
+ *   fwi_b200_cufd      <- cufd(...)       deps/CustomOps/FWI/Src/libCUFD.cu:34-38
+ *                                         (declared deps/CustomOps/FWI/FwiOp.h:9-12)
+ *   fwi_b200_forward   <- forward(...)    deps/CustomOps/FWI/FwiOp.h:14-19   (calc_id 0)
+ *   fwi_b200_backward  <- backward(...)   deps/CustomOps/FWI/FwiOp.h:21-27   (calc_id 1)
+ *   fwi_b200_obscalc   <- obscalc(...)    deps/CustomOps/FWI/FwiOp.h:29-33   (calc_id 2)
+ *
+ * Same argument order, meaning, units and array layouts as the reference:
+ *   Lambda, Mu, Den : (nz, nx) double, ROW-MAJOR [z][x] (nz, nx = padded sizes of the
+ *                     para file), Lambda/Mu in MPa          (libCUFD.cu:68-78)
+ *   stf             : (nShotsTotal, nSteps) double row-major, row = GLOBAL shot id
+ *                                                            (Src_Rec.cu:132-137)
+ *   shot_ids        : group_size int32, 0-based; survey keys "shot<id>" (Src_Rec.cu:86)
+ *   grad_*          : same shapes as the inputs, d(misfit)/d(MPa) for Lambda/Mu;
+ *                     grad_stf is (group_size, nSteps), row = POSITION in the group
+ *                     (libCUFD.cu:454-456)
+ *   para_fname      : path of the single-line JSON parameter file (Parameter.cpp:16-178);
+ *                     it names the survey file and the Data directory holding
+ *                     Shot<id>.bin (float32, [rec][time])   (libCUFD.cu:189-192,514-521)
+ * The only deliberate differences: `const char*` instead of `std::string`, and
+ * errors are RETURNED (0 = ok, <0 = error, text via fwi_b200_last_error()) instead
+ * of printf + exit() (utilities.h:25-33).
+ *
+ * All compute runs in hand-written CUDA kernels for sm_100a.  There is no CPU
+ * fallback: without a usable CUDA device every compute entry point fails with
+ * FWI_B200_ERR_CUDA.
+ */
+#ifndef FWI_B200_H_
+#define FWI_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FWI_B200_OK 0
+#define FWI_B200_ERR_ARG (-1)     /* bad argument / calc_id                       */
+#define FWI_B200_ERR_IO (-2)      /* para / survey / Shot<id>.bin file problem     */
+#define FWI_B200_ERR_JSON (-3)    /* malformed or incomplete JSON                  */
+#define FWI_B200_ERR_CFL (-4)     /* Courant number > 1 (utilities.cu:225-240)     */
+#define FWI_B200_ERR_CUDA (-5)    /* CUDA runtime error / no device                */
+#define FWI_B200_ERR_UNSUPPORTED (-6) /* if_win / filter / if_src_update requested */
+#define FWI_B200_ERR_GEOM (-7)    /* source / receiver outside the grid, grid too small */
+
+/* ---- reference-compatible host-buffer entry points ------------------------- */
+
+int fwi_b200_cufd(double *misfit, double *grad_Lambda, double *grad_Mu, double *grad_Den,
+                  double *grad_stf, const double *Lambda, const double *Mu, const double *Den,
+                  const double *stf, int calc_id, int gpu_id, int group_size,
+                  const int *shot_ids, const char *para_fname);
+
+int fwi_b200_forward(double *misfit, const double *Lambda, const double *Mu, const double *Den,
+                     const double *stf, int gpu_id, int group_size, const int *shot_ids,
+                     const char *para_fname);
+
+int fwi_b200_backward(double *grad_Lambda, double *grad_Mu, double *grad_Den, double *grad_stf,
+                      const double *Lambda, const double *Mu, const double *Den,
+                      const double *stf, int gpu_id, int group_size, const int *shot_ids,
+                      const char *para_fname);
+
+int fwi_b200_obscalc(double *misfit, const double *Lambda, const double *Mu, const double *Den,
+                     const double *stf, int gpu_id, int group_size, const int *shot_ids,
+                     const char *para_fname);
+
+/* Fused loss + gradient from ONE forward propagation (the reference propagates twice
+ * per L-BFGS evaluation: FwiOp.cpp:100 and :220).  Any output pointer may be NULL. */
+int fwi_b200_misfit_and_gradient(double *misfit, double *grad_Lambda, double *grad_Mu,
+                                 double *grad_Den, double *grad_stf, const double *Lambda,
+                                 const double *Mu, const double *Den, const double *stf,
+                                 int gpu_id, int group_size, const int *shot_ids,
+                                 const char *para_fname);
+
+/* Text of the last error raised on the calling thread ("" if none). */
+const char *fwi_b200_last_error(void);
+
+/* Free every cached device context (plans are cached per gpu / para file content). */
+void fwi_b200_release(void);
+
+/* ---- device-resident plan API (what the host entry points are built on) ----- *
+ * A plan owns, on one GPU, everything that `cufd` allocates and frees per call
+ * (libCUFD.cu:115-137,538-575): model + derived coefficients, CPML profiles,
+ * wavefields for a batch of concurrent shots, boundary-frame store, traces.
+ * Inputs can be pushed once and kept resident across calls; outputs stay on the
+ * device until asked for, so that a multi-GPU driver can all-reduce them in place. */
+typedef struct fwi_b200_plan fwi_b200_plan;
+
+/* max_batch: shots advanced per kernel launch (0 = choose from free memory). */
+int fwi_b200_plan_create(fwi_b200_plan **plan, const char *para_fname, int gpu_id,
+                         int group_size, const int *shot_ids, int max_batch);
+void fwi_b200_plan_destroy(fwi_b200_plan *plan);
+
+/* host -> device.  Same layouts as fwi_b200_cufd. */
+int fwi_b200_plan_set_model(fwi_b200_plan *plan, const double *Lambda, const double *Mu,
+                            const double *Den);
+int fwi_b200_plan_set_stf(fwi_b200_plan *plan, const double *stf);
+/* observed data of the i-th shot of the group: (nrec, nSteps) float32, time fastest. */
+int fwi_b200_plan_set_obs(fwi_b200_plan *plan, int ishot, const float *obs);
+/* read data_dir_name/Shot<id>.bin for every shot of the group (libCUFD.cu:189-192). */
+int fwi_b200_plan_load_obs_files(fwi_b200_plan *plan);
+
+/* Enqueue one evaluation on `stream` (a cudaStream_t; NULL = the plan's own stream):
+ * calc_id 0 misfit, 1 gradient (+misfit), 2 synthetic traces.  Does not synchronise
+ * unless `sync` != 0.  Results stay on the device. */
+int fwi_b200_plan_run(fwi_b200_plan *plan, int calc_id, void *stream, int sync);
+
+/* Device pointer to the packed result [grad_Lambda | grad_Mu | grad_Den | misfit]:
+ * 3*nz*nx + 1 float32, gradients ROW-MAJOR [z][x] per MPa, misfit = 0.5*sum(res^2).
+ * This is the buffer a multi-GPU driver all-reduces (ncclAllReduce, sum). */
+float *fwi_b200_plan_result_device(fwi_b200_plan *plan);
+size_t fwi_b200_plan_result_count(fwi_b200_plan *plan);
+
+/* device -> host copies (synchronise the plan's stream first). */
+int fwi_b200_plan_get_result(fwi_b200_plan *plan, double *misfit, double *grad_Lambda,
+                             double *grad_Mu, double *grad_Den, double *grad_stf);
+/* which: 0 synthetic, 1 residual (tapered), 2 conditioned observed -- (nrec, nSteps) float32 */
+int fwi_b200_plan_get_traces(fwi_b200_plan *plan, int ishot, int which, float *out);
+int fwi_b200_plan_write_obs_files(fwi_b200_plan *plan);
+
+/* Geometry / bookkeeping queries. */
+int fwi_b200_plan_info(fwi_b200_plan *plan, int *nz, int *nx, int *nSteps, int *nPml, int *nPad,
+                       int *group_size, int *batch, int *max_nrec);
+/* resolved 0-based padded indices of the i-th shot of the group (Src_Rec.cu:86-113). */
+int fwi_b200_plan_shot_geometry(fwi_b200_plan *plan, int ishot, int *z_src, int *x_src,
+                                int *nrec, int *z_rec, int *x_rec);
+/* number of kernels launched by the plan since creation (bench.py's gpu_launches). */
+long long fwi_b200_plan_launch_count(fwi_b200_plan *plan);
+/* Debug / invariant tests: copy one wavefield of shot `ishot` of the current batch to the
+ * host as [z][x] float32.  field: 0 vz 1 vx 2 szz 3 sxx 4 sxz (forward / reconstructed). */
+int fwi_b200_plan_get_field(fwi_b200_plan *plan, int ishot, int field, float *out);
+
+/* Kernel timing for the roofline: runs `iters` launches of one hot kernel on the plan's
+ * current state (which: 0 forward step, 1 forward step + frame save, 2 reverse+imaging,
+ * 3 adjoint step) on `stream` between two CUDA events, returns the mean ms per launch
+ * and the algorithmic bytes one launch moves. */
+int fwi_b200_plan_time_kernel(fwi_b200_plan *plan, int which, int iters, void *stream,
+                              float *ms_per_launch, double *alg_bytes_per_launch);
+
+/* Library / device self-description (JSON text, static storage). */
+const char *fwi_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FWI_B200_H_ */
