@@ -1,0 +1,143 @@
+// Device-side data layout and kernel launchers of the FWI hot path (sm_100a).
+//
+// Layout in HBM (all float32, z fastest like the reference's a[x*nz+z]):
+//   plane  = one 2-D array, column pitch P (multiple of 32 floats), XM margin columns on
+//            either side of x and SLACK floats before/after, so halo reads never leave the
+//            allocation.  A "plane pointer" always points at (z=0, x=0).
+//   state  = [shot][slot][plane]: 36 planes per concurrent shot (slots below)
+//   model  = lambda, mu, mu_bar, byc_a, byc_b planes shared by all shots
+//   frames = [shot][step][field 0..4][flen]  saved boundary frames (5 layers)
+//   traces = [shot][step][nrp]  (receiver fastest -> coalesced record / inject)
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+#include <cstdint>
+
+namespace fwi {
+
+constexpr int XM = 4;        // margin columns in x
+constexpr int SLACK = 256;   // floats before / after each plane
+constexpr int TILE_Z = 64;   // owner tile (z fastest)
+constexpr int TILE_X = 32;
+constexpr int NTHREADS = 256;
+
+// state slots
+enum Slot : int {
+  S_FA = 0,    // forward fields, buffer A: vz vx szz sxx sxz
+  S_FB = 5,    // forward fields, buffer B
+  S_AA = 10,   // adjoint fields, buffer A
+  S_AB = 15,   // adjoint fields, buffer B
+  S_PSI_A = 20,  // memory of velocity derivatives: dvz_dz dvx_dx dvx_dz dvz_dx (buffer A)
+  S_PSI_B = 24,
+  S_PHI_A = 28,  // memory of stress derivatives: dszz_dz dsxz_dx dsxz_dz dsxx_dx (buffer A)
+  S_PHI_B = 32,
+  S_COUNT = 36
+};
+enum Field : int { F_VZ = 0, F_VX = 1, F_SZZ = 2, F_SXX = 3, F_SXZ = 4 };
+enum Psi : int { PSI_VZ_Z = 0, PSI_VX_X = 1, PSI_VX_Z = 2, PSI_VZ_X = 3 };
+enum Phi : int { PHI_SZZ_Z = 0, PHI_SXZ_X = 1, PHI_SXZ_Z = 2, PHI_SXX_X = 3 };
+// z / x profile rows inside the packed profile arrays
+enum Prof : int { PR_RK = 0, PR_A = 1, PR_B = 2, PR_RKH = 3, PR_AH = 4, PR_BH = 5, PR_COUNT = 6 };
+
+struct Grid {
+  int nz, nx, nPml, nPad, nSteps;
+  int P;               // column pitch
+  long long plane;     // floats per plane (incl. margins and slack)
+  long long origin;    // offset of (z=0,x=0) inside a plane allocation
+  int az_hi, ax_hi;    // last active cell: nz-nPad-3, nx-3 (first active = 2)
+  int zlo, zhi, xlo, xhi;  // inner box (reconstruction / imaging region)
+  int tiles_z, tiles_x;    // tile grid covering [0,nz) x [0,nx)
+  float dt, rdz, rdx;      // 1/dz, 1/dx
+  // boundary frames
+  int f_nzB;           // zhi-zlo+5
+  int f_len;           // floats per field per step
+};
+
+struct Model {
+  const float *lam, *mu, *amu, *bya, *byb;  // plane pointers
+};
+
+struct Profiles {
+  const float *z;  // [PR_COUNT][P]      index by z (valid for z < nz-nPad)
+  const float *x;  // [PR_COUNT][nxp]    index by x + XM
+  int nxp;
+};
+
+struct ShotTables {
+  const int *src_z, *src_x;     // [batch]
+  const float *stf;             // [batch][nSteps]  tapered source, float
+  const int *rec_ptr;           // [batch][ntiles+1] CSR over tiles
+  const int *rec_loc;           // [batch][nrp]  (lz | lx << 16) inside the tile
+  const int *rec_id;            // [batch][nrp]  receiver index
+  int nrp;                      // padded receiver count (row pitch of traces)
+};
+
+struct FwdArgs {
+  Grid g;
+  Model m;
+  Profiles pr;
+  ShotTables st;
+  float *state;        // [batch][S_COUNT][plane] (allocation base)
+  float *traces;       // [batch][nSteps][nrp]
+  float *frames;       // [batch][nSteps][5][f_len] or nullptr
+  int batch;
+  int it;              // time index of the state being advanced (it -> it+1)
+  int cur;             // 0: read buffer A, write B; 1: the reverse
+};
+
+struct BwdArgs {
+  Grid g;
+  Model m;
+  Profiles pr;
+  ShotTables st;
+  float *state;
+  const float *res;    // [batch][nSteps][nrp] tapered residual
+  const float *frames;
+  float *gacc;         // [batch][3][plane] gradient accumulators (lambda, mu, den)
+  float *stf_grad;     // [batch][nSteps]
+  int batch;
+  int it;
+  int cur_f;           // forward-field buffer holding state it+1
+  int cur_a;           // adjoint buffer holding the pre-update adjoint state
+};
+
+// one forward time step for `batch` shots: stress + source + velocity + record (+ frame save)
+void launch_forward_step(const FwdArgs &a, bool save_frames, cudaStream_t s);
+// reverse-time reconstruction it+1 -> it with frame restore + imaging condition
+void launch_reverse_imaging(const BwdArgs &a, cudaStream_t s);
+// adjoint step: source_grad, adjoint velocity, residual injection, adjoint stress
+void launch_adjoint_step(const BwdArgs &a, cudaStream_t s);
+
+// model preparation: double row-major MPa -> float planes (Pa), derived coefficients, max cp
+void launch_model_prep(const Grid &g, const double *d_lam, const double *d_mu, const double *d_den, float *lam,
+                       float *mu, float *den, float *amu, float *bya, float *byb, unsigned int *cpmax_bits,
+                       cudaStream_t s);
+
+// residual: taper obs & syn, res = obs - syn (t=0 -> 0), partial sums of res^2, taper res
+struct ResidualArgs {
+  const float *syn_tr;   // [nSteps][nrp]  raw synthetic (receiver fastest)
+  const float *obs_rt;   // [nrec][nSteps] observed (time fastest, file layout)
+  const float *w2;       // [nSteps] taper multipliers
+  float *res_tr;         // [nSteps][nrp]  tapered residual for injection
+  float *syn_rt;         // [nrec][nSteps] conditioned synthetic   (may be null)
+  float *res_rt;         // [nrec][nSteps] tapered residual        (may be null)
+  float *obs_cond_rt;    // [nrec][nSteps] conditioned observed    (may be null)
+  double *partial;       // [gridDim] block partial sums
+  int nrec, nrp, nSteps;
+};
+void launch_residual(const ResidualArgs &a, int *nblocks_out, cudaStream_t s);
+void launch_sum_partials(const double *partial, int n, float *out_j, cudaStream_t s);
+void launch_misfit(const float *j_shot, int n, float *misfit_half, cudaStream_t s);
+// traces [nSteps][nrp] -> [nrec][nSteps]
+void launch_traces_to_rt(const float *tr, float *rt, int nrec, int nrp, int nSteps, cudaStream_t s);
+
+// result = [gl|gm|gd|misfit] row-major [z][x] float: sums the per-slot accumulators
+void launch_finalize(const Grid &g, const float *gacc, int nslots, const float *misfit_half, float *result,
+                     cudaStream_t s);
+
+size_t forward_smem_bytes();
+size_t reverse_smem_bytes();
+size_t adjoint_smem_bytes();
+void configure_kernels();  // cudaFuncSetAttribute for dynamic smem
+
+}  // namespace fwi

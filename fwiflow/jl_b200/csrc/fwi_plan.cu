@@ -1,0 +1,812 @@
+// Plan object + C ABI of libfwi_b200.so (include/fwi_b200.h).
+//
+// Host orchestration of the FWI hot path: what `cufd()` does in the reference
+// (deps/CustomOps/FWI/Src/libCUFD.cu:34-580), re-organised around a reusable
+// device-resident plan: shots advance in batches (one launch per time step for the
+// whole batch), all buffers live for the life of the plan, results stay on the device
+// until asked for.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <list>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "fwi_host.hpp"
+#include "fwi_kernels.cuh"
+
+using namespace fwi;
+
+#define CUDA_OK(call)                                                                                   \
+  do {                                                                                                  \
+    cudaError_t e_ = (call);                                                                            \
+    if (e_ != cudaSuccess)                                                                              \
+      throw Error(FWI_B200_ERR_CUDA, std::string("CUDA: ") + cudaGetErrorString(e_) + " at " + __FILE__ + ":" + \
+                                         std::to_string(__LINE__) + " (" #call ")");                    \
+  } while (0)
+
+namespace {
+
+template <typename T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  void alloc(size_t count) {
+    if (count <= n && p) return;
+    release();
+    CUDA_OK(cudaMalloc(reinterpret_cast<void **>(&p), std::max<size_t>(count, 1) * sizeof(T)));
+    n = count;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  size_t bytes() const { return n * sizeof(T); }
+};
+
+}  // namespace
+
+struct fwi_b200_plan {
+  int gpu = 0;
+  Para para;
+  Survey survey;
+  Grid g{};
+  int group = 0, batch = 0, nrp = 0, max_nrec = 0, ntiles = 0;
+  std::vector<int> shot_ids;
+  cudaStream_t stream = nullptr;
+  std::mutex mu;  // one evaluation at a time per plan
+  long long launches = 0;
+  bool model_set = false, stf_set = false;
+  std::vector<char> obs_set;
+  int last_calc = -1;
+  int cur_f_last = 0;  // forward-field buffer holding the newest state of the last batch
+
+  // device memory
+  DevBuf<float> model;        // lam mu den amu bya byb planes
+  DevBuf<double> model_in;    // 3 * nz*nx staging of the caller's doubles
+  DevBuf<unsigned int> cpmax;
+  DevBuf<float> zprof, xprof, w2;
+  DevBuf<float> state, gacc, frames, syn_tr, res_tr;
+  DevBuf<float> obs_rt, syn_rt, res_rt, obs_cond_rt;  // [group][max_nrec*nSteps]
+  DevBuf<int> src_z, src_x, rec_ptr, rec_loc, rec_id;
+  DevBuf<float> stf, stf_grad, j_shot, misfit_half, result;
+  DevBuf<double> partial;
+  int partial_per_shot = 0;
+  size_t trace_stride = 0;  // max_nrec * nSteps
+
+  float *mplane(int k) { return model.p + (long long)k * g.plane; }
+
+  ~fwi_b200_plan() {
+    cudaSetDevice(gpu);
+    if (stream) cudaStreamSynchronize(stream);
+    model.release(); model_in.release(); cpmax.release(); zprof.release(); xprof.release(); w2.release();
+    state.release(); gacc.release(); frames.release(); syn_tr.release(); res_tr.release();
+    obs_rt.release(); syn_rt.release(); res_rt.release(); obs_cond_rt.release();
+    src_z.release(); src_x.release(); rec_ptr.release(); rec_loc.release(); rec_id.release();
+    stf.release(); stf_grad.release(); j_shot.release(); misfit_half.release(); result.release();
+    partial.release();
+    if (stream) cudaStreamDestroy(stream);
+  }
+};
+
+namespace {
+
+int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+void use_device(int gpu) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    throw Error(FWI_B200_ERR_CUDA, std::string("no usable CUDA device (") + cudaGetErrorString(e) +
+                                       "); libfwi_b200 has no CPU fallback");
+  if (gpu < 0 || gpu >= n) throw Error(FWI_B200_ERR_ARG, "gpu_id " + std::to_string(gpu) + " out of range");
+  CUDA_OK(cudaSetDevice(gpu));
+}
+
+void build_grid(const Para &p, Grid &g) {
+  g.nz = p.nz; g.nx = p.nx; g.nPml = p.nPml; g.nPad = p.nPad; g.nSteps = p.nSteps;
+  g.P = round_up(p.nz, 32);
+  g.plane = (long long)(p.nx + 2 * XM) * g.P + 2 * SLACK;
+  g.plane = (g.plane + 31) / 32 * 32;
+  g.origin = SLACK + (long long)XM * g.P;
+  g.az_hi = p.nz - p.nPad - 3;
+  g.ax_hi = p.nx - 3;
+  g.zlo = p.nPml; g.zhi = p.nz - p.nPad - 1 - p.nPml;
+  g.xlo = p.nPml; g.xhi = p.nx - 1 - p.nPml;
+  g.tiles_z = (p.nz + TILE_Z - 1) / TILE_Z;
+  g.tiles_x = (p.nx + TILE_X - 1) / TILE_X;
+  g.dt = p.dt;
+  g.rdz = (float)(1.0 / (double)p.dz);
+  g.rdx = (float)(1.0 / (double)p.dx);
+  g.f_nzB = g.zhi - g.zlo + 5;
+  g.f_len = 10 * g.f_nzB + 10 * std::max(0, g.xhi - g.xlo + 1 - 6);
+  if (g.zhi - g.zlo + 1 < 8 || g.xhi - g.xlo + 1 < 8)
+    throw Error(FWI_B200_ERR_GEOM, "grid too small: fewer than 8 cells between the PML layers");
+}
+
+void upload_profiles(fwi_b200_plan &pl) {
+  const Grid &g = pl.g;
+  const Para &p = pl.para;
+  CpmlProfiles hz = cpml_profiles(p.nz - p.nPad, p.nPml, p.dz, p.f0, p.dt);  // Cpml.cu:46-48
+  CpmlProfiles hx = cpml_profiles(p.nx, p.nPml, p.dx, p.f0, p.dt);           // Cpml.cu:50-52
+  const int nxp = p.nx + 2 * XM;
+  std::vector<float> z((size_t)PR_COUNT * g.P, 0.0f), x((size_t)PR_COUNT * nxp, 0.0f);
+  for (int i = 0; i < g.P; i++) { z[PR_RK * g.P + i] = 1.0f; z[PR_RKH * g.P + i] = 1.0f; z[PR_B * g.P + i] = 1.0f; z[PR_BH * g.P + i] = 1.0f; }
+  for (int i = 0; i < nxp; i++) { x[PR_RK * nxp + i] = 1.0f; x[PR_RKH * nxp + i] = 1.0f; x[PR_B * nxp + i] = 1.0f; x[PR_BH * nxp + i] = 1.0f; }
+  for (int i = 0; i < p.nz - p.nPad; i++) {
+    z[PR_RK * g.P + i] = 1.0f / hz.K[i];  z[PR_A * g.P + i] = hz.a[i];  z[PR_B * g.P + i] = hz.b[i];
+    z[PR_RKH * g.P + i] = 1.0f / hz.Kh[i]; z[PR_AH * g.P + i] = hz.ah[i]; z[PR_BH * g.P + i] = hz.bh[i];
+  }
+  for (int i = 0; i < p.nx; i++) {
+    x[PR_RK * nxp + i + XM] = 1.0f / hx.K[i];  x[PR_A * nxp + i + XM] = hx.a[i];  x[PR_B * nxp + i + XM] = hx.b[i];
+    x[PR_RKH * nxp + i + XM] = 1.0f / hx.Kh[i]; x[PR_AH * nxp + i + XM] = hx.ah[i]; x[PR_BH * nxp + i + XM] = hx.bh[i];
+  }
+  pl.zprof.alloc(z.size());
+  pl.xprof.alloc(x.size());
+  CUDA_OK(cudaMemcpy(pl.zprof.p, z.data(), z.size() * sizeof(float), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(pl.xprof.p, x.data(), x.size() * sizeof(float), cudaMemcpyHostToDevice));
+  std::vector<float> w2;
+  if (!taper_weights(p.nSteps, p.dt, 0.005f, w2)) w2.assign(p.nSteps, 1.0f);  // libCUFD.cu:63,268-270
+  pl.w2.alloc(w2.size());
+  CUDA_OK(cudaMemcpy(pl.w2.p, w2.data(), w2.size() * sizeof(float), cudaMemcpyHostToDevice));
+}
+
+// receiver tables: per shot, receivers sorted by owner tile (CSR) so that the tile that owns a
+// receiver cell records / injects it from shared memory.
+void upload_tables(fwi_b200_plan &pl) {
+  const Grid &g = pl.g;
+  const int G = pl.group;
+  pl.ntiles = g.tiles_z * g.tiles_x;
+  pl.max_nrec = 0;
+  for (const Shot &s : pl.survey.shots) pl.max_nrec = std::max<int>(pl.max_nrec, (int)s.z_rec.size());
+  pl.nrp = std::max(32, round_up(pl.max_nrec, 32));
+  std::vector<int> sz(G), sx(G), ptr((size_t)G * (pl.ntiles + 1), 0), loc((size_t)G * pl.nrp, 0), rid((size_t)G * pl.nrp, 0);
+  for (int i = 0; i < G; i++) {
+    const Shot &s = pl.survey.shots[i];
+    // the reference stamps a 9x9 patch around the source (utilities.cu:529-536): keep it inside the grid
+    if (s.z_src < 4 || s.z_src > g.nz - 5 || s.x_src < 4 || s.x_src > g.nx - 5)
+      throw Error(FWI_B200_ERR_GEOM, "shot" + std::to_string(s.id) + ": source outside the padded grid");
+    sz[i] = s.z_src;
+    sx[i] = s.x_src;
+    const int nrec = (int)s.z_rec.size();
+    std::vector<int> cnt(pl.ntiles + 1, 0);
+    std::vector<int> tile_of(nrec);
+    for (int r = 0; r < nrec; r++) {
+      const int z = s.z_rec[r], x = s.x_rec[r];
+      if (z < 0 || z >= g.nz || x < 0 || x >= g.nx)
+        throw Error(FWI_B200_ERR_GEOM, "shot" + std::to_string(s.id) + ": receiver " + std::to_string(r) +
+                                           " outside the padded grid");
+      tile_of[r] = (x / TILE_X) * g.tiles_z + (z / TILE_Z);
+      cnt[tile_of[r] + 1]++;
+    }
+    for (int t = 0; t < pl.ntiles; t++) cnt[t + 1] += cnt[t];
+    int *p = ptr.data() + (size_t)i * (pl.ntiles + 1);
+    std::copy(cnt.begin(), cnt.end(), p);
+    std::vector<int> fill(cnt.begin(), cnt.end() - 1);
+    for (int r = 0; r < nrec; r++) {  // stable: receivers of a tile keep their file order
+      const int k = fill[tile_of[r]]++;
+      loc[(size_t)i * pl.nrp + k] = (s.z_rec[r] % TILE_Z) | ((s.x_rec[r] % TILE_X) << 16);
+      rid[(size_t)i * pl.nrp + k] = r;
+    }
+  }
+  pl.src_z.alloc(G); pl.src_x.alloc(G); pl.rec_ptr.alloc(ptr.size()); pl.rec_loc.alloc(loc.size()); pl.rec_id.alloc(rid.size());
+  CUDA_OK(cudaMemcpy(pl.src_z.p, sz.data(), G * sizeof(int), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(pl.src_x.p, sx.data(), G * sizeof(int), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(pl.rec_ptr.p, ptr.data(), ptr.size() * sizeof(int), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(pl.rec_loc.p, loc.data(), loc.size() * sizeof(int), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(pl.rec_id.p, rid.data(), rid.size() * sizeof(int), cudaMemcpyHostToDevice));
+}
+
+size_t per_shot_bytes(const fwi_b200_plan &pl, bool with_frames) {
+  const Grid &g = pl.g;
+  size_t b = (size_t)(S_COUNT + 3) * g.plane * sizeof(float);
+  b += (size_t)2 * g.nSteps * pl.nrp * sizeof(float);
+  if (with_frames) b += (size_t)5 * g.f_len * g.nSteps * sizeof(float);
+  return b;
+}
+
+void choose_batch(fwi_b200_plan &pl, int max_batch) {
+  size_t free_b = 0, total_b = 0;
+  CUDA_OK(cudaMemGetInfo(&free_b, &total_b));
+  // traces of the whole group (obs + syn) stay resident as well
+  const size_t resident = (size_t)2 * pl.group * pl.trace_stride * sizeof(float) + (size_t)8 * pl.g.plane * sizeof(float);
+  const size_t budget = free_b > resident ? (size_t)((free_b - resident) * 0.85) : 0;
+  size_t fit = budget / per_shot_bytes(pl, true);
+  if (fit < 1) throw Error(FWI_B200_ERR_CUDA, "not enough device memory for one shot (incl. boundary frames)");
+  int b = (int)std::min<size_t>(fit, (size_t)pl.group);
+  // enough tiles to fill the machine, no more: beyond ~64 concurrent shots nothing is gained
+  b = std::min(b, 64);
+  if (max_batch > 0) b = std::min(b, max_batch);
+  pl.batch = std::max(1, b);
+}
+
+void alloc_run_buffers(fwi_b200_plan &pl, int calc_id) {
+  const Grid &g = pl.g;
+  pl.state.alloc((size_t)pl.batch * S_COUNT * g.plane);
+  pl.syn_tr.alloc((size_t)pl.batch * g.nSteps * pl.nrp);
+  if (calc_id != 2) {
+    pl.res_tr.alloc((size_t)pl.batch * g.nSteps * pl.nrp);
+    const int nb = ((g.nSteps + 31) / 32) * ((pl.max_nrec + 31) / 32);
+    pl.partial_per_shot = nb;
+    pl.partial.alloc((size_t)pl.batch * nb);
+  }
+  if (calc_id == 1) {
+    pl.gacc.alloc((size_t)pl.batch * 3 * g.plane);
+    pl.frames.alloc((size_t)pl.batch * g.nSteps * 5 * g.f_len);
+  }
+  if (calc_id == 2 || pl.para.save_scratch) pl.syn_rt.alloc((size_t)pl.group * pl.trace_stride);
+  if (pl.para.save_scratch && calc_id == 1) {
+    pl.res_rt.alloc((size_t)pl.group * pl.trace_stride);
+    pl.obs_cond_rt.alloc((size_t)pl.group * pl.trace_stride);
+  }
+}
+
+ShotTables tables_for(fwi_b200_plan &pl, int first) {
+  ShotTables st;
+  st.src_z = pl.src_z.p + first;
+  st.src_x = pl.src_x.p + first;
+  st.stf = pl.stf.p + (size_t)first * pl.g.nSteps;
+  st.rec_ptr = pl.rec_ptr.p + (size_t)first * (pl.ntiles + 1);
+  st.rec_loc = pl.rec_loc.p + (size_t)first * pl.nrp;
+  st.rec_id = pl.rec_id.p + (size_t)first * pl.nrp;
+  st.nrp = pl.nrp;
+  return st;
+}
+
+Model model_of(fwi_b200_plan &pl) {
+  Model m;
+  m.lam = pl.mplane(0) + pl.g.origin;
+  m.mu = pl.mplane(1) + pl.g.origin;
+  m.amu = pl.mplane(3) + pl.g.origin;
+  m.bya = pl.mplane(4) + pl.g.origin;
+  m.byb = pl.mplane(5) + pl.g.origin;
+  return m;
+}
+
+void run_locked(fwi_b200_plan &pl, int calc_id, cudaStream_t s) {
+  const Grid &g = pl.g;
+  if (calc_id < 0 || calc_id > 2) throw Error(FWI_B200_ERR_ARG, "invalid calc_id " + std::to_string(calc_id));
+  if (!pl.model_set) throw Error(FWI_B200_ERR_ARG, "plan: model not set");
+  if (!pl.stf_set) throw Error(FWI_B200_ERR_ARG, "plan: source time functions not set");
+  if (calc_id != 2)
+    for (int i = 0; i < pl.group; i++)
+      if (!pl.obs_set[i]) throw Error(FWI_B200_ERR_ARG, "plan: observed data of shot " + std::to_string(pl.shot_ids[i]) + " not set");
+  alloc_run_buffers(pl, calc_id);
+  const bool if_res = calc_id != 2, with_adj = calc_id == 1;
+  Model m = model_of(pl);
+  FwdArgs fa{};
+  fa.g = g; fa.m = m;
+  fa.pr.z = pl.zprof.p; fa.pr.x = pl.xprof.p; fa.pr.nxp = g.nx + 2 * XM;
+  BwdArgs ba{};
+  ba.g = g; ba.m = m; ba.pr = fa.pr;
+
+  if (with_adj) {
+    CUDA_OK(cudaMemsetAsync(pl.gacc.p, 0, pl.gacc.bytes(), s));
+    CUDA_OK(cudaMemsetAsync(pl.stf_grad.p, 0, pl.stf_grad.bytes(), s));
+  }
+  if (if_res) CUDA_OK(cudaMemsetAsync(pl.j_shot.p, 0, pl.j_shot.bytes(), s));
+  const int N = g.nSteps;
+  for (int first = 0; first < pl.group; first += pl.batch) {
+    const int nb = std::min(pl.batch, pl.group - first);
+    ShotTables st = tables_for(pl, first);
+    // libCUFD.cu:163-187: zero wavefields, CPML memory and the synthetic traces
+    CUDA_OK(cudaMemsetAsync(pl.state.p, 0, (size_t)nb * S_COUNT * g.plane * sizeof(float), s));
+    CUDA_OK(cudaMemsetAsync(pl.syn_tr.p, 0, (size_t)nb * N * pl.nrp * sizeof(float), s));
+    fa.st = st; fa.state = pl.state.p; fa.traces = pl.syn_tr.p; fa.frames = with_adj ? pl.frames.p : nullptr; fa.batch = nb;
+    for (int it = 0; it <= N - 2; it++) {  // libCUFD.cu:202-240
+      fa.it = it; fa.cur = it & 1;
+      launch_forward_step(fa, with_adj, s);
+      pl.launches++;
+    }
+    int cur_f = (N - 1) & 1;
+    pl.cur_f_last = cur_f;
+    if (!if_res) {
+      for (int k = 0; k < nb; k++) {
+        const int nrec = (int)pl.survey.shots[first + k].z_rec.size();
+        launch_traces_to_rt(pl.syn_tr.p + (size_t)k * N * pl.nrp, pl.syn_rt.p + (size_t)(first + k) * pl.trace_stride, nrec, pl.nrp, N, s);
+        pl.launches++;
+      }
+      continue;
+    }
+    // residual + misfit: libCUFD.cu:254-330
+    for (int k = 0; k < nb; k++) {
+      const int nrec = (int)pl.survey.shots[first + k].z_rec.size();
+      ResidualArgs ra{};
+      ra.syn_tr = pl.syn_tr.p + (size_t)k * N * pl.nrp;
+      ra.obs_rt = pl.obs_rt.p + (size_t)(first + k) * pl.trace_stride;
+      ra.w2 = pl.w2.p;
+      ra.res_tr = pl.res_tr.p + (size_t)k * N * pl.nrp;
+      const bool keep = pl.para.save_scratch && with_adj;
+      ra.syn_rt = keep ? pl.syn_rt.p + (size_t)(first + k) * pl.trace_stride : nullptr;
+      ra.res_rt = keep ? pl.res_rt.p + (size_t)(first + k) * pl.trace_stride : nullptr;
+      ra.obs_cond_rt = keep ? pl.obs_cond_rt.p + (size_t)(first + k) * pl.trace_stride : nullptr;
+      ra.partial = pl.partial.p + (size_t)k * pl.partial_per_shot;
+      ra.nrec = nrec; ra.nrp = pl.nrp; ra.nSteps = N;
+      if (nrec > 0) {
+        CUDA_OK(cudaMemsetAsync(ra.res_tr, 0, (size_t)N * pl.nrp * sizeof(float), s));
+        int nblk = 0;
+        launch_residual(ra, &nblk, s);
+        launch_sum_partials(ra.partial, nblk, pl.j_shot.p + first + k, s);
+        pl.launches += 2;
+      }
+    }
+    if (!with_adj) continue;
+    // backward: libCUFD.cu:334-457
+    CUDA_OK(cudaMemset2DAsync(pl.state.p + (size_t)S_AA * g.plane, (size_t)S_COUNT * g.plane * sizeof(float), 0,
+                              (size_t)(S_COUNT - S_AA) * g.plane * sizeof(float), nb, s));
+    ba.st = st; ba.state = pl.state.p; ba.res = pl.res_tr.p; ba.frames = pl.frames.p; ba.gacc = pl.gacc.p;
+    ba.stf_grad = pl.stf_grad.p + (size_t)first * N; ba.batch = nb;
+    int cur_a = 0;
+    ba.it = N - 1; ba.cur_f = cur_f; ba.cur_a = cur_a;   // priming: libCUFD.cu:353-373
+    launch_adjoint_step(ba, s);
+    pl.launches++;
+    cur_a ^= 1;
+    for (int it = N - 2; it >= 0; it--) {  // libCUFD.cu:374-445
+      ba.it = it; ba.cur_f = cur_f; ba.cur_a = cur_a;
+      launch_reverse_imaging(ba, s);
+      pl.launches++;
+      // (at it == 0 only the source_grad part of this launch is observable; kept for grad_stf[0])
+      launch_adjoint_step(ba, s);
+      pl.launches++;
+      cur_f ^= 1;
+      cur_a ^= 1;
+    }
+    pl.cur_f_last = cur_f;
+  }
+  if (if_res) {
+    launch_misfit(pl.j_shot.p, pl.group, pl.misfit_half.p, s);
+    pl.launches++;
+  }
+  if (with_adj) {
+    launch_finalize(g, pl.gacc.p, std::min(pl.batch, pl.group), pl.misfit_half.p, pl.result.p, s);
+    pl.launches++;
+  } else if (if_res) {
+    CUDA_OK(cudaMemcpyAsync(pl.result.p + 3LL * g.nz * g.nx, pl.misfit_half.p, sizeof(float), cudaMemcpyDeviceToDevice, s));
+  }
+  CUDA_OK(cudaGetLastError());
+  pl.last_calc = calc_id;
+}
+
+template <typename F>
+int guarded(F &&f) {
+  try {
+    set_last_error("");
+    f();
+    return FWI_B200_OK;
+  } catch (const Error &e) {
+    set_last_error(e.what());
+    return e.code;
+  } catch (const std::exception &e) {
+    set_last_error(e.what());
+    return FWI_B200_ERR_ARG;
+  }
+}
+
+}  // namespace
+
+// =================================================================================================
+// plan API
+// =================================================================================================
+extern "C" int fwi_b200_plan_create(fwi_b200_plan **out, const char *para_fname, int gpu_id, int group_size,
+                                    const int *shot_ids, int max_batch) {
+  return guarded([&] {
+    if (!out || !para_fname || group_size <= 0 || !shot_ids) throw Error(FWI_B200_ERR_ARG, "plan_create: bad arguments");
+    *out = nullptr;
+    std::unique_ptr<fwi_b200_plan> pl(new fwi_b200_plan());
+    pl->para = read_para(para_fname);
+    pl->survey = read_survey(pl->para.survey_fname, pl->para.nPml, group_size, shot_ids);
+    pl->group = group_size;
+    pl->shot_ids.assign(shot_ids, shot_ids + group_size);
+    pl->obs_set.assign(group_size, 0);
+    build_grid(pl->para, pl->g);
+    use_device(gpu_id);
+    pl->gpu = gpu_id;
+    configure_kernels();
+    CUDA_OK(cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking));
+    const Grid &g = pl->g;
+    pl->model.alloc((size_t)6 * g.plane);
+    CUDA_OK(cudaMemset(pl->model.p, 0, pl->model.bytes()));
+    pl->model_in.alloc((size_t)3 * g.nz * g.nx);
+    pl->cpmax.alloc(1);
+    upload_profiles(*pl);
+    upload_tables(*pl);
+    pl->trace_stride = (size_t)pl->max_nrec * g.nSteps;
+    pl->stf.alloc((size_t)group_size * g.nSteps);
+    pl->stf_grad.alloc((size_t)group_size * g.nSteps);
+    pl->j_shot.alloc(group_size);
+    pl->misfit_half.alloc(1);
+    pl->result.alloc((size_t)3 * g.nz * g.nx + 1);
+    CUDA_OK(cudaMemset(pl->result.p, 0, pl->result.bytes()));
+    CUDA_OK(cudaMemset(pl->misfit_half.p, 0, sizeof(float)));
+    CUDA_OK(cudaMemset(pl->stf_grad.p, 0, pl->stf_grad.bytes()));
+    choose_batch(*pl, max_batch);
+    *out = pl.release();
+  });
+}
+
+extern "C" void fwi_b200_plan_destroy(fwi_b200_plan *plan) { delete plan; }
+
+extern "C" int fwi_b200_plan_set_model(fwi_b200_plan *pl, const double *Lambda, const double *Mu, const double *Den) {
+  return guarded([&] {
+    if (!pl || !Lambda || !Mu || !Den) throw Error(FWI_B200_ERR_ARG, "set_model: null pointer");
+    std::lock_guard<std::mutex> lk(pl->mu);
+    use_device(pl->gpu);
+    const Grid &g = pl->g;
+    const size_t n = (size_t)g.nz * g.nx;
+    cudaStream_t s = pl->stream;
+    CUDA_OK(cudaMemcpyAsync(pl->model_in.p, Lambda, n * sizeof(double), cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaMemcpyAsync(pl->model_in.p + n, Mu, n * sizeof(double), cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaMemcpyAsync(pl->model_in.p + 2 * n, Den, n * sizeof(double), cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaMemsetAsync(pl->cpmax.p, 0, sizeof(unsigned int), s));
+    launch_model_prep(g, pl->model_in.p, pl->model_in.p + n, pl->model_in.p + 2 * n, pl->mplane(0), pl->mplane(1),
+                      pl->mplane(2), pl->mplane(3), pl->mplane(4), pl->mplane(5), pl->cpmax.p, s);
+    pl->launches += 2;
+    unsigned int bits = 0;
+    CUDA_OK(cudaMemcpyAsync(&bits, pl->cpmax.p, sizeof(bits), cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaStreamSynchronize(s));
+    float cpmax;
+    std::memcpy(&cpmax, &bits, sizeof(float));
+    const float cn = courant_number(cpmax, pl->para.dt, pl->para.dz, pl->para.dx);
+    pl->model_set = false;
+    if (cn > 1.0f)  // utilities.cu:239 exits silently; we report
+      throw Error(FWI_B200_ERR_CFL, "Courant number " + std::to_string(cn) + " > 1 (max cp " + std::to_string(cpmax) + ")");
+    pl->model_set = true;
+  });
+}
+
+extern "C" int fwi_b200_plan_set_stf(fwi_b200_plan *pl, const double *stf) {
+  return guarded([&] {
+    if (!pl || !stf) throw Error(FWI_B200_ERR_ARG, "set_stf: null pointer");
+    std::lock_guard<std::mutex> lk(pl->mu);
+    use_device(pl->gpu);
+    const int N = pl->g.nSteps;
+    std::vector<float> w2;
+    const bool ok = taper_weights(N, pl->para.dt, 0.001f, w2);  // Src_Rec.cu:140
+    std::vector<float> h((size_t)pl->group * N);
+    for (int i = 0; i < pl->group; i++) {
+      if (pl->shot_ids[i] < 0) throw Error(FWI_B200_ERR_ARG, "negative shot id");
+      const double *row = stf + (size_t)pl->shot_ids[i] * N;  // row = GLOBAL shot id (Src_Rec.cu:135)
+      for (int t = 0; t < N; t++) {
+        float v = (float)row[t];
+        if (ok) v *= w2[t];
+        h[(size_t)i * N + t] = v;
+      }
+    }
+    CUDA_OK(cudaMemcpyAsync(pl->stf.p, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice, pl->stream));
+    CUDA_OK(cudaStreamSynchronize(pl->stream));
+    pl->stf_set = true;
+  });
+}
+
+extern "C" int fwi_b200_plan_set_obs(fwi_b200_plan *pl, int ishot, const float *obs) {
+  return guarded([&] {
+    if (!pl || !obs || ishot < 0 || ishot >= pl->group) throw Error(FWI_B200_ERR_ARG, "set_obs: bad arguments");
+    std::lock_guard<std::mutex> lk(pl->mu);
+    use_device(pl->gpu);
+    pl->obs_rt.alloc((size_t)pl->group * pl->trace_stride);
+    const size_t n = pl->survey.shots[ishot].z_rec.size() * (size_t)pl->g.nSteps;
+    CUDA_OK(cudaMemcpyAsync(pl->obs_rt.p + (size_t)ishot * pl->trace_stride, obs, n * sizeof(float), cudaMemcpyHostToDevice, pl->stream));
+    CUDA_OK(cudaStreamSynchronize(pl->stream));
+    pl->obs_set[ishot] = 1;
+  });
+}
+
+extern "C" int fwi_b200_plan_load_obs_files(fwi_b200_plan *pl) {
+  return guarded([&] {
+    if (!pl) throw Error(FWI_B200_ERR_ARG, "load_obs_files: null plan");
+    std::lock_guard<std::mutex> lk(pl->mu);
+    use_device(pl->gpu);
+    pl->obs_rt.alloc((size_t)pl->group * pl->trace_stride);
+    std::vector<float> h(pl->trace_stride);
+    for (int i = 0; i < pl->group; i++) {
+      const size_t n = pl->survey.shots[i].z_rec.size() * (size_t)pl->g.nSteps;
+      read_f32(pl->para.data_dir_name + "/Shot" + std::to_string(pl->shot_ids[i]) + ".bin", h.data(), n);
+      CUDA_OK(cudaMemcpyAsync(pl->obs_rt.p + (size_t)i * pl->trace_stride, h.data(), n * sizeof(float), cudaMemcpyHostToDevice, pl->stream));
+      CUDA_OK(cudaStreamSynchronize(pl->stream));
+      pl->obs_set[i] = 1;
+    }
+  });
+}
+
+extern "C" int fwi_b200_plan_run(fwi_b200_plan *pl, int calc_id, void *stream, int sync) {
+  return guarded([&] {
+    if (!pl) throw Error(FWI_B200_ERR_ARG, "run: null plan");
+    std::lock_guard<std::mutex> lk(pl->mu);
+    use_device(pl->gpu);
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : pl->stream;
+    run_locked(*pl, calc_id, s);
+    if (sync) CUDA_OK(cudaStreamSynchronize(s));
+  });
+}
+
+extern "C" float *fwi_b200_plan_result_device(fwi_b200_plan *pl) { return pl ? pl->result.p : nullptr; }
+extern "C" size_t fwi_b200_plan_result_count(fwi_b200_plan *pl) { return pl ? (size_t)3 * pl->g.nz * pl->g.nx + 1 : 0; }
+
+extern "C" int fwi_b200_plan_get_result(fwi_b200_plan *pl, double *misfit, double *gl, double *gm, double *gd, double *gs) {
+  return guarded([&] {
+    if (!pl) throw Error(FWI_B200_ERR_ARG, "get_result: null plan");
+    std::lock_guard<std::mutex> lk(pl->mu);
+    use_device(pl->gpu);
+    CUDA_OK(cudaDeviceSynchronize());
+    const size_t n = (size_t)pl->g.nz * pl->g.nx;
+    if (gl || gm || gd) {
+      std::vector<float> h(3 * n + 1);
+      CUDA_OK(cudaMemcpy(h.data(), pl->result.p, h.size() * sizeof(float), cudaMemcpyDeviceToHost));
+      if (gl) for (size_t i = 0; i < n; i++) gl[i] = h[i];
+      if (gm) for (size_t i = 0; i < n; i++) gm[i] = h[n + i];
+      if (gd) for (size_t i = 0; i < n; i++) gd[i] = h[2 * n + i];
+      if (misfit) *misfit = h[3 * n];
+    } else if (misfit) {
+      float m = 0;
+      CUDA_OK(cudaMemcpy(&m, pl->result.p + 3 * n, sizeof(float), cudaMemcpyDeviceToHost));
+      *misfit = m;
+    }
+    if (gs) {
+      std::vector<float> h((size_t)pl->group * pl->g.nSteps);
+      CUDA_OK(cudaMemcpy(h.data(), pl->stf_grad.p, h.size() * sizeof(float), cudaMemcpyDeviceToHost));
+      for (size_t i = 0; i < h.size(); i++) gs[i] = h[i];
+    }
+  });
+}
+
+extern "C" int fwi_b200_plan_get_traces(fwi_b200_plan *pl, int ishot, int which, float *out) {
+  return guarded([&] {
+    if (!pl || !out || ishot < 0 || ishot >= pl->group) throw Error(FWI_B200_ERR_ARG, "get_traces: bad arguments");
+    std::lock_guard<std::mutex> lk(pl->mu);
+    use_device(pl->gpu);
+    CUDA_OK(cudaDeviceSynchronize());
+    DevBuf<float> *src = which == 0 ? &pl->syn_rt : which == 1 ? &pl->res_rt : which == 2 ? &pl->obs_cond_rt : nullptr;
+    if (!src || !src->p) throw Error(FWI_B200_ERR_ARG, "get_traces: these traces were not kept by the last run");
+    const size_t n = pl->survey.shots[ishot].z_rec.size() * (size_t)pl->g.nSteps;
+    CUDA_OK(cudaMemcpy(out, src->p + (size_t)ishot * pl->trace_stride, n * sizeof(float), cudaMemcpyDeviceToHost));
+  });
+}
+
+static void write_group_files(fwi_b200_plan *pl, DevBuf<float> &buf, const std::string &dir, const std::string &stem) {
+  std::vector<float> h(pl->trace_stride);
+  for (int i = 0; i < pl->group; i++) {
+    const size_t n = pl->survey.shots[i].z_rec.size() * (size_t)pl->g.nSteps;
+    CUDA_OK(cudaMemcpy(h.data(), buf.p + (size_t)i * pl->trace_stride, n * sizeof(float), cudaMemcpyDeviceToHost));
+    write_f32(dir + "/" + stem + std::to_string(pl->shot_ids[i]) + ".bin", h.data(), n);
+  }
+}
+
+extern "C" int fwi_b200_plan_write_obs_files(fwi_b200_plan *pl) {
+  return guarded([&] {
+    if (!pl) throw Error(FWI_B200_ERR_ARG, "write_obs_files: null plan");
+    std::lock_guard<std::mutex> lk(pl->mu);
+    use_device(pl->gpu);
+    CUDA_OK(cudaDeviceSynchronize());
+    if (pl->last_calc != 2 || !pl->syn_rt.p) throw Error(FWI_B200_ERR_ARG, "write_obs_files: last run was not calc_id 2");
+    write_group_files(pl, pl->syn_rt, pl->para.data_dir_name, "Shot");  // libCUFD.cu:514-521
+  });
+}
+
+extern "C" int fwi_b200_plan_info(fwi_b200_plan *pl, int *nz, int *nx, int *nSteps, int *nPml, int *nPad, int *group_size,
+                                  int *batch, int *max_nrec) {
+  if (!pl) return FWI_B200_ERR_ARG;
+  if (nz) *nz = pl->g.nz;
+  if (nx) *nx = pl->g.nx;
+  if (nSteps) *nSteps = pl->g.nSteps;
+  if (nPml) *nPml = pl->g.nPml;
+  if (nPad) *nPad = pl->g.nPad;
+  if (group_size) *group_size = pl->group;
+  if (batch) *batch = pl->batch;
+  if (max_nrec) *max_nrec = pl->max_nrec;
+  return FWI_B200_OK;
+}
+
+extern "C" int fwi_b200_plan_shot_geometry(fwi_b200_plan *pl, int ishot, int *z_src, int *x_src, int *nrec, int *z_rec, int *x_rec) {
+  if (!pl || ishot < 0 || ishot >= pl->group) return FWI_B200_ERR_ARG;
+  const Shot &s = pl->survey.shots[ishot];
+  if (z_src) *z_src = s.z_src;
+  if (x_src) *x_src = s.x_src;
+  if (nrec) *nrec = (int)s.z_rec.size();
+  if (z_rec) std::copy(s.z_rec.begin(), s.z_rec.end(), z_rec);
+  if (x_rec) std::copy(s.x_rec.begin(), s.x_rec.end(), x_rec);
+  return FWI_B200_OK;
+}
+
+extern "C" long long fwi_b200_plan_launch_count(fwi_b200_plan *pl) { return pl ? pl->launches : 0; }
+
+extern "C" int fwi_b200_plan_get_field(fwi_b200_plan *pl, int ishot, int field, float *out) {
+  return guarded([&] {
+    if (!pl || !out || field < 0 || field > 4 || ishot < 0 || ishot >= pl->batch) throw Error(FWI_B200_ERR_ARG, "get_field: bad arguments");
+    std::lock_guard<std::mutex> lk(pl->mu);
+    use_device(pl->gpu);
+    CUDA_OK(cudaDeviceSynchronize());
+    const Grid &g = pl->g;
+    std::vector<float> h((size_t)g.plane);
+    const int slot = (pl->cur_f_last ? S_FB : S_FA) + field;
+    CUDA_OK(cudaMemcpy(h.data(), pl->state.p + ((size_t)ishot * S_COUNT + slot) * g.plane, h.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    for (int z = 0; z < g.nz; z++)
+      for (int x = 0; x < g.nx; x++) out[(size_t)z * g.nx + x] = h[g.origin + (size_t)x * g.P + z];
+  });
+}
+
+extern "C" int fwi_b200_plan_time_kernel(fwi_b200_plan *pl, int which, int iters, void *stream, float *ms_per_launch,
+                                         double *alg_bytes) {
+  return guarded([&] {
+    if (!pl || iters <= 0 || which < 0 || which > 3) throw Error(FWI_B200_ERR_ARG, "time_kernel: bad arguments");
+    std::lock_guard<std::mutex> lk(pl->mu);
+    use_device(pl->gpu);
+    const Grid &g = pl->g;
+    alloc_run_buffers(*pl, 1);
+    if (!pl->obs_rt.p) pl->obs_rt.alloc((size_t)pl->group * pl->trace_stride);
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : pl->stream;
+    const int nb = std::min(pl->batch, pl->group);
+    FwdArgs fa{};
+    fa.g = g; fa.m = model_of(*pl);
+    fa.pr.z = pl->zprof.p; fa.pr.x = pl->xprof.p; fa.pr.nxp = g.nx + 2 * XM;
+    fa.st = tables_for(*pl, 0); fa.state = pl->state.p; fa.traces = pl->syn_tr.p; fa.frames = pl->frames.p; fa.batch = nb;
+    BwdArgs ba{};
+    ba.g = g; ba.m = fa.m; ba.pr = fa.pr; ba.st = fa.st; ba.state = pl->state.p; ba.res = pl->res_tr.p;
+    ba.frames = pl->frames.p; ba.gacc = pl->gacc.p; ba.stf_grad = pl->stf_grad.p; ba.batch = nb;
+    cudaEvent_t e0, e1;
+    CUDA_OK(cudaEventCreate(&e0));
+    CUDA_OK(cudaEventCreate(&e1));
+    auto one = [&](int k) {
+      const int it = 1 + (k % std::max(1, g.nSteps - 3));
+      if (which <= 1) { fa.it = it; fa.cur = k & 1; launch_forward_step(fa, which == 1, s); }
+      else if (which == 2) { ba.it = it; ba.cur_f = k & 1; ba.cur_a = 0; launch_reverse_imaging(ba, s); }
+      else { ba.it = it; ba.cur_f = 0; ba.cur_a = k & 1; launch_adjoint_step(ba, s); }
+    };
+    for (int k = 0; k < 3; k++) one(k);
+    CUDA_OK(cudaEventRecord(e0, s));
+    for (int k = 0; k < iters; k++) one(k);
+    CUDA_OK(cudaEventRecord(e1, s));
+    CUDA_OK(cudaEventSynchronize(e1));
+    pl->launches += iters + 3;
+    float ms = 0;
+    CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (ms_per_launch) *ms_per_launch = ms / iters;
+    if (alg_bytes) {
+      // algorithmic bytes per cell-update
+      const double cells = (double)g.nz * g.nx * nb;
+      const double box = (double)(g.zhi - g.zlo + 1) * (g.xhi - g.xlo + 1) * nb;
+      const double fz = 2.0 * g.nPml / g.nz, fx = 2.0 * g.nPml / g.nx;
+      double b = 0;
+      if (which <= 1) b = cells * (60.0 + 32.0 * (fz + fx));
+      else if (which == 2) b = box * 104.0;        // 10 R + 5 W state, 5 coeff, 3 R+W gradients
+      else b = cells * (60.0 + 64.0 * (fz + fx));  // 5 R + 5 W adjoint state, 5 coeff, psi/phi in the strips
+      if (which == 1) b += (double)nb * 5 * g.f_len * 4.0;
+      *alg_bytes = b;
+    }
+  });
+}
+
+extern "C" const char *fwi_b200_version(void) {
+  return "{\"name\":\"fwi_b200\",\"abi\":1,\"arch\":\"sm_100a\",\"tile\":[64,32],\"fp64_promote\":true}";
+}
+
+extern "C" const char *fwi_b200_last_error(void) { return last_error_cstr(); }
+
+// =================================================================================================
+// reference-compatible host-buffer entry points, on top of a small plan cache
+// =================================================================================================
+namespace {
+
+struct CacheEntry {
+  int gpu;
+  std::string key;
+  std::unique_ptr<fwi_b200_plan> plan;
+};
+std::mutex g_cache_mu;
+std::list<CacheEntry> g_cache;
+constexpr size_t kCacheMax = 4;
+
+std::string cache_key(const char *para_fname, const Para &p, const std::string &survey_text, int group, const int *ids) {
+  std::string k = std::string(para_fname) + "\n" + p.text + "\n" + survey_text + "\n";
+  for (int i = 0; i < group; i++) k += std::to_string(ids[i]) + ",";
+  return k;
+}
+
+fwi_b200_plan *cached_plan(const char *para_fname, int gpu, int group, const int *ids) {
+  Para p = read_para(para_fname);
+  std::string survey_text;
+  {
+    FILE *fp = std::fopen(p.survey_fname.c_str(), "rb");
+    if (!fp) throw Error(FWI_B200_ERR_IO, "cannot open survey file '" + p.survey_fname + "'");
+    char buf[1 << 16];
+    size_t n;
+    while ((n = std::fread(buf, 1, sizeof buf, fp)) > 0) survey_text.append(buf, n);
+    std::fclose(fp);
+  }
+  const std::string key = cache_key(para_fname, p, survey_text, group, ids);
+  std::lock_guard<std::mutex> lk(g_cache_mu);
+  for (auto it = g_cache.begin(); it != g_cache.end(); ++it)
+    if (it->gpu == gpu && it->key == key) {
+      g_cache.splice(g_cache.begin(), g_cache, it);
+      return g_cache.front().plan.get();
+    }
+  while (g_cache.size() >= kCacheMax) g_cache.pop_back();
+  fwi_b200_plan *raw = nullptr;
+  int rc = fwi_b200_plan_create(&raw, para_fname, gpu, group, ids, 0);
+  if (rc != FWI_B200_OK) throw Error(rc, last_error_cstr());
+  g_cache.push_front(CacheEntry{gpu, key, std::unique_ptr<fwi_b200_plan>(raw)});
+  return raw;
+}
+
+void check(int rc) {
+  if (rc != FWI_B200_OK) throw Error(rc, last_error_cstr());
+}
+
+int host_call(double *misfit, double *gl, double *gm, double *gd, double *gs, const double *Lambda, const double *Mu,
+              const double *Den, const double *stf, int calc_id, bool also_misfit, int gpu_id, int group_size,
+              const int *shot_ids, const char *para_fname) {
+  return guarded([&] {
+    if (calc_id < 0 || calc_id > 2) throw Error(FWI_B200_ERR_ARG, "Invalid calc_id " + std::to_string(calc_id));
+    if (!Lambda || !Mu || !Den || !stf || !shot_ids || !para_fname || group_size <= 0)
+      throw Error(FWI_B200_ERR_ARG, "cufd: null input");
+    if (calc_id == 1 && !(gl && gm && gd && gs) && !also_misfit)
+      throw Error(FWI_B200_ERR_ARG, "cufd: calc_id 1 needs the four gradient outputs");
+    fwi_b200_plan *pl = cached_plan(para_fname, gpu_id, group_size, shot_ids);
+    check(fwi_b200_plan_set_model(pl, Lambda, Mu, Den));
+    check(fwi_b200_plan_set_stf(pl, stf));
+    if (calc_id != 2) check(fwi_b200_plan_load_obs_files(pl));
+    check(fwi_b200_plan_run(pl, calc_id, nullptr, 1));
+    if (calc_id == 2) {
+      check(fwi_b200_plan_write_obs_files(pl));
+      if (misfit) *misfit = 0.0;  // FwiOp.cpp:316
+    } else if (calc_id == 0) {
+      check(fwi_b200_plan_get_result(pl, misfit, nullptr, nullptr, nullptr, nullptr));
+    } else {
+      // the reference never writes *misfit for calc_id 1 (libCUFD.cu:528); the fused entry point does
+      check(fwi_b200_plan_get_result(pl, also_misfit ? misfit : nullptr, gl, gm, gd, gs));
+      if (pl->para.save_scratch) {  // libCUFD.cu:493-511
+        std::lock_guard<std::mutex> lk(pl->mu);
+        write_group_files(pl, pl->res_rt, pl->para.scratch_dir_name, "Residual_Shot");
+        write_group_files(pl, pl->syn_rt, pl->para.scratch_dir_name, "Syn_Shot");
+        write_group_files(pl, pl->obs_cond_rt, pl->para.scratch_dir_name, "CondObs_Shot");
+        std::vector<float> h((size_t)pl->group * pl->g.nSteps);
+        CUDA_OK(cudaMemcpy(h.data(), pl->stf.p, h.size() * sizeof(float), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < pl->group; i++)
+          write_f32(pl->para.scratch_dir_name + "/src_updated" + std::to_string(pl->shot_ids[i]) + ".bin",
+                    h.data() + (size_t)i * pl->g.nSteps, pl->g.nSteps);
+      }
+    }
+  });
+}
+
+}  // namespace
+
+extern "C" int fwi_b200_cufd(double *misfit, double *gl, double *gm, double *gd, double *gs, const double *Lambda,
+                             const double *Mu, const double *Den, const double *stf, int calc_id, int gpu_id,
+                             int group_size, const int *shot_ids, const char *para_fname) {
+  return host_call(misfit, gl, gm, gd, gs, Lambda, Mu, Den, stf, calc_id, false, gpu_id, group_size, shot_ids, para_fname);
+}
+
+extern "C" int fwi_b200_forward(double *misfit, const double *Lambda, const double *Mu, const double *Den, const double *stf,
+                                int gpu_id, int group_size, const int *shot_ids, const char *para_fname) {
+  return host_call(misfit, nullptr, nullptr, nullptr, nullptr, Lambda, Mu, Den, stf, 0, false, gpu_id, group_size, shot_ids, para_fname);
+}
+
+extern "C" int fwi_b200_backward(double *gl, double *gm, double *gd, double *gs, const double *Lambda, const double *Mu,
+                                 const double *Den, const double *stf, int gpu_id, int group_size, const int *shot_ids,
+                                 const char *para_fname) {
+  return host_call(nullptr, gl, gm, gd, gs, Lambda, Mu, Den, stf, 1, false, gpu_id, group_size, shot_ids, para_fname);
+}
+
+extern "C" int fwi_b200_obscalc(double *misfit, const double *Lambda, const double *Mu, const double *Den, const double *stf,
+                                int gpu_id, int group_size, const int *shot_ids, const char *para_fname) {
+  return host_call(misfit, nullptr, nullptr, nullptr, nullptr, Lambda, Mu, Den, stf, 2, false, gpu_id, group_size, shot_ids, para_fname);
+}
+
+extern "C" int fwi_b200_misfit_and_gradient(double *misfit, double *gl, double *gm, double *gd, double *gs,
+                                            const double *Lambda, const double *Mu, const double *Den, const double *stf,
+                                            int gpu_id, int group_size, const int *shot_ids, const char *para_fname) {
+  return host_call(misfit, gl, gm, gd, gs, Lambda, Mu, Den, stf, 1, true, gpu_id, group_size, shot_ids, para_fname);
+}
+
+extern "C" void fwi_b200_release(void) {
+  std::lock_guard<std::mutex> lk(g_cache_mu);
+  g_cache.clear();
+}

@@ -1,0 +1,168 @@
+"""High-level FWI API, Python mirror of the reference's `src/FWI.jl`.
+
+* ``FWI``                  -- struct holding geometry + file locations          (src/FWI.jl:3-25, 38-60)
+* ``compute_observation``  -- forward modelling -> (nShots, nSteps, nrec) array  (src/FWI.jl:109-135)
+* ``compute_misfit``       -- masked model -> moduli -> fwi_op                   (src/FWI.jl:156-189)
+* ``compute_misfit_and_gradient`` -- same, plus gradients w.r.t. (cp, cs, rho) through the chain rule
+  that TensorFlow autodiff applies in the reference (velocity_to_moduli + mask blend)
+* ``padding`` / ``try_pad`` -- symmetric PML padding                              (src/FWI.jl:193-232)
+
+Shot ids are 1-based here, exactly like the Julia API, and converted to 0-based before the op.
+"""
+from __future__ import annotations
+
+import os
+import tempfile
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import ops
+from .utils import (moduli_to_velocity_grads, paraGen, surveyGen, symmetric_pad, velocity_to_moduli)
+
+__all__ = ["FWI", "FWIExample", "compute_observation", "compute_misfit", "compute_misfit_and_gradient", "padding",
+           "try_pad"]
+
+
+@dataclass
+class FWI:
+    nz: int = 134
+    nx: int = 384
+    dz: float = 24.0
+    dx: float = 24.0
+    nSteps: int = 2000
+    dt: float = 0.0025
+    f0: float = 4.5
+    nPml: int = 32
+    nPad: int | None = None
+    para_fname: str = "para_file.json"
+    survey_fname: str = "survey_file.json"
+    data_dir_name: str = "Data"
+    WORKSPACE: str = field(default_factory=lambda: tempfile.mkdtemp(prefix="fwi_b200_"))
+    ind_src_x: np.ndarray | None = None
+    ind_src_z: np.ndarray | None = None
+    ind_rec_x: np.ndarray | None = None
+    ind_rec_z: np.ndarray | None = None
+    mask: np.ndarray | None = None
+    mask_neg: np.ndarray | None = None
+
+    def __post_init__(self):
+        if self.nPad is None:
+            self.nPad = 32 - ((self.nz + 2 * self.nPml) % 32)       # src/FWI.jl:12
+        self.nz_pad = self.nz + 2 * self.nPml + self.nPad           # src/FWI.jl:13
+        self.nx_pad = self.nx + 2 * self.nPml                       # src/FWI.jl:14
+        for k in ("ind_src_x", "ind_src_z", "ind_rec_x", "ind_rec_z"):
+            v = getattr(self, k)
+            if v is None:
+                raise ValueError(f"FWI: {k} is required")
+            setattr(self, k, np.asarray(v, dtype=np.int64).ravel())
+        assert len(self.ind_rec_x) == len(self.ind_rec_z)
+        assert len(self.ind_src_x) == len(self.ind_src_z)
+        P, nz, nx = self.nPml, self.nz, self.nx
+        Mask = np.zeros((self.nz_pad, self.nx_pad))                 # src/FWI.jl:45-49
+        Mask[P:P + nz, P:P + nx] = 1.0
+        Mask[P:P + 10, :] = 0.0
+        self.mask = Mask
+        self.mask_neg = 1.0 - Mask
+        os.makedirs(self.WORKSPACE, exist_ok=True)
+        paraGen(self.nz_pad, self.nx_pad, self.dz, self.dx, self.nSteps, self.dt, self.f0, self.nPml, self.nPad,
+                self.para_path, os.path.join(self.WORKSPACE, self.survey_fname),
+                os.path.join(self.WORKSPACE, self.data_dir_name))
+        surveyGen(self.ind_src_z, self.ind_src_x, self.ind_rec_z, self.ind_rec_x,
+                  os.path.join(self.WORKSPACE, self.survey_fname))
+
+    @property
+    def para_path(self):
+        return os.path.join(self.WORKSPACE, self.para_fname)
+
+
+def FWIExample(**kw):
+    """The Marmousi geometry of the reference (src/FWI.jl:87-97)."""
+    ind_src_x = np.arange(4, 385, 8)
+    ind_rec_x = np.arange(3, 382)
+    return FWI(nz=134, nx=384, dz=24.0, dx=24.0, nSteps=2000, dt=0.0025, ind_src_x=ind_src_x,
+               ind_src_z=2 * np.ones_like(ind_src_x), ind_rec_x=ind_rec_x, ind_rec_z=2 * np.ones_like(ind_rec_x), **kw)
+
+
+def padding(fwi: FWI, *arrays):
+    """tf.pad(cp, [nPml (nPml+nPad); nPml nPml], "SYMMETRIC") (src/FWI.jl:193-205).  Inputs must already
+    have the (nz, nx) shape (the reference's bilinear resize of mismatching inputs is not reproduced)."""
+    out = []
+    for a in arrays:
+        a = np.asarray(a, dtype=np.float64)
+        if a.shape != (fwi.nz, fwi.nx):
+            raise ValueError(f"padding: expected shape {(fwi.nz, fwi.nx)}, got {a.shape}")
+        out.append(symmetric_pad(a, fwi.nPml, fwi.nPad))
+    return out[0] if len(out) == 1 else out
+
+
+def try_pad(fwi: FWI, *arrays):
+    out = []
+    for a in arrays:
+        a = np.asarray(a, dtype=np.float64)
+        out.append(a if a.shape == (fwi.nz_pad, fwi.nx_pad) else padding(fwi, a))
+    return out[0] if len(out) == 1 else out
+
+
+def _stf_rows(fwi, stf_array):
+    stf = np.asarray(stf_array, dtype=np.float64)
+    if stf.ndim == 1 or (stf.ndim == 2 and stf.shape[0] == 1 and len(fwi.ind_src_z) > 1):
+        stf = np.repeat(stf.reshape(1, -1), len(fwi.ind_src_z), axis=0)   # src/FWI.jl:118-120
+    return stf
+
+
+def compute_observation(fwi: FWI, cp, cs, rho, stf_array, shot_ids=None, gpu_id=0):
+    """Writes WORKSPACE/Data/Shot<id>.bin and returns data[i, :, :] = (nSteps, nrec) per shot (src/FWI.jl:109-135)."""
+    cp_pad, cs_pad, rho_pad = try_pad(fwi, cp, cs, rho)
+    stf = _stf_rows(fwi, stf_array)
+    lam, mu = velocity_to_moduli(cp_pad, cs_pad, rho_pad)
+    if shot_ids is None:
+        shot_ids = np.arange(1, len(fwi.ind_src_x) + 1)
+    ids0 = np.asarray(shot_ids, dtype=np.int32) - 1
+    ops.fwi_obs_op(lam, mu, rho_pad, stf, gpu_id, ids0, fwi.para_path)
+    nrec = len(fwi.ind_rec_z)
+    data = np.zeros((len(ids0), fwi.nSteps, nrec))
+    for i, sid in enumerate(ids0):
+        a = np.fromfile(os.path.join(fwi.WORKSPACE, fwi.data_dir_name, f"Shot{int(sid)}.bin"), np.float32)
+        data[i] = a.reshape(nrec, fwi.nSteps).T      # Julia reshape (nSteps, nrec) column-major
+    return data
+
+
+def _masked_models(fwi, cp, cs, rho, is_masked, cp_ref, cs_ref, rho_ref):
+    cp_pad, cs_pad, rho_pad = try_pad(fwi, cp, cs, rho)
+    if is_masked:
+        return cp_pad, cs_pad, rho_pad
+    if cp_ref is None or cs_ref is None or rho_ref is None:
+        raise ValueError("compute_misfit: cp_ref, cs_ref, rho_ref are required when is_masked is False")
+    cp_r, cs_r, rho_r = try_pad(fwi, cp_ref, cs_ref, rho_ref)
+    return (cp_pad * fwi.mask + cp_r * fwi.mask_neg, cs_pad * fwi.mask + cs_r * fwi.mask_neg,
+            rho_pad * fwi.mask + rho_r * fwi.mask_neg)                  # src/FWI.jl:174-176
+
+
+def compute_misfit(fwi: FWI, cp, cs, rho, stf_array, shot_ids=None, gpu_id=0, is_masked=False, cp_ref=None,
+                   cs_ref=None, rho_ref=None):
+    """Misfit of the (masked) model against the data in WORKSPACE/Data (src/FWI.jl:156-189)."""
+    cp_m, cs_m, rho_m = _masked_models(fwi, cp, cs, rho, is_masked, cp_ref, cs_ref, rho_ref)
+    lam, mu = velocity_to_moduli(cp_m, cs_m, rho_m)
+    stf = _stf_rows(fwi, stf_array)
+    if shot_ids is None:
+        shot_ids = np.arange(1, len(fwi.ind_src_x) + 1)
+    ids0 = np.asarray(shot_ids, dtype=np.int32) - 1
+    return ops.fwi_op(lam, mu, rho_m, stf, gpu_id, ids0, fwi.para_path)
+
+
+def compute_misfit_and_gradient(fwi: FWI, cp, cs, rho, stf_array, shot_ids=None, gpu_id=0, is_masked=False,
+                                cp_ref=None, cs_ref=None, rho_ref=None):
+    """(misfit, d/dcp, d/dcs, d/drho) on the padded grid: what `gradients(loss, [cp, cs, rho])` yields in the
+    reference (mask blend -> velocity_to_moduli -> fwi_op), from a single propagation pair."""
+    cp_m, cs_m, rho_m = _masked_models(fwi, cp, cs, rho, is_masked, cp_ref, cs_ref, rho_ref)
+    lam, mu = velocity_to_moduli(cp_m, cs_m, rho_m)
+    stf = _stf_rows(fwi, stf_array)
+    if shot_ids is None:
+        shot_ids = np.arange(1, len(fwi.ind_src_x) + 1)
+    ids0 = np.asarray(shot_ids, dtype=np.int32) - 1
+    misfit, gl, gm, gd, _ = ops.fwi_op_and_grad(lam, mu, rho_m, stf, gpu_id, ids0, fwi.para_path)
+    g_cp, g_cs, g_rho = moduli_to_velocity_grads(cp_m, cs_m, rho_m, gl, gm, gd)
+    if not is_masked:
+        g_cp, g_cs, g_rho = g_cp * fwi.mask, g_cs * fwi.mask, g_rho * fwi.mask
+    return misfit, g_cp, g_cs, g_rho

@@ -1,0 +1,235 @@
+"""Operator surface of the FWI path, Python mirror of the reference's Julia wrappers.
+
+* ``fwi_op(lambda, mu, den, stf, gpu_id, shot_ids, para_fname)``      -- src/Core.jl:20-31
+* ``fwi_obs_op(lambda, mu, den, stf, gpu_id, shot_ids, para_fname)``  -- src/Core.jl:42-53
+* ``fwi_op_grad(...)``  -- the FwiOpGrad kernel (deps/CustomOps/FWI/FwiOp.cpp:130-223)
+* ``FwiOp``             -- torch.autograd.Function with the same forward/backward pairing as
+                           ADCME's ``load_op_and_grad`` (loss from calc_id 0, gradient from calc_id 1)
+* ``Plan``              -- device-resident plan (include/fwi_b200.h) for callers that keep
+                           inputs on the GPU / all-reduce gradients across GPUs
+
+Same argument meaning as the reference: lambda/mu in MPa, (nz_pad, nx_pad) float64 arrays
+(row-major like the TF tensors), stf (nShots, nSteps), shot_ids 0-based int32.
+All compute happens in libfwi_b200.so (CUDA, sm_100a); nothing here falls back to the CPU.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import FwiError, c_dp, c_fp, c_ip, check
+
+__all__ = ["fwi_op", "fwi_obs_op", "fwi_op_grad", "fwi_op_and_grad", "FwiOp", "Plan", "release", "FwiError"]
+
+
+def _f64(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+
+
+def _dp(a):
+    return None if a is None else a.ctypes.data_as(c_dp)
+
+
+def _prep(lam, mu, den, stf, shot_ids):
+    lam, mu, den, stf = _f64(lam), _f64(mu), _f64(den), _f64(stf)
+    if stf.ndim == 1:
+        stf = stf.reshape(1, -1)
+    ids = np.ascontiguousarray(np.asarray(shot_ids, dtype=np.int32).ravel())
+    if lam.shape != mu.shape or lam.shape != den.shape or lam.ndim != 2:
+        raise FwiError(-1, "lambda, mu, den must be 2-D arrays of the same (nz_pad, nx_pad) shape")
+    return lam, mu, den, stf, ids
+
+
+def fwi_op(lam, mu, den, stf, gpu_id, shot_ids, para_fname):
+    """FWI loss 0.5 * sum(residual^2) over the shots in `shot_ids` (calc_id 0)."""
+    lam, mu, den, stf, ids = _prep(lam, mu, den, stf, shot_ids)
+    misfit = ctypes.c_double(0.0)
+    check(_lib.lib().fwi_b200_forward(ctypes.cast(ctypes.byref(misfit), c_dp), _dp(lam), _dp(mu), _dp(den), _dp(stf),
+                                      int(gpu_id), len(ids), ids.ctypes.data_as(c_ip), str(para_fname).encode()))
+    return float(misfit.value)
+
+
+def fwi_obs_op(lam, mu, den, stf, gpu_id, shot_ids, para_fname):
+    """Forward modelling: writes data_dir_name/Shot<id>.bin, returns 0.0 (calc_id 2)."""
+    lam, mu, den, stf, ids = _prep(lam, mu, den, stf, shot_ids)
+    misfit = ctypes.c_double(0.0)
+    check(_lib.lib().fwi_b200_obscalc(ctypes.cast(ctypes.byref(misfit), c_dp), _dp(lam), _dp(mu), _dp(den), _dp(stf),
+                                      int(gpu_id), len(ids), ids.ctypes.data_as(c_ip), str(para_fname).encode()))
+    return float(misfit.value)
+
+
+def fwi_op_grad(lam, mu, den, stf, gpu_id, shot_ids, para_fname):
+    """Gradients (d/dlambda, d/dmu [per MPa], d/dden, d/dstf) of the loss (calc_id 1).
+
+    grad_stf has shape (nShotsTotal, nSteps): the reference fills row k = position in the group
+    and leaves the rest uninitialised; here the rows of the group's GLOBAL shot ids
+    are filled and every other row is zero, which is what an optimiser over stf needs.
+    """
+    lam, mu, den, stf, ids = _prep(lam, mu, den, stf, shot_ids)
+    gl, gm, gd = np.zeros_like(lam), np.zeros_like(lam), np.zeros_like(lam)
+    gs_group = np.zeros((len(ids), stf.shape[1]), np.float64)
+    check(_lib.lib().fwi_b200_backward(_dp(gl), _dp(gm), _dp(gd), _dp(gs_group), _dp(lam), _dp(mu), _dp(den), _dp(stf),
+                                       int(gpu_id), len(ids), ids.ctypes.data_as(c_ip), str(para_fname).encode()))
+    gs = np.zeros_like(stf)
+    gs[ids] = gs_group
+    return gl, gm, gd, gs
+
+
+def fwi_op_and_grad(lam, mu, den, stf, gpu_id, shot_ids, para_fname):
+    """Loss AND gradients from one forward propagation (the reference propagates twice)."""
+    lam, mu, den, stf, ids = _prep(lam, mu, den, stf, shot_ids)
+    gl, gm, gd = np.zeros_like(lam), np.zeros_like(lam), np.zeros_like(lam)
+    gs_group = np.zeros((len(ids), stf.shape[1]), np.float64)
+    misfit = ctypes.c_double(0.0)
+    check(_lib.lib().fwi_b200_misfit_and_gradient(
+        ctypes.cast(ctypes.byref(misfit), c_dp), _dp(gl), _dp(gm), _dp(gd), _dp(gs_group), _dp(lam), _dp(mu), _dp(den),
+        _dp(stf), int(gpu_id), len(ids), ids.ctypes.data_as(c_ip), str(para_fname).encode()))
+    gs = np.zeros_like(stf)
+    gs[ids] = gs_group
+    return float(misfit.value), gl, gm, gd, gs
+
+
+def release():
+    """Free the cached device contexts behind the host-buffer entry points."""
+    _lib.lib().fwi_b200_release()
+
+
+try:  # torch is plumbing: only needed for the autograd wrapper and device-tensor interop
+    import torch
+
+    class FwiOp(torch.autograd.Function):
+        """loss = FwiOp.apply(lam, mu, den, stf, gpu_id, shot_ids, para_fname) with autograd.
+
+        Like the reference's FwiOpGrad (FwiOp.cpp:220-222) the upstream gradient is NOT ignored here:
+        the returned gradients are scaled by grad_output (the reference drops it).
+        """
+
+        @staticmethod
+        def forward(ctx, lam, mu, den, stf, gpu_id, shot_ids, para_fname):
+            ctx.save_for_backward(lam, mu, den, stf)
+            ctx.meta = (int(gpu_id), np.asarray(shot_ids, dtype=np.int32), str(para_fname))
+            v = fwi_op(lam.detach().cpu().numpy(), mu.detach().cpu().numpy(), den.detach().cpu().numpy(),
+                       stf.detach().cpu().numpy(), *ctx.meta)
+            return torch.tensor(v, dtype=torch.float64)
+
+        @staticmethod
+        def backward(ctx, gout):
+            lam, mu, den, stf = ctx.saved_tensors
+            gl, gm, gd, gs = fwi_op_grad(lam.detach().cpu().numpy(), mu.detach().cpu().numpy(),
+                                         den.detach().cpu().numpy(), stf.detach().cpu().numpy(), *ctx.meta)
+            s = float(gout)
+            mk = lambda a, ref: torch.from_numpy(a * s).to(dtype=ref.dtype, device=ref.device).reshape(ref.shape)
+            return mk(gl, lam), mk(gm, mu), mk(gd, den), mk(gs, stf), None, None, None
+except Exception:  # pragma: no cover
+    torch = None
+    FwiOp = None
+
+
+class Plan:
+    """Device-resident FWI plan (fwi_b200_plan_* in include/fwi_b200.h)."""
+
+    def __init__(self, para_fname, shot_ids, gpu_id=0, max_batch=0):
+        self._L = _lib.lib()
+        self._h = ctypes.c_void_p()
+        ids = np.ascontiguousarray(np.asarray(shot_ids, dtype=np.int32).ravel())
+        self.shot_ids = ids
+        check(self._L.fwi_b200_plan_create(ctypes.byref(self._h), str(para_fname).encode(), int(gpu_id), len(ids),
+                                           ids.ctypes.data_as(c_ip), int(max_batch)))
+        v = [ctypes.c_int() for _ in range(8)]
+        check(self._L.fwi_b200_plan_info(self._h, *[ctypes.byref(x) for x in v]))
+        (self.nz, self.nx, self.nSteps, self.nPml, self.nPad, self.group_size, self.batch,
+         self.max_nrec) = [x.value for x in v]
+        self.gpu_id = int(gpu_id)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._L.fwi_b200_plan_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_model(self, lam, mu, den):
+        lam, mu, den = _f64(lam), _f64(mu), _f64(den)
+        assert lam.shape == (self.nz, self.nx) == mu.shape == den.shape
+        check(self._L.fwi_b200_plan_set_model(self._h, _dp(lam), _dp(mu), _dp(den)))
+
+    def set_stf(self, stf):
+        stf = _f64(stf)
+        if stf.ndim == 1:
+            stf = stf.reshape(1, -1)
+        assert stf.shape[1] == self.nSteps and stf.shape[0] > int(self.shot_ids.max())
+        check(self._L.fwi_b200_plan_set_stf(self._h, _dp(stf)))
+
+    def set_obs(self, ishot, obs):
+        obs = np.ascontiguousarray(np.asarray(obs, dtype=np.float32))
+        check(self._L.fwi_b200_plan_set_obs(self._h, int(ishot), obs.ctypes.data_as(c_fp)))
+
+    def load_obs_files(self):
+        check(self._L.fwi_b200_plan_load_obs_files(self._h))
+
+    def run(self, calc_id, stream=None, sync=True):
+        check(self._L.fwi_b200_plan_run(self._h, int(calc_id), ctypes.c_void_p(stream) if stream else None,
+                                        1 if sync else 0))
+
+    def result(self, with_grad=True):
+        misfit = ctypes.c_double(0.0)
+        mp = ctypes.cast(ctypes.byref(misfit), c_dp)
+        if not with_grad:
+            check(self._L.fwi_b200_plan_get_result(self._h, mp, None, None, None, None))
+            return float(misfit.value)
+        gl = np.zeros((self.nz, self.nx)); gm = np.zeros_like(gl); gd = np.zeros_like(gl)
+        gs = np.zeros((self.group_size, self.nSteps))
+        check(self._L.fwi_b200_plan_get_result(self._h, mp, _dp(gl), _dp(gm), _dp(gd), _dp(gs)))
+        return float(misfit.value), gl, gm, gd, gs
+
+    def result_device_ptr(self):
+        return int(self._L.fwi_b200_plan_result_device(self._h)), int(self._L.fwi_b200_plan_result_count(self._h))
+
+    def result_tensor(self):
+        """The packed [grad_lambda|grad_mu|grad_den|misfit] float32 buffer as a torch CUDA tensor (no copy)."""
+        ptr, n = self.result_device_ptr()
+
+        class _Wrap:  # __cuda_array_interface__ view of memory owned by the plan
+            __cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+        return torch.as_tensor(_Wrap(), device=f"cuda:{self.gpu_id}")
+
+    def traces(self, ishot, which=0):
+        nrec = self.shot_geometry(ishot)[2]
+        out = np.zeros((nrec, self.nSteps), np.float32)
+        check(self._L.fwi_b200_plan_get_traces(self._h, int(ishot), int(which), out.ctypes.data_as(c_fp)))
+        return out
+
+    def write_obs_files(self):
+        check(self._L.fwi_b200_plan_write_obs_files(self._h))
+
+    def shot_geometry(self, ishot):
+        zs, xs, nr = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        check(self._L.fwi_b200_plan_shot_geometry(self._h, int(ishot), ctypes.byref(zs), ctypes.byref(xs),
+                                                  ctypes.byref(nr), None, None))
+        zr = np.zeros(nr.value, np.int32); xr = np.zeros(nr.value, np.int32)
+        check(self._L.fwi_b200_plan_shot_geometry(self._h, int(ishot), None, None, None, zr.ctypes.data_as(c_ip),
+                                                  xr.ctypes.data_as(c_ip)))
+        return zs.value, xs.value, nr.value, zr, xr
+
+    def launch_count(self):
+        return int(self._L.fwi_b200_plan_launch_count(self._h))
+
+    def field(self, ishot, field):
+        out = np.zeros((self.nz, self.nx), np.float32)
+        check(self._L.fwi_b200_plan_get_field(self._h, int(ishot), int(field), out.ctypes.data_as(c_fp)))
+        return out
+
+    def time_kernel(self, which, iters=20, stream=None):
+        ms = ctypes.c_float(0.0)
+        nbytes = ctypes.c_double(0.0)
+        check(self._L.fwi_b200_plan_time_kernel(self._h, int(which), int(iters),
+                                                ctypes.c_void_p(stream) if stream else None,
+                                                ctypes.byref(ms), ctypes.cast(ctypes.byref(nbytes), c_dp)))
+        return float(ms.value), float(nbytes.value)

@@ -1,0 +1,163 @@
+"""CPU: host-side conventions and the C ABI surface (no compute call needs a GPU here)."""
+import ctypes
+import json
+import os
+import re
+import tempfile
+
+import numpy as np
+import pytest
+
+from fwiflow.jl_b200 import _lib, ops, synthetic, utils
+from fwiflow.jl_b200.fwi import FWI, FWIExample
+from helpers import ROOT
+
+
+def test_library_exports_every_declared_symbol(lib_built):
+    hdr = open(os.path.join(ROOT, "include", "fwi_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(fwi_b200_[a-z_]+)\s*\(", hdr)))
+    assert declared, "no declarations found"
+    assert sorted(_lib.SYMBOLS) == declared
+    L = ctypes.CDLL(lib_built)
+    for s in declared:
+        assert hasattr(L, s), s
+    assert b"sm_100a" in _lib.lib().fwi_b200_version()
+
+
+def test_paragen_surveygen_roundtrip():
+    wd = tempfile.mkdtemp()
+    para = os.path.join(wd, "para_file.json")
+    survey = os.path.join(wd, "survey_file.json")
+    utils.paraGen(224, 448, 24.0, 24.0, 2000, 0.0025, 4.5, 32, 26, para, survey, os.path.join(wd, "Data"))
+    utils.surveyGen([2, 2], [4, 12], [2, 2, 2], [3, 4, 5], survey)
+    text = open(para).read()
+    assert "\n" not in text                      # the reference parser reads ONE line (Parameter.cpp:28)
+    p = json.loads(text)
+    assert list(p)[:9] == ["nz", "nx", "dz", "dx", "nSteps", "dt", "f0", "nPoints_pml", "nPad"]
+    assert p["nz"] == 224 and p["survey_fname"] == survey and os.path.isdir(p["data_dir_name"])
+    s = json.loads(open(survey).read())
+    assert s["nShots"] == 2 and s["shot1"]["x_src"] == 12 and s["shot0"]["nrec"] == 3
+    assert s["shot1"]["x_rec"] == [3, 4, 5]
+
+
+def test_sourcegene_matches_julia_definition():
+    f, n, dt = 4.5, 2000, 0.0025
+    s = utils.sourceGene(f, n, dt)
+    e = np.pi ** 2 * f ** 2
+    src = np.zeros(n)
+    for it in range(n):
+        t = dt * it - 1.2 / f
+        src[it] = (1 - 2 * e * t * t) * np.exp(-e * t * t)
+    for it in range(1, n):
+        src[it] += src[it - 1]
+    assert s.shape == (1, n)
+    np.testing.assert_allclose(s[0], src * dt, rtol=1e-12, atol=1e-18)
+
+
+def test_reference_source_fixture_is_this_wavelet_family():
+    """docs/data/sourceF_4p5_2_high.bin peaks at sample 175 with 0.0287;
+    sourceGene(4.5, 2000, 0.0025) is the same integrated Ricker up to the fixture's extra filtering."""
+    s = utils.sourceGene(4.5, 2000, 0.0025)[0]
+    assert 100 < int(np.argmax(s)) < 140 and 0.02 < s.max() < 0.06
+
+
+def test_velocity_moduli_chain_rule():
+    rng = np.random.default_rng(0)
+    cp = 3000 + 100 * rng.random((5, 6)); cs = cp / 1.8; rho = 2000 + 50 * rng.random((5, 6))
+    gl, gm, gd = rng.random((5, 6)), rng.random((5, 6)), rng.random((5, 6))
+    g_cp, g_cs, g_rho = utils.moduli_to_velocity_grads(cp, cs, rho, gl, gm, gd)
+    f = lambda cp, cs, rho: sum(np.sum(g * v) for g, v in zip((gl, gm), utils.velocity_to_moduli(cp, cs, rho))) + np.sum(gd * rho)
+    h = 1e-3
+    for arr, g in ((cp, g_cp), (cs, g_cs), (rho, g_rho)):
+        d = np.zeros_like(arr); d[2, 3] = h
+        args = [cp, cs, rho]
+        idx = [i for i, a in enumerate(args) if a is arr][0]
+        up = list(args); up[idx] = arr + d
+        dn = list(args); dn[idx] = arr - d
+        assert (f(*up) - f(*dn)) / (2 * h) == pytest.approx(g[2, 3], rel=1e-6)
+
+
+def test_fwi_struct_matches_reference_conventions():
+    fwi = FWIExample()
+    assert (fwi.nPad, fwi.nz_pad, fwi.nx_pad) == (26, 224, 448)         # src/FWI.jl:12-14
+    assert len(fwi.ind_src_x) == 48 and len(fwi.ind_rec_x) == 379        # src/FWI.jl:87-91
+    assert fwi.mask.shape == (224, 448) and fwi.mask[32:42].sum() == 0 and fwi.mask[42, 32] == 1
+    p = json.loads(open(fwi.para_path).read())
+    assert (p["nz"], p["nx"], p["nPad"]) == (224, 448, 26)
+    assert utils.nPad_rule(100) == 28 and utils.nPad_rule(64) == 32
+
+
+def test_symmetric_padding_is_tf_symmetric():
+    a = np.arange(12.0).reshape(3, 4)
+    p = utils.symmetric_pad(a, 2, 1)
+    assert p.shape == (3 + 2 + 3, 4 + 4)
+    assert p[1, 2] == a[0, 0] and p[0, 2] == a[1, 0] and p[2 + 3, 2] == a[2, 0] and p[2 + 3 + 2, 2] == a[0, 0]
+
+
+def _case_files():
+    c = synthetic.case_small("host", nz=40, nx=56, nSteps=50, nshots=2)
+    wd = tempfile.mkdtemp()
+    return c, wd, c.write_files(wd)
+
+
+def test_unsupported_keys_are_rejected_not_ignored(lib_built):
+    c, wd, para = _case_files()
+    lam, mu, rho = c.moduli("true")
+    p = json.loads(open(para).read())
+    for extra in ({"filter": [0.0, 0.1, 100.0, 200.0]}, {"if_win": True}, {"if_src_update": True}):
+        q = dict(p); q.update(extra)
+        fn = os.path.join(wd, "para_bad.json")
+        open(fn, "w").write(json.dumps(q))
+        with pytest.raises(ops.FwiError) as ei:
+            ops.fwi_obs_op(lam, mu, rho, c.stf, 0, [0], fn)
+        assert ei.value.code == -6
+    q = dict(p); q.update({"if_win": False, "if_src_update": False, "isAc": True})   # the reference's sample file
+    fn = os.path.join(wd, "para_ok.json")
+    open(fn, "w").write(json.dumps(q, indent=1))      # multi-line is tolerated
+    with pytest.raises(ops.FwiError) as ei:
+        ops.fwi_obs_op(lam, mu, rho, c.stf, 0, [0], fn)
+    assert ei.value.code == -5                        # parsed fine; fails only because this box has no GPU
+
+
+def test_error_codes_instead_of_exit(lib_built):
+    c, wd, para = _case_files()
+    lam, mu, rho = c.moduli("true")
+    with pytest.raises(ops.FwiError) as ei:
+        ops.fwi_op(lam, mu, rho, c.stf, 0, [0], os.path.join(wd, "nope.json"))
+    assert ei.value.code == -2
+    open(os.path.join(wd, "broken.json"), "w").write('{"nz": 12, ')
+    with pytest.raises(ops.FwiError) as ei:
+        ops.fwi_op(lam, mu, rho, c.stf, 0, [0], os.path.join(wd, "broken.json"))
+    assert ei.value.code == -3
+    p = json.loads(open(para).read()); del p["nSteps"]
+    open(os.path.join(wd, "missing.json"), "w").write(json.dumps(p))
+    with pytest.raises(ops.FwiError) as ei:
+        ops.fwi_op(lam, mu, rho, c.stf, 0, [0], os.path.join(wd, "missing.json"))
+    assert ei.value.code == -3
+    with pytest.raises(ops.FwiError):
+        ops.fwi_op(lam, mu, rho, c.stf, 0, [7], para)   # shot7 is not in the survey
+
+
+def test_no_cpu_fallback(lib_built):
+    """Without a CUDA device the product path must fail loudly (never route through the oracle)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    c, wd, para = _case_files()
+    lam, mu, rho = c.moduli("true")
+    with pytest.raises(ops.FwiError) as ei:
+        ops.fwi_obs_op(lam, mu, rho, c.stf, 0, [0, 1], para)
+    assert ei.value.code == -5 and "no CPU fallback" in str(ei.value)
+    src = ""
+    for root, _, files in os.walk(os.path.join(ROOT, "fwiflow")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cpp", ".hpp", ".cuh", ".h")):
+                src += open(os.path.join(root, f)).read()
+    assert "oracle_py" not in src and "fwi_oracle" not in src and "libCUFD_ref" not in src
+
+
+def test_synthetic_cases_have_baseline_shapes():
+    c2 = synthetic.case_c2(nSteps=10)
+    assert (c2.nz_pad, c2.nx_pad, c2.nShots, c2.nrec) == (224, 448, 30, 378 + 0) or c2.nrec in (378, 379)
+    c1 = synthetic.case_c1(nSteps=10)
+    assert (c1.nz_pad, c1.nx_pad, c1.nShots, c1.nrec) == (192, 164, 1, 94)

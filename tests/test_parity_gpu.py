@@ -1,0 +1,303 @@
+"""GPU (B200): parity of the CUDA path (through the C ABI of libfwi_b200.so) against
+(1) golden vectors produced by the reference itself, (2) the CPU oracle on fresh inputs, and
+(3) size-independent properties at BASELINE sizes.  Tolerances are BASELINE.json's: rel-L2 <= 1e-4 on
+traces, <= 1e-3 on gradients, indices bit-exact."""
+import json
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+from helpers import (TOL_GRAD, TOL_MISFIT, TOL_TRACE, away_from_sources, b200_cufd, golden_cases, interior_mask,
+                     load_golden, rel, run_case)
+
+pytestmark = pytest.mark.gpu
+
+CASES = golden_cases()
+
+
+@pytest.fixture(scope="module")
+def ops():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from fwiflow.jl_b200 import _lib, ops as _ops
+    assert os.path.exists(_lib.LIB_PATH), "libfwi_b200.so missing: the CUDA path must be built in-tree"
+    return _ops
+
+
+@pytest.fixture(scope="module")
+def b200_runs(ops):
+    return {name: run_case(name, c, b200_cufd, tempfile.mkdtemp(prefix=f"b200_{name}_")) for name, c in CASES.items()}
+
+
+# ---- (1) golden vectors of the reference -------------------------------------------------------------
+@pytest.mark.parametrize("name", list(CASES))
+def test_traces_match_reference_golden(name, b200_runs):
+    g, m = load_golden(name), b200_runs[name]
+    assert m["obs"].shape == g["obs"].shape
+    assert rel(m["obs"][..., 1:], g["obs"][..., 1:]) <= TOL_TRACE
+    assert np.all(m["obs"][..., 0] == 0.0)
+
+
+@pytest.mark.parametrize("name", [n for n in CASES if n != "c1"])
+def test_misfit_and_gradients_match_reference_golden(name, b200_runs):
+    g, m, c = load_golden(name), b200_runs[name], CASES[name]
+    assert float(m["misfit_true"]) == 0.0
+    assert abs(float(m["misfit_init"]) - float(g["misfit_init"])) <= TOL_MISFIT * float(g["misfit_init"])
+    inner, far = interior_mask(c), away_from_sources(c)
+    for k in ("grad_lambda", "grad_den"):
+        assert rel(m[k], g[k]) <= TOL_GRAD, k
+        assert rel(m[k][inner], g[k][inner]) <= TOL_GRAD, k
+    if name == "small_acoustic":   # see tests/test_oracle_golden.py: float32 noise on the source/receiver row
+        assert rel(m["grad_mu"][inner], g["grad_mu"][inner]) <= TOL_GRAD
+    else:
+        assert rel(m["grad_mu"], g["grad_mu"]) <= TOL_GRAD
+    assert rel(m["grad_mu"][far & inner], g["grad_mu"][far & inner]) <= TOL_GRAD
+    assert rel(m["grad_stf"], g["grad_stf"]) <= 5e-3
+    assert np.all(m["grad_stf"][:, -1] == 0.0)
+    for k in ("grad_lambda", "grad_mu", "grad_den", "grad_stf"):
+        assert np.isfinite(m[k]).all()
+
+
+# ---- (2) the CPU oracle on inputs that are not in the golden set -----------------------------------------
+def _ragged_case():
+    """two shots with DIFFERENT receiver counts, receivers in the volume, off-centre sources, nz not /32."""
+    from fwiflow.jl_b200 import synthetic
+    c = synthetic.case_small("ragged", nz=50, nx=70, nSteps=400, nshots=2, seed=11)
+    wd = tempfile.mkdtemp(prefix="ragged_")
+    para = c.write_files(wd)
+    sv = json.loads(open(os.path.join(wd, "survey_file.json")).read())
+    sv["shot1"]["z_rec"] = [5, 9, 13, 17, 30]
+    sv["shot1"]["x_rec"] = [7, 20, 33, 46, 60]
+    sv["shot1"]["nrec"] = 5
+    sv["shot0"]["z_src"], sv["shot0"]["x_src"] = 12, 9
+    open(os.path.join(wd, "survey_file.json"), "w").write(json.dumps(sv))
+    return c, para
+
+
+def test_ragged_receivers_against_oracle(ops):
+    from oracle import oracle_py as op
+    c, para = _ragged_case()
+    ids = np.array([0, 1], np.int32)
+    lam, mu, rho = c.moduli("true")
+    lam0, mu0, rho0 = c.moduli("init")
+    mine = b200_cufd(2, lam, mu, rho, c.stf, ids, para)
+    obs = [t.copy() for t in mine["syn"]]
+    orc = op.oracle_cufd(2, lam, mu, rho, c.stf, ids, para)       # overwrites Data/ with its own obs
+    assert [t.shape for t in obs] == [t.shape for t in orc["syn"]] == [(c.nrec, 400), (5, 400)]
+    for a, b in zip(obs, orc["syn"]):
+        assert rel(a[:, 1:], b[:, 1:]) <= TOL_TRACE
+    g_or = op.oracle_cufd(1, lam0, mu0, rho0, c.stf, ids, para)
+    j_or = op.oracle_cufd(0, lam0, mu0, rho0, c.stf, ids, para)["misfit"]
+    g_b = b200_cufd(1, lam0, mu0, rho0, c.stf, ids, para)
+    j_b = b200_cufd(0, lam0, mu0, rho0, c.stf, ids, para)["misfit"]
+    assert abs(j_b - j_or) <= TOL_MISFIT * j_or
+    for k in ("grad_lambda", "grad_mu", "grad_den"):
+        assert rel(g_b[k], g_or[k]) <= TOL_GRAD, k
+    assert rel(g_b["grad_stf"], g_or["grad_stf"]) <= 5e-3
+
+
+def test_shot_and_receiver_indices_bit_exact(ops):
+    """Src_Rec.cu:86-113: json + nPml, row order = order in the file; file names Shot<id>.bin."""
+    c, para = _ragged_case()
+    sv = json.loads(open(json.loads(open(para).read())["survey_fname"]).read())
+    plan = ops.Plan(para, [1, 0])
+    for pos, sid in enumerate([1, 0]):
+        zs, xs, nrec, zr, xr = plan.shot_geometry(pos)
+        sh = sv[f"shot{sid}"]
+        assert (zs, xs, nrec) == (sh["z_src"] + 32, sh["x_src"] + 32, sh["nrec"])
+        assert zr.tolist() == [v + 32 for v in sh["z_rec"]] and xr.tolist() == [v + 32 for v in sh["x_rec"]]
+    plan.close()
+    lam, mu, rho = c.moduli("true")
+    data_dir = json.loads(open(para).read())["data_dir_name"]
+    for f in os.listdir(data_dir):
+        os.remove(os.path.join(data_dir, f))
+    ops.fwi_obs_op(lam, mu, rho, c.stf, 0, [1], para)
+    assert os.listdir(data_dir) == ["Shot1.bin"]
+    assert os.path.getsize(os.path.join(data_dir, "Shot1.bin")) == 5 * 400 * 4      # [rec][time] float32
+
+
+# ---- (3) properties ------------------------------------------------------------------------------------
+def test_forward_is_linear_in_the_source(ops):
+    c = CASES["gradtest"]
+    para = c.write_files(tempfile.mkdtemp())
+    lam, mu, rho = c.moduli("true")
+    a = b200_cufd(2, lam, mu, rho, c.stf, [0], para)["syn"][0].copy()
+    b = b200_cufd(2, lam, mu, rho, 2.0 * c.stf, [0], para)["syn"][0]
+    assert rel(b, 2.0 * a) <= 1e-6
+
+
+def test_shot_sum_and_batch_invariance(ops):
+    c = CASES["small_elastic"]
+    para = c.write_files(tempfile.mkdtemp())
+    lam, mu, rho = c.moduli("true")
+    lam0, mu0, rho0 = c.moduli("init")
+    ops.fwi_obs_op(lam, mu, rho, c.stf, 0, [0, 1], para)
+    both = ops.fwi_op_grad(lam0, mu0, rho0, c.stf, 0, [0, 1], para)
+    s0 = ops.fwi_op_grad(lam0, mu0, rho0, c.stf, 0, [0], para)
+    s1 = ops.fwi_op_grad(lam0, mu0, rho0, c.stf, 0, [1], para)
+    for k in range(3):
+        assert rel(s0[k] + s1[k], both[k]) <= 1e-5
+    assert rel(s0[3] + s1[3], both[3]) <= 1e-6
+    j = ops.fwi_op(lam0, mu0, rho0, c.stf, 0, [0, 1], para)
+    assert abs(ops.fwi_op(lam0, mu0, rho0, c.stf, 0, [0], para) + ops.fwi_op(lam0, mu0, rho0, c.stf, 0, [1], para) - j) <= 1e-5 * j
+    # one shot per launch vs both shots in one launch
+    res = []
+    for mb in (1, 2):
+        p = ops.Plan(para, [0, 1], max_batch=mb)
+        assert p.batch == mb
+        p.set_model(lam0, mu0, rho0); p.set_stf(c.stf); p.load_obs_files(); p.run(1)
+        res.append(p.result())
+        p.close()
+    assert abs(res[0][0] - res[1][0]) <= 1e-6 * res[1][0]
+    for k in range(1, 5):
+        assert rel(res[0][k], res[1][k]) <= 1e-5
+    # fused loss+gradient == the two separate calls
+    fused = ops.fwi_op_and_grad(lam0, mu0, rho0, c.stf, 0, [0, 1], para)
+    assert fused[0] == pytest.approx(j, rel=1e-6)
+    for k in range(4):
+        assert rel(fused[1 + k], both[k]) <= 1e-6
+
+
+def test_reverse_time_reconstruction_returns_to_rest(ops):
+    """gradtest.jl:111-120 as an invariant: after the backward pass the reconstructed forward field is the
+    state at t=0, i.e. (almost) zero inside the PML-free box, relative to the field at the last step."""
+    c = CASES["small_elastic"]
+    para = c.write_files(tempfile.mkdtemp())
+    lam, mu, rho = c.moduli("true")
+    ops.fwi_obs_op(lam, mu, rho, c.stf, 0, [0, 1], para)
+    p = ops.Plan(para, [0, 1])
+    p.set_model(*c.moduli("init")); p.set_stf(c.stf); p.load_obs_files()
+    p.run(2)
+    last = [p.field(0, f) for f in range(5)]
+    p.run(1)
+    P = c.nPml
+    box = (slice(P, c.nz_pad - c.nPad - P), slice(P, c.nx_pad - P))
+    for f in range(5):
+        rec0 = p.field(0, f)
+        assert np.abs(rec0[box]).max() <= 2e-4 * np.abs(last[f]).max(), f
+    p.close()
+
+
+def test_baseline_size_properties_c2(ops):
+    """C2 geometry (224x448 padded, 379 receivers), 3 shots, shortened record: misfit(true) == 0 exactly,
+    gradient is finite, zero outside the imaging region, and additive over shots."""
+    from fwiflow.jl_b200 import synthetic
+    c = synthetic.case_c2(nshots=3, nSteps=400)
+    assert (c.nz_pad, c.nx_pad) == (224, 448)
+    para = c.write_files(tempfile.mkdtemp())
+    lam, mu, rho = c.moduli("true")
+    lam0, mu0, rho0 = c.moduli("init")
+    ids = np.arange(3, dtype=np.int32)
+    ops.fwi_obs_op(lam, mu, rho, c.stf, 0, ids, para)
+    assert ops.fwi_op(lam, mu, rho, c.stf, 0, ids, para) == 0.0
+    j, gl, gm, gd, gs = ops.fwi_op_and_grad(lam0, mu0, rho0, c.stf, 0, ids, para)
+    assert j > 0 and all(np.isfinite(a).all() for a in (gl, gm, gd, gs))
+    P = c.nPml
+    outside = np.ones((224, 448), bool)
+    outside[P:224 - c.nPad - P, P:448 - P + 1] = False      # box + the x+1 spray column
+    assert np.all(gl[outside] == 0) and np.all(gm[outside] == 0) and np.all(gd[outside] == 0)
+    parts = [ops.fwi_op_grad(lam0, mu0, rho0, c.stf, 0, [k], para) for k in range(3)]
+    assert rel(sum(p[0] for p in parts), gl) <= 1e-5 and rel(sum(p[2] for p in parts), gd) <= 1e-5
+
+
+def test_c2_two_shots_against_oracle(ops):
+    from oracle import oracle_py as op
+    from fwiflow.jl_b200 import synthetic
+    c = synthetic.case_c2(nshots=2, nSteps=500)
+    para = c.write_files(tempfile.mkdtemp())
+    lam, mu, rho = c.moduli("true")
+    lam0, mu0, rho0 = c.moduli("init")
+    ids = np.arange(2, dtype=np.int32)
+    mine = [t.copy() for t in b200_cufd(2, lam, mu, rho, c.stf, ids, para)["syn"]]
+    orc = op.oracle_cufd(2, lam, mu, rho, c.stf, ids, para)["syn"]
+    for a, b in zip(mine, orc):
+        assert rel(a[:, 1:], b[:, 1:]) <= TOL_TRACE
+    g_or = op.oracle_cufd(1, lam0, mu0, rho0, c.stf, ids, para)
+    g_b = b200_cufd(1, lam0, mu0, rho0, c.stf, ids, para)
+    inner = interior_mask(c)
+    for k in ("grad_lambda", "grad_mu", "grad_den"):
+        assert rel(g_b[k][inner], g_or[k][inner]) <= TOL_GRAD, k
+        assert rel(g_b[k], g_or[k]) <= 5 * TOL_GRAD, k     # incl. the ill-conditioned source cells
+
+
+# ---- errors, high-level API, sharding -------------------------------------------------------------------
+def test_courant_violation_and_missing_data_are_errors(ops):
+    c = CASES["small_elastic"]
+    wd = tempfile.mkdtemp()
+    para = c.write_files(wd)
+    lam, mu, rho = c.moduli("true")
+    with pytest.raises(ops.FwiError) as ei:
+        ops.fwi_obs_op(lam * 9.0, mu * 9.0, rho, c.stf, 0, [0], para)
+    assert ei.value.code == -4
+    with pytest.raises(ops.FwiError) as ei:
+        ops.fwi_op(lam, mu, rho, c.stf, 0, [0], para)      # Data/Shot0.bin was never written
+    assert ei.value.code == -2
+    with pytest.raises(ops.FwiError):
+        ops.fwi_op(lam, mu, rho, c.stf, 99, [0], para)     # no such GPU
+
+
+def test_high_level_api(ops):
+    from fwiflow.jl_b200 import FWI, compute_misfit, compute_misfit_and_gradient, compute_observation, sourceGene
+    rng = np.random.default_rng(3)
+    nz, nx = 40, 60
+    fwi = FWI(nz=nz, nx=nx, dz=20.0, dx=20.0, nSteps=300, dt=0.002, f0=6.0, ind_src_x=[10, 40], ind_src_z=[12, 12],
+              ind_rec_x=np.arange(3, 57), ind_rec_z=np.full(54, 12))
+    cp = 2500.0 + 300.0 * (np.arange(nz)[:, None] / nz) * np.ones((1, nx))
+    cs = cp / np.sqrt(3.0); rho = np.full((nz, nx), 2200.0)
+    stf = sourceGene(6.0, 300, 0.002)
+    obs = compute_observation(fwi, cp, cs, rho, stf)
+    assert obs.shape == (2, 300, 54) and np.abs(obs).max() > 0
+    assert compute_misfit(fwi, cp, cs, rho, stf, cp_ref=cp, cs_ref=cs, rho_ref=rho) == 0.0
+    cp2 = cp * (1.0 + 0.03 * rng.random(cp.shape))
+    j, g_cp, g_cs, g_rho = compute_misfit_and_gradient(fwi, cp2, cs, rho, stf, cp_ref=cp, cs_ref=cs, rho_ref=rho)
+    assert j > 0 and g_cp.shape == (fwi.nz_pad, fwi.nx_pad) and np.all(g_cp[fwi.mask == 0] == 0)
+    assert j == pytest.approx(compute_misfit(fwi, cp2, cs, rho, stf, shot_ids=[1, 2], cp_ref=cp, cs_ref=cs, rho_ref=rho), rel=1e-6)
+    # directional derivative of the misfit along the gradient direction (first-order check)
+    d = g_cp / np.abs(g_cp).max()
+    eps = 2.0
+    inner = (slice(fwi.nPml, fwi.nPml + nz), slice(fwi.nPml, fwi.nPml + nx))
+    jp = compute_misfit(fwi, cp2 + eps * d[inner], cs, rho, stf, cp_ref=cp, cs_ref=cs, rho_ref=rho)
+    jm = compute_misfit(fwi, cp2 - eps * d[inner], cs, rho, stf, cp_ref=cp, cs_ref=cs, rho_ref=rho)
+    fd = (jp - jm) / (2 * eps)
+    an = float(np.sum(g_cp[inner] * d[inner]))
+    assert fd == pytest.approx(an, rel=0.1)
+
+
+def test_sharded_gradient_single_rank_and_device_buffer(ops):
+    import torch
+    from fwiflow.jl_b200 import dist as fdist
+    c = CASES["small_elastic"]
+    para = c.write_files(tempfile.mkdtemp())
+    lam, mu, rho = c.moduli("true")
+    lam0, mu0, rho0 = c.moduli("init")
+    ops.fwi_obs_op(lam, mu, rho, c.stf, 0, [0, 1], para)
+    j, gl, gm, gd = fdist.sharded_gradient(lambda ids: ops.Plan(para, ids), [0, 1], 0, 1, lam0, mu0, rho0, c.stf)
+    ref = ops.fwi_op_and_grad(lam0, mu0, rho0, c.stf, 0, [0, 1], para)
+    assert j == pytest.approx(ref[0], rel=1e-6)
+    assert rel(gl, ref[1]) <= 1e-6 and rel(gm, ref[2]) <= 1e-6 and rel(gd, ref[3]) <= 1e-6
+    # two "ranks" emulated on one GPU: partial results summed on the device equal the full gradient
+    bufs = []
+    for r in range(2):
+        p = ops.Plan(para, fdist.shard_shots([0, 1], r, 2))
+        p.set_model(lam0, mu0, rho0); p.set_stf(c.stf); p.load_obs_files(); p.run(1)
+        t = p.result_tensor()
+        assert t.is_cuda and t.dtype == torch.float32 and t.numel() == 3 * c.nz_pad * c.nx_pad + 1
+        bufs.append(t.clone()); p.close()
+    tot = (bufs[0] + bufs[1]).cpu().numpy().astype(np.float64)
+    n = c.nz_pad * c.nx_pad
+    assert rel(tot[:n].reshape(c.nz_pad, c.nx_pad), ref[1]) <= 1e-5 and tot[3 * n] == pytest.approx(ref[0], rel=1e-5)
+
+
+def test_kernel_timer_reports_bytes(ops):
+    c = CASES["small_elastic"]
+    para = c.write_files(tempfile.mkdtemp())
+    p = ops.Plan(para, [0, 1])
+    p.set_model(*c.moduli("init")); p.set_stf(c.stf)
+    n0 = p.launch_count()
+    for which in range(4):
+        ms, nbytes = p.time_kernel(which, iters=5)
+        assert ms > 0 and nbytes > 0
+    assert p.launch_count() > n0
+    p.close()
