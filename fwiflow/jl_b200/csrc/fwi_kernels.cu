@@ -12,11 +12,13 @@
 //                       replaces source_grad / el_velocity_adj / res_injection / el_stress_adj
 //                       (reference: libCUFD.cu:376,405-427)
 // All three use shared-memory tiles with halos (the second half-step is computed from the
-// first half-step's tile without a round trip to HBM), ping-pong state buffers, and the
-// reference's arithmetic (float storage, double promotion where the reference's C
-// expressions promote -- FWI_FP64_PROMOTE).  Derivatives multiply by 1/dz instead of
-// dividing (<= 1 ulp per derivative).
+// first half-step's tile without a round trip to HBM), staged with cp.async, one float4 "quad"
+// of 4 consecutive z cells per thread (16-byte loads / stores everywhere), ping-pong state
+// buffers, and the reference's arithmetic (float storage; with FWI_FP64_PROMOTE=1 the double
+// promotion of the reference's C expressions is reproduced).  Derivatives multiply by 1/dz
+// instead of dividing (<= 1 ulp per derivative).
 #include <cstdio>
+#include <cstdlib>
 
 #include "fwi_kernels.cuh"
 
@@ -88,20 +90,58 @@ __device__ __forceinline__ bool in_box(const Grid &g, int z, int x) {
 }
 
 // =================================================================================================
-// forward step
+// forward step: one float4 "quad" (4 consecutive z cells) per thread, 16 quads = one sigma-tile
+// column per half-warp.  Velocity tile (halo rounded up to whole quads) staged with cp.async.
 // =================================================================================================
-constexpr int FV_Z = TILE_Z + 6, FV_X = TILE_X + 6;  // velocity tile (halo 3)
-constexpr int FS_Z = TILE_Z + 4, FS_X = TILE_X + 4;  // stress tile   (halo 2)
-constexpr size_t FWD_SMEM = (size_t)(2 * FV_Z * FV_X + 3 * FS_Z * FS_X) * sizeof(float);
+struct F4 {
+  float v[4];
+};
+__device__ __forceinline__ F4 ld4(const float *p) {
+  const float4 t = *reinterpret_cast<const float4 *>(p);
+  return F4{{t.x, t.y, t.z, t.w}};
+}
+__device__ __forceinline__ void st4(float *p, const F4 &a) {
+  *reinterpret_cast<float4 *>(p) = make_float4(a.v[0], a.v[1], a.v[2], a.v[3]);
+}
+__device__ __forceinline__ void cp_async16(float *smem_dst, const float *gsrc) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+// 7 consecutive samples w[0..6] = f[z-2 .. z+4]  ->  D-z at the 4 cells z..z+3
+__device__ __forceinline__ void dz_minus4(const F4 &A, const F4 &B, const F4 &C, float rh, float *out) {
+  const float w[7] = {A.v[2], A.v[3], B.v[0], B.v[1], B.v[2], B.v[3], C.v[0]};
+#pragma unroll
+  for (int k = 0; k < 4; k++) out[k] = (C1 * (w[k + 2] - w[k + 1]) - C2 * (w[k + 3] - w[k])) * rh;
+}
+// samples u[0..6] = f[z-1 .. z+5]  ->  D+z at the 4 cells
+__device__ __forceinline__ void dz_plus4(const F4 &A, const F4 &B, const F4 &C, float rh, float *out) {
+  const float u[7] = {A.v[3], B.v[0], B.v[1], B.v[2], B.v[3], C.v[0], C.v[1]};
+#pragma unroll
+  for (int k = 0; k < 4; k++) out[k] = (C1 * (u[k + 2] - u[k + 1]) - C2 * (u[k + 3] - u[k])) * rh;
+}
+// columns x-2, x-1, x, x+1 -> D-x ;  columns x-1, x, x+1, x+2 -> D+x   (same expression shape)
+__device__ __forceinline__ void dx4(const F4 &m2, const F4 &m1, const F4 &c0, const F4 &p1, float rh, float *out) {
+#pragma unroll
+  for (int k = 0; k < 4; k++) out[k] = (C1 * (c0.v[k] - m1.v[k]) - C2 * (p1.v[k] - m2.v[k])) * rh;
+}
+
+constexpr int QS = (TILE_Z + 8) / 4;      // 16 quads: sigma-tile rows z0-4 .. z0+TILE_Z+3
+constexpr int QV = (TILE_Z + 16) / 4;     // 18 quads: velocity-tile rows z0-8 .. z0+TILE_Z+7
+constexpr int VP = QV * 4, SP = QS * 4;   // row pitches (floats)
+constexpr int VC = TILE_X + 6, SC = TILE_X + 4;
+constexpr size_t FWD_SMEM = (size_t)(2 * VC * VP + 3 * SC * SP) * sizeof(float);
+static_assert(TILE_Z % 4 == 0 && QS == 16, "half-warp per sigma column");
 
 template <bool SAVE>
 __global__ void __launch_bounds__(NTHREADS) fwd_step_kernel(const __grid_constant__ FwdArgs a) {
-  extern __shared__ float smem[];
+  extern __shared__ __align__(16) float smem[];
   float *s_vz = smem;
-  float *s_vx = s_vz + FV_Z * FV_X;
-  float *s_zz = s_vx + FV_Z * FV_X;
-  float *s_xx = s_zz + FS_Z * FS_X;
-  float *s_xz = s_xx + FS_Z * FS_X;
+  float *s_vx = s_vz + VC * VP;
+  float *s_zz = s_vx + VC * VP;
+  float *s_xx = s_zz + SC * SP;
+  float *s_xz = s_xx + SC * SP;
   const Grid &g = a.g;
   const int tid = threadIdx.x;
   const int shot = blockIdx.x % a.batch;
@@ -112,36 +152,32 @@ __global__ void __launch_bounds__(NTHREADS) fwd_step_kernel(const __grid_constan
   const int r0 = a.st.rec_ptr[shot * (ntiles + 1) + tile];
   const int r1 = a.st.rec_ptr[shot * (ntiles + 1) + tile + 1];
   const int sz = a.st.src_z[shot], sx = a.st.src_x[shot];
-  const bool src_here = sz >= z0 - 2 && sz < z0 + TILE_Z + 2 && sx >= x0 - 2 && sx < x0 + TILE_X + 2;
-  if (z0 - 2 > g.az_hi && r1 == r0 && !src_here) return;  // nothing ever changes in this tile
+  const bool src_here = sz >= z0 - 4 && sz < z0 + TILE_Z + 4 && sx >= x0 - 2 && sx < x0 + TILE_X + 2;
+  if (z0 - 4 > g.az_hi && r1 == r0 && !src_here) return;  // nothing ever changes in this tile
 
-  const int fin = a.cur ? S_FB : S_FA, fout = a.cur ? S_FA : S_FB;
-  const int pin = a.cur ? S_PSI_B : S_PSI_A, pout = a.cur ? S_PSI_A : S_PSI_B;
-  const float *vz_i = plane_of(a.state, g, shot, fin + F_VZ);
-  const float *vx_i = plane_of(a.state, g, shot, fin + F_VX);
-  const float *szz_i = plane_of(a.state, g, shot, fin + F_SZZ);
-  const float *sxx_i = plane_of(a.state, g, shot, fin + F_SXX);
-  const float *sxz_i = plane_of(a.state, g, shot, fin + F_SXZ);
-  float *vz_o = plane_of(a.state, g, shot, fout + F_VZ);
-  float *vx_o = plane_of(a.state, g, shot, fout + F_VX);
-  float *szz_o = plane_of(a.state, g, shot, fout + F_SZZ);
-  float *sxx_o = plane_of(a.state, g, shot, fout + F_SXX);
-  float *sxz_o = plane_of(a.state, g, shot, fout + F_SXZ);
   const int P = g.P;
   const int xmax = g.nx + XM - 1;
   const float dt = g.dt, rdz = g.rdz, rdx = g.rdx;
+  float *sbase = a.state + (long long)shot * S_COUNT * g.plane + g.origin;
+  const long long pl = g.plane;
+  const int fin = a.cur ? S_FB : S_FA, fout = a.cur ? S_FA : S_FB;
+  const int pin = a.cur ? S_PSI_B : S_PSI_A, pout = a.cur ? S_PSI_A : S_PSI_B;
+  const float *fi = sbase + fin * pl;
+  float *fo = sbase + fout * pl;
 
-  // ---- phase 1: velocity tile with halo 3 -> shared ----
-  for (int i = tid; i < FV_Z * FV_X; i += NTHREADS) {
-    const int lx = i / FV_Z, lz = i - lx * FV_Z;
-    const int gx = min(x0 - 3 + lx, xmax);
-    const long long off = (long long)gx * P + (z0 - 3 + lz);
-    s_vz[i] = vz_i[off];
-    s_vx[i] = vx_i[off];
+  // ---- phase 1: velocity tile (18 quads x 38 columns) -> shared, asynchronously ----
+  for (int i = tid; i < VC * QV; i += NTHREADS) {
+    const int col = i / QV, q = i - col * QV;
+    const int gx = min(x0 - 3 + col, xmax);
+    const int off = gx * P + (z0 - 8 + 4 * q);
+    cp_async16(s_vz + col * VP + 4 * q, fi + F_VZ * pl + off);
+    cp_async16(s_vx + col * VP + 4 * q, fi + F_VX * pl + off);
   }
+  cp_async_wait_all();
   __syncthreads();
 
-  const bool pml_tile = (z0 - 2 < g.nPml) || (z0 + TILE_Z + 1 > g.nz - g.nPml - g.nPad - 1) || (x0 - 2 < g.nPml) ||
+  const int zp_hi = g.nz - g.nPml - g.nPad - 1;  // z > zp_hi is bottom PML
+  const bool pml_tile = (z0 - 4 < g.nPml) || (z0 + TILE_Z + 3 > zp_hi) || (x0 - 2 < g.nPml) ||
                         (x0 + TILE_X + 1 > g.nx - g.nPml - 1);
   bool frame_tile = false;
   float *frm = nullptr;
@@ -150,73 +186,112 @@ __global__ void __launch_bounds__(NTHREADS) fwd_step_kernel(const __grid_constan
                  !(z0 > g.zlo + 2 && z0 + TILE_Z - 1 < g.zhi - 2 && x0 > g.xlo + 2 && x0 + TILE_X - 1 < g.xhi - 2);
     frm = a.frames + ((long long)shot * g.nSteps + a.it) * 5 * g.f_len;
   }
+  const int h = tid >> 4, q = tid & 15;
 
-  // ---- phase 2: stress on the tile + halo 2 ----
-  for (int i = tid; i < FS_Z * FS_X; i += NTHREADS) {
-    const int lx = i / FS_Z, lz = i - lx * FS_Z;
-    const int gz = z0 - 2 + lz, gx = x0 - 2 + lx;
-    const long long off = (long long)min(gx, xmax) * P + gz;
-    float szz = szz_i[off], sxx = sxx_i[off], sxz = sxz_i[off];
-    const bool owner = lz >= 2 && lz < TILE_Z + 2 && lx >= 2 && lx < TILE_X + 2 && gz < g.nz && gx < g.nx;
-    const float *pz = s_vz + (lx + 1) * FV_Z + (lz + 1);
-    const float *px = s_vx + (lx + 1) * FV_Z + (lz + 1);
-    if (SAVE && frame_tile && owner) {
-      const int fi = frame_index(g, gz, gx);
-      if (fi >= 0) {
-        frm[F_SZZ * g.f_len + fi] = szz;
-        frm[F_SXX * g.f_len + fi] = sxx;
-        frm[F_SXZ * g.f_len + fi] = sxz;
-        frm[F_VZ * g.f_len + fi] = pz[0];
-        frm[F_VX * g.f_len + fi] = px[0];
-      }
-    }
-    if (is_active(g, gz, gx)) {
-      float dvz_dz = d_minus(pz, 1, rdz);
-      float dvx_dx = d_minus(px, FV_Z, rdx);
-      float dvx_dz = d_plus(px, 1, rdz);
-      float dvz_dx = d_plus(pz, FV_Z, rdx);
-      if (pml_tile) {
-        if (z_in_pml(g, gz)) {
-          const float *zp = a.pr.z + gz;
-          float m = zp[PR_B * P] * plane_of(a.state, g, shot, pin + PSI_VZ_Z)[off] + zp[PR_A * P] * dvz_dz;
-          dvz_dz = dvz_dz * zp[PR_RK * P] + m;
-          float mh = zp[PR_BH * P] * plane_of(a.state, g, shot, pin + PSI_VX_Z)[off] + zp[PR_AH * P] * dvx_dz;
-          dvx_dz = dvx_dz * zp[PR_RKH * P] + mh;
-          if (owner) {
-            plane_of(a.state, g, shot, pout + PSI_VZ_Z)[off] = m;
-            plane_of(a.state, g, shot, pout + PSI_VX_Z)[off] = mh;
-          }
-        }
-        if (x_in_pml_s(g, gx)) {
-          const float *xp = a.pr.x + gx + XM;
-          const int n = a.pr.nxp;
-          float m = xp[PR_B * n] * plane_of(a.state, g, shot, pin + PSI_VX_X)[off] + xp[PR_A * n] * dvx_dx;
-          dvx_dx = dvx_dx * xp[PR_RK * n] + m;
-          float mh = xp[PR_BH * n] * plane_of(a.state, g, shot, pin + PSI_VZ_X)[off] + xp[PR_AH * n] * dvz_dx;
-          dvz_dx = dvz_dx * xp[PR_RKH * n] + mh;
-          if (owner) {
-            plane_of(a.state, g, shot, pout + PSI_VX_X)[off] = m;
-            plane_of(a.state, g, shot, pout + PSI_VZ_X)[off] = mh;
+  // ---- phase 2: stress on 16 quads x 36 columns ----
+  {
+    const int gz = z0 - 4 + 4 * q;
+    for (int c = h; c < SC; c += NTHREADS / 16) {
+      const int gx = x0 - 2 + c;
+      const int off = min(gx, xmax) * P + gz;
+      const float *vzc = s_vz + (c + 1) * VP + 4 * (q + 1);
+      const float *vxc = s_vx + (c + 1) * VP + 4 * (q + 1);
+      float dvz_dz[4], dvx_dz[4], dvx_dx[4], dvz_dx[4];
+      const F4 zB = ld4(vzc), xB = ld4(vxc);
+      dz_minus4(ld4(vzc - 4), zB, ld4(vzc + 4), rdz, dvz_dz);
+      dz_plus4(ld4(vxc - 4), xB, ld4(vxc + 4), rdz, dvx_dz);
+      // the outermost halo columns only need one of the two x-derivatives; keep their reads inside the tile
+      dx4(ld4(vxc - (c > 0 ? 2 : 1) * VP), ld4(vxc - VP), xB, ld4(vxc + VP), rdx, dvx_dx);
+      dx4(ld4(vzc - VP), zB, ld4(vzc + VP), ld4(vzc + (c < SC - 1 ? 2 : 1) * VP), rdx, dvz_dx);
+      F4 szz = ld4(fi + F_SZZ * pl + off), sxx = ld4(fi + F_SXX * pl + off), sxz = ld4(fi + F_SXZ * pl + off);
+      const bool owner = q >= 1 && q <= TILE_Z / 4 && c >= 2 && c < TILE_X + 2 && gx < g.nx && gz < g.nz;
+      if (SAVE && frame_tile && owner) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const int fidx = frame_index(g, gz + k, gx);
+          if (fidx >= 0) {
+            frm[F_SZZ * g.f_len + fidx] = szz.v[k];
+            frm[F_SXX * g.f_len + fidx] = sxx.v[k];
+            frm[F_SXZ * g.f_len + fidx] = sxz.v[k];
+            frm[F_VZ * g.f_len + fidx] = zB.v[k];
+            frm[F_VX * g.f_len + fidx] = xB.v[k];
           }
         }
       }
-      const float lam = a.m.lam[off], mu = a.m.mu[off], amu = a.m.amu[off];
-      szz = stress_inc(szz, lam, mu, dvz_dz, dvx_dx, dt, 1.0f);
-      sxx = stress_inc(sxx, lam, mu, dvx_dx, dvz_dz, dt, 1.0f);
-      sxz = sxz + amu * (dvx_dz + dvz_dx) * dt;
-    }
-    if (gz == sz && gx == sx) {  // add_source (utilities.cu:521-537), point stamp
-      const float amp = a.st.stf[shot * g.nSteps + a.it];
-      szz += SRC_SCALE * amp * dt;
-      sxx = (float)((double)sxx + 3.0 * (double)SRC_SCALE * (double)amp * (double)dt);
-    }
-    s_zz[i] = szz;
-    s_xx[i] = sxx;
-    s_xz[i] = sxz;
-    if (owner) {
-      szz_o[off] = szz;
-      sxx_o[off] = sxx;
-      sxz_o[off] = sxz;
+      const bool col_act = gx >= 2 && gx <= g.ax_hi;
+      if (col_act && gz + 3 >= 2 && gz <= g.az_hi) {
+        if (pml_tile) {
+          if (gz < g.nPml || gz + 3 > zp_hi) {  // quad touches the z-PML
+            F4 m1 = ld4(sbase + (pin + PSI_VZ_Z) * pl + off), m2 = ld4(sbase + (pin + PSI_VX_Z) * pl + off);
+            const int zc = min(gz, P - 4);
+            const F4 b = ld4(a.pr.z + PR_B * P + zc), aa = ld4(a.pr.z + PR_A * P + zc), rk = ld4(a.pr.z + PR_RK * P + zc);
+            const F4 bh = ld4(a.pr.z + PR_BH * P + zc), ah = ld4(a.pr.z + PR_AH * P + zc), rkh = ld4(a.pr.z + PR_RKH * P + zc);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+              const int z = gz + k;
+              if ((z < g.nPml || z > zp_hi) && z >= 2 && z <= g.az_hi) {
+                m1.v[k] = b.v[k] * m1.v[k] + aa.v[k] * dvz_dz[k];
+                dvz_dz[k] = dvz_dz[k] * rk.v[k] + m1.v[k];
+                m2.v[k] = bh.v[k] * m2.v[k] + ah.v[k] * dvx_dz[k];
+                dvx_dz[k] = dvx_dz[k] * rkh.v[k] + m2.v[k];
+              }
+            }
+            if (owner) {
+              st4(sbase + (pout + PSI_VZ_Z) * pl + off, m1);
+              st4(sbase + (pout + PSI_VX_Z) * pl + off, m2);
+            }
+          }
+          if (gx < g.nPml || gx > g.nx - g.nPml - 1) {  // column in the x-PML (stress flavour)
+            F4 m1 = ld4(sbase + (pin + PSI_VX_X) * pl + off), m2 = ld4(sbase + (pin + PSI_VZ_X) * pl + off);
+            const float *xp = a.pr.x + gx + XM;
+            const int n = a.pr.nxp;
+            const float b = xp[PR_B * n], aa = xp[PR_A * n], rk = xp[PR_RK * n];
+            const float bh = xp[PR_BH * n], ah = xp[PR_AH * n], rkh = xp[PR_RKH * n];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+              const int z = gz + k;
+              if (z >= 2 && z <= g.az_hi) {
+                m1.v[k] = b * m1.v[k] + aa * dvx_dx[k];
+                dvx_dx[k] = dvx_dx[k] * rk + m1.v[k];
+                m2.v[k] = bh * m2.v[k] + ah * dvz_dx[k];
+                dvz_dx[k] = dvz_dx[k] * rkh + m2.v[k];
+              }
+            }
+            if (owner) {
+              st4(sbase + (pout + PSI_VX_X) * pl + off, m1);
+              st4(sbase + (pout + PSI_VZ_X) * pl + off, m2);
+            }
+          }
+        }
+        const F4 lam = ld4(a.m.lam + off), mu = ld4(a.m.mu + off), amu = ld4(a.m.amu + off);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const int z = gz + k;
+          if (z >= 2 && z <= g.az_hi) {
+            szz.v[k] = stress_inc(szz.v[k], lam.v[k], mu.v[k], dvz_dz[k], dvx_dx[k], dt, 1.0f);
+            sxx.v[k] = stress_inc(sxx.v[k], lam.v[k], mu.v[k], dvx_dx[k], dvz_dz[k], dt, 1.0f);
+            sxz.v[k] = sxz.v[k] + amu.v[k] * (dvx_dz[k] + dvz_dx[k]) * dt;
+          }
+        }
+      }
+      if (gx == sx && sz >= gz && sz < gz + 4) {  // add_source (utilities.cu:521-537), point stamp
+        const float amp = a.st.stf[shot * g.nSteps + a.it];
+        const int k = sz - gz;
+#pragma unroll
+        for (int kk = 0; kk < 4; kk++)
+          if (kk == k) {
+            szz.v[kk] += SRC_SCALE * amp * dt;
+            sxx.v[kk] = (float)((double)sxx.v[kk] + 3.0 * (double)SRC_SCALE * (double)amp * (double)dt);
+          }
+      }
+      st4(s_zz + c * SP + 4 * q, szz);
+      st4(s_xx + c * SP + 4 * q, sxx);
+      st4(s_xz + c * SP + 4 * q, sxz);
+      if (owner) {
+        st4(fo + F_SZZ * pl + off, szz);
+        st4(fo + F_SXX * pl + off, sxx);
+        st4(fo + F_SXZ * pl + off, sxz);
+      }
     }
   }
   __syncthreads();
@@ -225,78 +300,103 @@ __global__ void __launch_bounds__(NTHREADS) fwd_step_kernel(const __grid_constan
   for (int k = r0 + tid; k < r1; k += NTHREADS) {
     const int loc = a.st.rec_loc[shot * a.st.nrp + k];
     const int lz = loc & 0xffff, lx = loc >> 16;
-    const int j = (lx + 2) * FS_Z + lz + 2;
+    const int j = (lx + 2) * SP + lz + 4;
     a.traces[((long long)shot * g.nSteps + a.it + 1) * a.st.nrp + a.st.rec_id[shot * a.st.nrp + k]] =
         (float)((double)s_zz[j] + 3.0 * (double)s_xx[j]);
   }
 
-  // ---- phase 3: velocity on the owner tile ----
-  for (int i = tid; i < TILE_Z * TILE_X; i += NTHREADS) {
-    const int lx = i / TILE_Z, lz = i - lx * TILE_Z;
-    const int gz = z0 + lz, gx = x0 + lx;
-    if (gz >= g.nz || gx >= g.nx) continue;
-    const long long off = (long long)gx * P + gz;
-    float vz = s_vz[(lx + 3) * FV_Z + lz + 3], vx = s_vx[(lx + 3) * FV_Z + lz + 3];
-    if (is_active(g, gz, gx)) {
-      const float *zz = s_zz + (lx + 2) * FS_Z + lz + 2;
-      const float *xx = s_xx + (lx + 2) * FS_Z + lz + 2;
-      const float *xz = s_xz + (lx + 2) * FS_Z + lz + 2;
-      float dszz_dz = d_plus(zz, 1, rdz);
-      float dsxz_dx = d_minus(xz, FS_Z, rdx);
-      float dsxz_dz = d_minus(xz, 1, rdz);
-      float dsxx_dx = d_plus(xx, FS_Z, rdx);
-      if (pml_tile) {
-        if (z_in_pml(g, gz)) {
-          const float *zp = a.pr.z + gz;
-          float *q1 = plane_of(a.state, g, shot, S_PHI_A + PHI_SZZ_Z) + off;
-          float *q2 = plane_of(a.state, g, shot, S_PHI_A + PHI_SXZ_Z) + off;
-          float m = zp[PR_BH * P] * (*q1) + zp[PR_AH * P] * dszz_dz;
-          *q1 = m;
-          dszz_dz = dszz_dz * zp[PR_RKH * P] + m;
-          float m2 = zp[PR_B * P] * (*q2) + zp[PR_A * P] * dsxz_dz;
-          *q2 = m2;
-          dsxz_dz = dsxz_dz * zp[PR_RK * P] + m2;
+  // ---- phase 3: velocity on 14 quads x 32 columns ----
+  if (q < TILE_Z / 4) {
+    const int gz = z0 + 4 * q;
+    for (int c = h; c < TILE_X; c += NTHREADS / 16) {
+      const int gx = x0 + c;
+      if (gx >= g.nx || gz >= g.nz) continue;
+      const int off = gx * P + gz;
+      const float *zz = s_zz + (c + 2) * SP + 4 * (q + 1);
+      const float *xx = s_xx + (c + 2) * SP + 4 * (q + 1);
+      const float *xz = s_xz + (c + 2) * SP + 4 * (q + 1);
+      F4 vz = ld4(s_vz + (c + 3) * VP + 4 * (q + 2)), vx = ld4(s_vx + (c + 3) * VP + 4 * (q + 2));
+      if (gx >= 2 && gx <= g.ax_hi && gz + 3 >= 2 && gz <= g.az_hi) {
+        float dszz_dz[4], dsxz_dz[4], dsxz_dx[4], dsxx_dx[4];
+        const F4 xzB = ld4(xz);
+        dz_plus4(ld4(zz - 4), ld4(zz), ld4(zz + 4), rdz, dszz_dz);
+        dz_minus4(ld4(xz - 4), xzB, ld4(xz + 4), rdz, dsxz_dz);
+        dx4(ld4(xz - 2 * SP), ld4(xz - SP), xzB, ld4(xz + SP), rdx, dsxz_dx);
+        dx4(ld4(xx - SP), ld4(xx), ld4(xx + SP), ld4(xx + 2 * SP), rdx, dsxx_dx);
+        if (pml_tile) {
+          if (gz < g.nPml || gz + 3 > zp_hi) {
+            float *q1 = sbase + (S_PHI_A + PHI_SZZ_Z) * pl + off, *q2 = sbase + (S_PHI_A + PHI_SXZ_Z) * pl + off;
+            F4 m1 = ld4(q1), m2 = ld4(q2);
+            const int zc = min(gz, P - 4);
+            const F4 b = ld4(a.pr.z + PR_B * P + zc), aa = ld4(a.pr.z + PR_A * P + zc), rk = ld4(a.pr.z + PR_RK * P + zc);
+            const F4 bh = ld4(a.pr.z + PR_BH * P + zc), ah = ld4(a.pr.z + PR_AH * P + zc), rkh = ld4(a.pr.z + PR_RKH * P + zc);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+              const int z = gz + k;
+              if ((z < g.nPml || z > zp_hi) && z >= 2 && z <= g.az_hi) {
+                m1.v[k] = bh.v[k] * m1.v[k] + ah.v[k] * dszz_dz[k];
+                dszz_dz[k] = dszz_dz[k] * rkh.v[k] + m1.v[k];
+                m2.v[k] = b.v[k] * m2.v[k] + aa.v[k] * dsxz_dz[k];
+                dsxz_dz[k] = dsxz_dz[k] * rk.v[k] + m2.v[k];
+              }
+            }
+            st4(q1, m1);
+            st4(q2, m2);
+          }
+          if (gx < g.nPml || gx > g.nx - g.nPml) {  // velocity flavour of the x-PML test (el_velocity.cu:56)
+            float *q1 = sbase + (S_PHI_A + PHI_SXZ_X) * pl + off, *q2 = sbase + (S_PHI_A + PHI_SXX_X) * pl + off;
+            F4 m1 = ld4(q1), m2 = ld4(q2);
+            const float *xp = a.pr.x + gx + XM;
+            const int n = a.pr.nxp;
+            const float b = xp[PR_B * n], aa = xp[PR_A * n], rk = xp[PR_RK * n];
+            const float bh = xp[PR_BH * n], ah = xp[PR_AH * n], rkh = xp[PR_RKH * n];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+              const int z = gz + k;
+              if (z >= 2 && z <= g.az_hi) {
+                m1.v[k] = b * m1.v[k] + aa * dsxz_dx[k];
+                dsxz_dx[k] = dsxz_dx[k] * rk + m1.v[k];
+                m2.v[k] = bh * m2.v[k] + ah * dsxx_dx[k];
+                dsxx_dx[k] = dsxx_dx[k] * rkh + m2.v[k];
+              }
+            }
+            st4(q1, m1);
+            st4(q2, m2);
+          }
         }
-        if (x_in_pml_v(g, gx)) {
-          const float *xp = a.pr.x + gx + XM;
-          const int n = a.pr.nxp;
-          float *q1 = plane_of(a.state, g, shot, S_PHI_A + PHI_SXZ_X) + off;
-          float *q2 = plane_of(a.state, g, shot, S_PHI_A + PHI_SXX_X) + off;
-          float m = xp[PR_B * n] * (*q1) + xp[PR_A * n] * dsxz_dx;
-          *q1 = m;
-          dsxz_dx = dsxz_dx * xp[PR_RK * n] + m;
-          float m2 = xp[PR_BH * n] * (*q2) + xp[PR_AH * n] * dsxx_dx;
-          *q2 = m2;
-          dsxx_dx = dsxx_dx * xp[PR_RKH * n] + m2;
+        const F4 bya = ld4(a.m.bya + off), byb = ld4(a.m.byb + off);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const int z = gz + k;
+          if (z >= 2 && z <= g.az_hi) {
+            vz.v[k] += (dszz_dz[k] + dsxz_dx[k]) * bya.v[k] * dt;
+            vx.v[k] += (dsxz_dz[k] + dsxx_dx[k]) * byb.v[k] * dt;
+          }
         }
       }
-      vz += (dszz_dz + dsxz_dx) * a.m.bya[off] * dt;
-      vx += (dsxz_dz + dsxx_dx) * a.m.byb[off] * dt;
+      st4(fo + F_VZ * pl + off, vz);
+      st4(fo + F_VX * pl + off, vx);
     }
-    vz_o[off] = vz;
-    vx_o[off] = vx;
   }
 }
 
 // =================================================================================================
-// reverse-time reconstruction + imaging condition
+// reverse-time reconstruction + imaging.  The imaging condition only ACCUMULATES the
+// per-cell source terms (5 planes: lambda, mu-direct, mu-spray amplitude S, rho-a, rho-b); the
+// reference's 4-point "spray" (el_stress.cu:113-124, el_velocity.cu:101-110) is linear in those, so it
+// is applied once, as a deterministic gather, by finalize_kernel.
 // =================================================================================================
-constexpr int RS_Z = TILE_Z + 8, RS_X = TILE_X + 8;  // sigma^{it+1} tile (halo 4)
-constexpr int RV_Z = TILE_Z + 4, RV_X = TILE_X + 4;  // v^{it}, ga, gb tile (halo 2)
-constexpr int RG_Z = TILE_Z + 1, RG_X = TILE_X + 1;  // mu-spray tile (halo 1 on the low side)
-constexpr size_t REV_SMEM = (size_t)(3 * RS_Z * RS_X + 4 * RV_Z * RV_X + RG_Z * RG_X) * sizeof(float);
+constexpr int RC = TILE_X + 8;  // sigma^{it+1} tile columns (halo 4), rows as the velocity tile (QV quads)
+constexpr size_t REV_SMEM = (size_t)(3 * RC * VP + 2 * SC * SP) * sizeof(float);
 
 __global__ void __launch_bounds__(NTHREADS) rev_image_kernel(const __grid_constant__ BwdArgs a, int tz_first,
-                                                             int tx_first, int ntz) {
-  extern __shared__ float smem[];
+                                                               int tx_first, int ntz) {
+  extern __shared__ __align__(16) float smem[];
   float *s_zz = smem;
-  float *s_xx = s_zz + RS_Z * RS_X;
-  float *s_xz = s_xx + RS_Z * RS_X;
-  float *s_vz = s_xz + RS_Z * RS_X;
-  float *s_vx = s_vz + RV_Z * RV_X;
-  float *s_ga = s_vx + RV_Z * RV_X;
-  float *s_gb = s_ga + RV_Z * RV_X;
-  float *s_sp = s_gb + RV_Z * RV_X;
+  float *s_xx = s_zz + RC * VP;
+  float *s_xz = s_xx + RC * VP;
+  float *s_vz = s_xz + RC * VP;
+  float *s_vx = s_vz + SC * SP;
   const Grid &g = a.g;
   const int tid = threadIdx.x;
   const int shot = blockIdx.x % a.batch;
@@ -306,172 +406,178 @@ __global__ void __launch_bounds__(NTHREADS) rev_image_kernel(const __grid_consta
   const int P = g.P;
   const int xmax = g.nx + XM - 1;
   const float dt = g.dt, rdz = g.rdz, rdx = g.rdx;
-  const int fin = a.cur_f ? S_FB : S_FA, fout = a.cur_f ? S_FA : S_FB;
-  const int ain = a.cur_a ? S_AB : S_AA;
-  const float *szz_i = plane_of(a.state, g, shot, fin + F_SZZ);
-  const float *sxx_i = plane_of(a.state, g, shot, fin + F_SXX);
-  const float *sxz_i = plane_of(a.state, g, shot, fin + F_SXZ);
-  const float *vz_i = plane_of(a.state, g, shot, fin + F_VZ);
-  const float *vx_i = plane_of(a.state, g, shot, fin + F_VX);
+  const long long pl = g.plane;
+  float *sbase = a.state + (long long)shot * S_COUNT * pl + g.origin;
+  const float *fi = sbase + (a.cur_f ? S_FB : S_FA) * pl;
+  float *fo = sbase + (a.cur_f ? S_FA : S_FB) * pl;
+  const float *ai = sbase + (a.cur_a ? S_AB : S_AA) * pl;
+  float *acc = a.gacc + (long long)shot * G_COUNT * pl + g.origin;
   const float *frm = a.frames + ((long long)shot * g.nSteps + a.it) * 5 * g.f_len;
   const int sz = a.st.src_z[shot], sx = a.st.src_x[shot];
 
-  // ---- phase 1: sigma^{it+1} with halo 4 ----
-  for (int i = tid; i < RS_Z * RS_X; i += NTHREADS) {
-    const int lx = i / RS_Z, lz = i - lx * RS_Z;
-    const int gx = min(x0 - 4 + lx, xmax);
-    const long long off = (long long)gx * P + (z0 - 4 + lz);
-    s_zz[i] = szz_i[off];
-    s_xx[i] = sxx_i[off];
-    s_xz[i] = sxz_i[off];
+  // ---- phase 1: sigma^{it+1}, 18 quads x 40 columns ----
+  for (int i = tid; i < RC * QV; i += NTHREADS) {
+    const int col = i / QV, q = i - col * QV;
+    const int gx = min(x0 - 4 + col, xmax);
+    const int off = gx * P + (z0 - 8 + 4 * q);
+    cp_async16(s_zz + col * VP + 4 * q, fi + F_SZZ * pl + off);
+    cp_async16(s_xx + col * VP + 4 * q, fi + F_SXX * pl + off);
+    cp_async16(s_xz + col * VP + 4 * q, fi + F_SXZ * pl + off);
   }
+  cp_async_wait_all();
   __syncthreads();
 
-  // does this tile (+halo 2) touch the saved frames?
   const bool frame_tile =
-      !(z0 - 2 > g.zlo + 2 && z0 + TILE_Z + 1 < g.zhi - 2 && x0 - 2 > g.xlo + 2 && x0 + TILE_X + 1 < g.xhi - 2);
+      !(z0 - 4 > g.zlo + 2 && z0 + TILE_Z + 3 < g.zhi - 2 && x0 - 2 > g.xlo + 2 && x0 + TILE_X + 1 < g.xhi - 2);
+  const int h = tid >> 4, q = tid & 15;
 
-  // ---- phase 2: v^{it} on tile + halo 2, density imaging terms ----
+  // ---- phase 2: v^{it} on 16 quads x 36 columns; rho imaging terms on the owner cells ----
   {
-    const float *vza = plane_of(a.state, g, shot, ain + F_VZ);
-    const float *vxa = plane_of(a.state, g, shot, ain + F_VX);
-    float *vz_o = plane_of(a.state, g, shot, fout + F_VZ);
-    float *vx_o = plane_of(a.state, g, shot, fout + F_VX);
-    for (int i = tid; i < RV_Z * RV_X; i += NTHREADS) {
-      const int lx = i / RV_Z, lz = i - lx * RV_Z;
-      const int gz = z0 - 2 + lz, gx = x0 - 2 + lx;
-      const long long off = (long long)min(gx, xmax) * P + gz;
-      float vz = vz_i[off], vx = vx_i[off];
-      float ga = 0.0f, gb = 0.0f;
-      const bool box = in_box(g, gz, gx);
-      if (box) {
-        const float *zz = s_zz + (lx + 2) * RS_Z + lz + 2;
-        const float *xx = s_xx + (lx + 2) * RS_Z + lz + 2;
-        const float *xz = s_xz + (lx + 2) * RS_Z + lz + 2;
-        const float ea = d_plus(zz, 1, rdz) + d_minus(xz, RS_Z, rdx);
-        const float eb = d_minus(xz, 1, rdz) + d_plus(xx, RS_Z, rdx);
-        const float bya = a.m.bya[off], byb = a.m.byb[off];
-        vz -= ea * bya * dt;
-        vx -= eb * byb * dt;
-        // el_velocity.cu:101-104
-        ga = (float)((double)(-vza[off] * ea * dt) * (-((double)bya * (double)bya) / 2.0));
-        gb = (float)((double)(-vxa[off] * eb * dt) * (-((double)byb * (double)byb) / 2.0));
-      }
-      int fi = -1;
-      if (frame_tile) {
-        fi = frame_index(g, gz, gx);
-        if (fi >= 0) {
-          vz = frm[F_VZ * g.f_len + fi];
-          vx = frm[F_VX * g.f_len + fi];
+    const int gz = z0 - 4 + 4 * q;
+    for (int c = h; c < SC; c += NTHREADS / 16) {
+      const int gx = x0 - 2 + c;
+      const int off = min(gx, xmax) * P + gz;
+      F4 vz = ld4(fi + F_VZ * pl + off), vx = ld4(fi + F_VX * pl + off);
+      const bool owner = q >= 1 && q <= TILE_Z / 4 && c >= 2 && c < TILE_X + 2 && gx < g.nx && gz < g.nz;
+      const bool colbox = gx >= g.xlo && gx <= g.xhi;
+      if (colbox && gz + 3 >= g.zlo && gz <= g.zhi) {
+        const float *zz = s_zz + (c + 2) * VP + 4 * (q + 1);
+        const float *xx = s_xx + (c + 2) * VP + 4 * (q + 1);
+        const float *xz = s_xz + (c + 2) * VP + 4 * (q + 1);
+        float d1[4], d2[4], d3[4], d4[4];
+        const F4 xzB = ld4(xz);
+        dz_plus4(ld4(zz - 4), ld4(zz), ld4(zz + 4), rdz, d1);             // dszz_dz
+        dx4(ld4(xz - 2 * VP), ld4(xz - VP), xzB, ld4(xz + VP), rdx, d2);  // dsxz_dx
+        dz_minus4(ld4(xz - 4), xzB, ld4(xz + 4), rdz, d3);                // dsxz_dz
+        dx4(ld4(xx - VP), ld4(xx), ld4(xx + VP), ld4(xx + 2 * VP), rdx, d4);  // dsxx_dx
+        const F4 bya = ld4(a.m.bya + off), byb = ld4(a.m.byb + off);
+        F4 ga{{0, 0, 0, 0}}, gb{{0, 0, 0, 0}};
+        F4 vza{{0, 0, 0, 0}}, vxa{{0, 0, 0, 0}};
+        if (owner) {
+          vza = ld4(ai + F_VZ * pl + off);
+          vxa = ld4(ai + F_VX * pl + off);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const int z = gz + k;
+          if (z >= g.zlo && z <= g.zhi) {
+            const float ea = d1[k] + d2[k], eb = d3[k] + d4[k];
+            vz.v[k] -= ea * bya.v[k] * dt;
+            vx.v[k] -= eb * byb.v[k] * dt;
+            // el_velocity.cu:101-104
+#if FWI_FP64_PROMOTE
+            ga.v[k] = (float)((double)(-vza.v[k] * ea * dt) * (-((double)bya.v[k] * (double)bya.v[k]) / 2.0));
+            gb.v[k] = (float)((double)(-vxa.v[k] * eb * dt) * (-((double)byb.v[k] * (double)byb.v[k]) / 2.0));
+#else
+            ga.v[k] = (vza.v[k] * ea * dt) * (0.5f * bya.v[k] * bya.v[k]);
+            gb.v[k] = (vxa.v[k] * eb * dt) * (0.5f * byb.v[k] * byb.v[k]);
+#endif
+          }
+        }
+        if (owner) {
+          float *pa = acc + G_RHO_A * pl + off, *pb = acc + G_RHO_B * pl + off;
+          F4 A = ld4(pa), B = ld4(pb);
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            A.v[k] += ga.v[k];
+            B.v[k] += gb.v[k];
+          }
+          st4(pa, A);
+          st4(pb, B);
         }
       }
-      s_vz[i] = vz;
-      s_vx[i] = vx;
-      s_ga[i] = ga;
-      s_gb[i] = gb;
-      const bool owner = lz >= 2 && lz < TILE_Z + 2 && lx >= 2 && lx < TILE_X + 2;
-      if (owner && (box || fi >= 0)) {
-        vz_o[off] = vz;
-        vx_o[off] = vx;
+      bool in_rect = gx >= g.xlo - 2 && gx <= g.xhi + 2 && gz + 3 >= g.zlo - 2 && gz <= g.zhi + 2;
+      if (frame_tile && in_rect) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const int fidx = frame_index(g, gz + k, gx);
+          if (fidx >= 0) {
+            vz.v[k] = frm[F_VZ * g.f_len + fidx];
+            vx.v[k] = frm[F_VX * g.f_len + fidx];
+          }
+        }
+      }
+      st4(s_vz + c * SP + 4 * q, vz);
+      st4(s_vx + c * SP + 4 * q, vx);
+      if (owner && in_rect) {
+        st4(fo + F_VZ * pl + off, vz);
+        st4(fo + F_VX * pl + off, vx);
       }
     }
   }
   __syncthreads();
 
-  // ---- phase 3a: mu "spray" amplitude of every source cell on [z0-1, z0+TZ) x [x0-1, x0+TX) ----
-  {
-    const float *sxza = plane_of(a.state, g, shot, ain + F_SXZ);
-    for (int i = tid; i < RG_Z * RG_X; i += NTHREADS) {
-      const int lx = i / RG_Z, lz = i - lx * RG_Z;
-      const int gz = z0 - 1 + lz, gx = x0 - 1 + lx;
-      float sp = 0.0f;
-      if (in_box(g, gz, gx)) {
-        const long long off = (long long)gx * P + gz;
-        const float amu = a.m.amu[off];
-        if (amu != 0.0f) {
-          const float *pz = s_vz + (lx + 1) * RV_Z + lz + 1;
-          const float *px = s_vx + (lx + 1) * RV_Z + lz + 1;
-          const float e = d_plus(px, 1, rdz) + d_plus(pz, RV_Z, rdx);
-          // el_stress.cu:114-116 with  amu / sum(1/mu) == amu^2 / 4  (amu = 4 / sum(1/mu))
-          sp = -sxza[off] * e * dt * (250000.0f * amu) * amu;
-        }
-      }
-      s_sp[i] = sp;
-    }
-  }
-  __syncthreads();
-
-  // ---- phase 3b: sigma^{it} on the owner tile, lambda / mu / rho accumulation (gather) ----
-  {
-    const float *szza = plane_of(a.state, g, shot, ain + F_SZZ);
-    const float *sxxa = plane_of(a.state, g, shot, ain + F_SXX);
-    float *szz_o = plane_of(a.state, g, shot, fout + F_SZZ);
-    float *sxx_o = plane_of(a.state, g, shot, fout + F_SXX);
-    float *sxz_o = plane_of(a.state, g, shot, fout + F_SXZ);
-    float *gl = a.gacc + ((long long)shot * 3 + 0) * g.plane + g.origin;
-    float *gm = a.gacc + ((long long)shot * 3 + 1) * g.plane + g.origin;
-    float *gd = a.gacc + ((long long)shot * 3 + 2) * g.plane + g.origin;
-    for (int i = tid; i < TILE_Z * TILE_X; i += NTHREADS) {
-      const int lx = i / TILE_Z, lz = i - lx * TILE_Z;
-      const int gz = z0 + lz, gx = x0 + lx;
-      if (gz >= g.nz || gx >= g.nx) continue;
-      const long long off = (long long)gx * P + gz;
-      const bool box = in_box(g, gz, gx);
-      int fi = frame_tile ? frame_index(g, gz, gx) : -1;
-      if (box) {
-        const float *pz = s_vz + (lx + 2) * RV_Z + lz + 2;
-        const float *px = s_vx + (lx + 2) * RV_Z + lz + 2;
-        const float dvz_dz = d_minus(pz, 1, rdz);
-        const float dvx_dx = d_minus(px, RV_Z, rdx);
-        const float dvx_dz = d_plus(px, 1, rdz);
-        const float dvz_dx = d_plus(pz, RV_Z, rdx);
-        const int j = (lx + 4) * RS_Z + lz + 4;
-        float szz = s_zz[j], sxx = s_xx[j], sxz = s_xz[j];
-        if (gz == sz && gx == sx) {  // add_source(isFor=false): utilities.cu:538-551
+  // ---- phase 3: sigma^{it} on 14 quads x 32 columns; lambda / mu imaging terms ----
+  if (q < TILE_Z / 4) {
+    const int gz = z0 + 4 * q;
+    for (int c = h; c < TILE_X; c += NTHREADS / 16) {
+      const int gx = x0 + c;
+      if (gx >= g.nx || gz >= g.nz) continue;
+      if (!(gx >= g.xlo - 2 && gx <= g.xhi + 2 && gz + 3 >= g.zlo - 2 && gz <= g.zhi + 2)) continue;
+      const int off = gx * P + gz;
+      const int j = (c + 4) * VP + 4 * (q + 2);
+      F4 szz = ld4(s_zz + j), sxx = ld4(s_xx + j), sxz = ld4(s_xz + j);
+      if (gx >= g.xlo && gx <= g.xhi && gz + 3 >= g.zlo && gz <= g.zhi) {
+        const float *pz = s_vz + (c + 2) * SP + 4 * (q + 1);
+        const float *px = s_vx + (c + 2) * SP + 4 * (q + 1);
+        float dvz_dz[4], dvx_dz[4], dvx_dx[4], dvz_dx[4];
+        const F4 zB = ld4(pz), xB = ld4(px);
+        dz_minus4(ld4(pz - 4), zB, ld4(pz + 4), rdz, dvz_dz);
+        dz_plus4(ld4(px - 4), xB, ld4(px + 4), rdz, dvx_dz);
+        dx4(ld4(px - 2 * SP), ld4(px - SP), xB, ld4(px + SP), rdx, dvx_dx);
+        dx4(ld4(pz - SP), zB, ld4(pz + SP), ld4(pz + 2 * SP), rdx, dvz_dx);
+        const F4 lam = ld4(a.m.lam + off), mu = ld4(a.m.mu + off), amu = ld4(a.m.amu + off);
+        const F4 za = ld4(ai + F_SZZ * pl + off), xa = ld4(ai + F_SXX * pl + off), xza = ld4(ai + F_SXZ * pl + off);
+        float *pgl = acc + G_LAM * pl + off, *pgm = acc + G_MU * pl + off, *pgs = acc + G_MUS * pl + off;
+        F4 gl = ld4(pgl), gm = ld4(pgm), gs = ld4(pgs);
+        if (gx == sx && sz >= gz && sz < gz + 4) {  // add_source(isFor=false): utilities.cu:538-551
           const float amp = a.st.stf[shot * g.nSteps + a.it];
-          szz -= SRC_SCALE * amp * dt;
-          sxx = (float)((double)sxx - 3.0 * (double)SRC_SCALE * (double)amp * (double)dt);
+#pragma unroll
+          for (int k = 0; k < 4; k++)
+            if (k == sz - gz) {
+              szz.v[k] -= SRC_SCALE * amp * dt;
+              sxx.v[k] = (float)((double)sxx.v[k] - 3.0 * (double)SRC_SCALE * (double)amp * (double)dt);
+            }
         }
-        const float lam = a.m.lam[off], mu = a.m.mu[off];
-        szz = stress_inc(szz, lam, mu, dvz_dz, dvx_dx, dt, -1.0f);
-        sxx = stress_inc(sxx, lam, mu, dvx_dx, dvz_dz, dt, -1.0f);
-        sxz -= a.m.amu[off] * (dvx_dz + dvz_dx) * dt;
-        if (fi >= 0) {
-          szz = frm[F_SZZ * g.f_len + fi];
-          sxx = frm[F_SXX * g.f_len + fi];
-          sxz = frm[F_SXZ * g.f_len + fi];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const int z = gz + k;
+          if (z >= g.zlo && z <= g.zhi) {
+            szz.v[k] = stress_inc(szz.v[k], lam.v[k], mu.v[k], dvz_dz[k], dvx_dx[k], dt, -1.0f);
+            sxx.v[k] = stress_inc(sxx.v[k], lam.v[k], mu.v[k], dvx_dx[k], dvz_dz[k], dt, -1.0f);
+            const float e = dvx_dz[k] + dvz_dx[k];
+            sxz.v[k] -= amu.v[k] * e * dt;
+            // el_stress.cu:109-116
+#if FWI_FP64_PROMOTE
+            gl.v[k] = (float)((double)gl.v[k] + (double)(-(za.v[k] + xa.v[k]) * (dvz_dz[k] + dvx_dx[k]) * dt) * 1e6);
+            gm.v[k] = (float)((double)gm.v[k] + (-2.0 * (double)za.v[k] * (double)dvz_dz[k] * (double)dt -
+                                                 2.0 * (double)xa.v[k] * (double)dvx_dx[k] * (double)dt) * 1e6);
+#else
+            gl.v[k] += -(za.v[k] + xa.v[k]) * (dvz_dz[k] + dvx_dx[k]) * dt * 1e6f;
+            gm.v[k] += (-2.0f * za.v[k] * dvz_dz[k] * dt - 2.0f * xa.v[k] * dvx_dx[k] * dt) * 1e6f;
+#endif
+            //  amu / sum(1/mu) == amu^2 / 4  (amu = 4 / sum(1/mu)); zero where amu == 0
+            gs.v[k] += -xza.v[k] * e * dt * (250000.0f * amu.v[k]) * amu.v[k];
+          }
         }
-        szz_o[off] = szz;
-        sxx_o[off] = sxx;
-        sxz_o[off] = sxz;
-        // el_stress.cu:109-111
-        const float za = szza[off], xa = sxxa[off];
-        gl[off] = (float)((double)gl[off] + (double)(-(za + xa) * (dvz_dz + dvx_dx) * dt) * 1e6);
-        const double gm_dir =
-            (-2.0 * (double)za * (double)dvz_dz * (double)dt - 2.0 * (double)xa * (double)dvx_dx * (double)dt) * 1e6;
-        float gmv = (float)((double)gm[off] + gm_dir);
-        const int q = (lx + 1) * RG_Z + lz + 1;
-        const float G = s_sp[q] + s_sp[q - 1] + s_sp[q - RG_Z] + s_sp[q - RG_Z - 1];
-        if (G != 0.0f) gmv += G / (mu * mu);
-        gm[off] = gmv;
-        const int v = (lx + 2) * RV_Z + lz + 2;
-        gd[off] += s_ga[v] + s_gb[v] + s_ga[v - 1] + s_gb[v - RV_Z];
-      } else {
-        if (fi >= 0) {
-          szz_o[off] = frm[F_SZZ * g.f_len + fi];
-          sxx_o[off] = frm[F_SXX * g.f_len + fi];
-          sxz_o[off] = frm[F_SXZ * g.f_len + fi];
-        }
-        // column xhi+1 receives the x+1 spray of the last box column (el_stress.cu:120, el_velocity.cu:109)
-        if (gx == g.xhi + 1 && gz >= g.zlo && gz <= g.zhi) {
-          const int q = (lx + 1) * RG_Z + lz + 1;
-          const float G = s_sp[q - RG_Z];
-          const float mu = a.m.mu[off];
-          if (G != 0.0f) gm[off] += G / (mu * mu);
-          const int v = (lx + 2) * RV_Z + lz + 2;
-          gd[off] += s_gb[v - RV_Z];
+        st4(pgl, gl);
+        st4(pgm, gm);
+        st4(pgs, gs);
+      }
+      if (frame_tile) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const int fidx = frame_index(g, gz + k, gx);
+          if (fidx >= 0) {
+            szz.v[k] = frm[F_SZZ * g.f_len + fidx];
+            sxx.v[k] = frm[F_SXX * g.f_len + fidx];
+            sxz.v[k] = frm[F_SXZ * g.f_len + fidx];
+          }
         }
       }
+      st4(fo + F_SZZ * pl + off, szz);
+      st4(fo + F_SXX * pl + off, sxx);
+      st4(fo + F_SXZ * pl + off, sxz);
     }
   }
 }
@@ -479,17 +585,31 @@ __global__ void __launch_bounds__(NTHREADS) rev_image_kernel(const __grid_consta
 // =================================================================================================
 // adjoint step
 // =================================================================================================
-constexpr int AS_Z = TILE_Z + 6, AS_X = TILE_X + 6;  // adjoint stress tile (halo 3)
-constexpr int AV_Z = TILE_Z + 4, AV_X = TILE_X + 4;  // adjoint velocity tile (halo 2)
-constexpr size_t ADJ_SMEM = (size_t)(3 * AS_Z * AS_X + 2 * AV_Z * AV_X) * sizeof(float);
+// adjoint-kernel spelling of the differences (el_stress_adj.cu:54-61): (-c1*(..) + c2*(..)) / h
+__device__ __forceinline__ void adz_minus4(const F4 &A, const F4 &B, const F4 &C, float rh, float *out) {
+  const float w[7] = {A.v[2], A.v[3], B.v[0], B.v[1], B.v[2], B.v[3], C.v[0]};
+#pragma unroll
+  for (int k = 0; k < 4; k++) out[k] = (-C1 * (w[k + 2] - w[k + 1]) + C2 * (w[k + 3] - w[k])) * rh;
+}
+__device__ __forceinline__ void adz_plus4(const F4 &A, const F4 &B, const F4 &C, float rh, float *out) {
+  const float u[7] = {A.v[3], B.v[0], B.v[1], B.v[2], B.v[3], C.v[0], C.v[1]};
+#pragma unroll
+  for (int k = 0; k < 4; k++) out[k] = (-C1 * (u[k + 2] - u[k + 1]) + C2 * (u[k + 3] - u[k])) * rh;
+}
+__device__ __forceinline__ void adx4(const F4 &m2, const F4 &m1, const F4 &c0, const F4 &p1, float rh, float *out) {
+#pragma unroll
+  for (int k = 0; k < 4; k++) out[k] = (-C1 * (c0.v[k] - m1.v[k]) + C2 * (p1.v[k] - m2.v[k])) * rh;
+}
+
+constexpr size_t ADJ_SMEM = (size_t)(3 * VC * VP + 2 * SC * SP) * sizeof(float);
 
 __global__ void __launch_bounds__(NTHREADS) adj_step_kernel(const __grid_constant__ BwdArgs a) {
-  extern __shared__ float smem[];
+  extern __shared__ __align__(16) float smem[];
   float *s_zz = smem;
-  float *s_xx = s_zz + AS_Z * AS_X;
-  float *s_xz = s_xx + AS_Z * AS_X;
-  float *s_vz = s_xz + AS_Z * AS_X;
-  float *s_vx = s_vz + AV_Z * AV_X;
+  float *s_xx = s_zz + VC * VP;
+  float *s_xz = s_xx + VC * VP;
+  float *s_vz = s_xz + VC * VP;
+  float *s_vx = s_vz + SC * SP;
   const Grid &g = a.g;
   const int tid = threadIdx.x;
   const int shot = blockIdx.x % a.batch;
@@ -501,124 +621,173 @@ __global__ void __launch_bounds__(NTHREADS) adj_step_kernel(const __grid_constan
   const int r1 = a.st.rec_ptr[shot * (ntiles + 1) + tile + 1];
   const int sz = a.st.src_z[shot], sx = a.st.src_x[shot];
   const bool src_owner = sz >= z0 && sz < z0 + TILE_Z && sx >= x0 && sx < x0 + TILE_X;
-  if (z0 - 2 > g.az_hi && r1 == r0 && !src_owner) return;
+  if (z0 - 4 > g.az_hi && r1 == r0 && !src_owner) return;
 
   const int P = g.P;
   const int xmax = g.nx + XM - 1;
   const float dt = g.dt, rdz = g.rdz, rdx = g.rdx;
-  const int ain = a.cur_a ? S_AB : S_AA, aout = a.cur_a ? S_AA : S_AB;
-  const int pin = a.cur_a ? S_PSI_B : S_PSI_A, pout = a.cur_a ? S_PSI_A : S_PSI_B;
-  const int qin = a.cur_a ? S_PHI_B : S_PHI_A, qout = a.cur_a ? S_PHI_A : S_PHI_B;
-  const float *szz_i = plane_of(a.state, g, shot, ain + F_SZZ);
-  const float *sxx_i = plane_of(a.state, g, shot, ain + F_SXX);
-  const float *sxz_i = plane_of(a.state, g, shot, ain + F_SXZ);
-  const float *vz_i = plane_of(a.state, g, shot, ain + F_VZ);
-  const float *vx_i = plane_of(a.state, g, shot, ain + F_VX);
+  const long long pl = g.plane;
+  float *sbase = a.state + (long long)shot * S_COUNT * pl + g.origin;
+  const float *ai = sbase + (a.cur_a ? S_AB : S_AA) * pl;
+  float *ao = sbase + (a.cur_a ? S_AA : S_AB) * pl;
+  const float *psi_i = sbase + (a.cur_a ? S_PSI_B : S_PSI_A) * pl;
+  float *psi_o = sbase + (a.cur_a ? S_PSI_A : S_PSI_B) * pl;
+  const float *phi_i = sbase + (a.cur_a ? S_PHI_B : S_PHI_A) * pl;
+  float *phi_o = sbase + (a.cur_a ? S_PHI_A : S_PHI_B) * pl;
   const int nxp = a.pr.nxp;
+  const int zp_hi = g.nz - g.nPml - g.nPad - 1;
 
   // source_grad (utilities.cu:582-593): adjoint stress at the source BEFORE this step's update
   if (src_owner && tid == 0) {
-    const long long off = (long long)sx * P + sz;
-    a.stf_grad[shot * g.nSteps + a.it] = (float)(-((double)szz_i[off] + 3.0 * (double)sxx_i[off]) * (double)dt);
+    const int off = sx * P + sz;
+    a.stf_grad[shot * g.nSteps + a.it] =
+        (float)(-((double)ai[F_SZZ * pl + off] + 3.0 * (double)ai[F_SXX * pl + off]) * (double)dt);
   }
 
-  // ---- phase 1: adjoint stress tile with halo 3 ----
-  for (int i = tid; i < AS_Z * AS_X; i += NTHREADS) {
-    const int lx = i / AS_Z, lz = i - lx * AS_Z;
-    const int gx = min(x0 - 3 + lx, xmax);
-    const long long off = (long long)gx * P + (z0 - 3 + lz);
-    s_zz[i] = szz_i[off];
-    s_xx[i] = sxx_i[off];
-    s_xz[i] = sxz_i[off];
+  // ---- phase 1: adjoint stress tile, 18 quads x 38 columns ----
+  for (int i = tid; i < VC * QV; i += NTHREADS) {
+    const int col = i / QV, q = i - col * QV;
+    const int gx = min(x0 - 3 + col, xmax);
+    const int off = gx * P + (z0 - 8 + 4 * q);
+    cp_async16(s_zz + col * VP + 4 * q, ai + F_SZZ * pl + off);
+    cp_async16(s_xx + col * VP + 4 * q, ai + F_SXX * pl + off);
+    cp_async16(s_xz + col * VP + 4 * q, ai + F_SXZ * pl + off);
   }
+  cp_async_wait_all();
   __syncthreads();
 
   // psi arrays only matter within 2 cells of the PML
   const int zq_lo = g.nPml + 2, zq_hi = g.nz - g.nPad - g.nPml - 3;  // z-type psi zone: z < zq_lo || z > zq_hi
   const int xq_lo = g.nPml + 2, xq_hi = g.nx - g.nPml - 3;
-  const bool pml_tile = (z0 - 2 < zq_lo) || (z0 + TILE_Z + 1 > zq_hi) || (x0 - 2 < xq_lo) || (x0 + TILE_X + 1 > xq_hi);
+  const bool pml_tile = (z0 - 4 < zq_lo) || (z0 + TILE_Z + 3 > zq_hi) || (x0 - 2 < xq_lo) || (x0 + TILE_X + 1 > xq_hi);
+  const int h = tid >> 4, q = tid & 15;
 
-  // ---- phase 2: adjoint velocity on tile + halo 2 (el_velocity_adj.cu:56-100) ----
+  // ---- phase 2: adjoint velocity on 16 quads x 36 columns (el_velocity_adj.cu:56-100) ----
   {
-    float *vz_o = plane_of(a.state, g, shot, aout + F_VZ);
-    float *vx_o = plane_of(a.state, g, shot, aout + F_VX);
-    for (int i = tid; i < AV_Z * AV_X; i += NTHREADS) {
-      const int lx = i / AV_Z, lz = i - lx * AV_Z;
-      const int gz = z0 - 2 + lz, gx = x0 - 2 + lx;
-      const long long off = (long long)min(gx, xmax) * P + gz;
-      float vz = vz_i[off], vx = vx_i[off];
-      const bool owner = lz >= 2 && lz < TILE_Z + 2 && lx >= 2 && lx < TILE_X + 2 && gz < g.nz && gx < g.nx;
-      if (is_active(g, gz, gx)) {
-        const float *zz = s_zz + (lx + 1) * AS_Z + lz + 1;
-        const float *xx = s_xx + (lx + 1) * AS_Z + lz + 1;
-        const float *xz = s_xz + (lx + 1) * AS_Z + lz + 1;
-        const float lam = a.m.lam[off], mu = a.m.mu[off], amu = a.m.amu[off];
-        const float dszz_dx = ad_plus(zz, AS_Z, rdx);
-        const float dsxx_dx = ad_plus(xx, AS_Z, rdx);
-        const float dsxz_dz = ad_minus(xz, 1, rdz);
-        const float dszz_dz = ad_plus(zz, 1, rdz);
-        const float dsxx_dz = ad_plus(xx, 1, rdz);
-        const float dsxz_dx = ad_minus(xz, AS_Z, rdx);
-        float rKx = 1.0f, rKxh = 1.0f, rKz = 1.0f, rKzh = 1.0f;
-        float tpx1 = 0.0f, tpx2 = 0.0f, tpz1 = 0.0f, tpz2 = 0.0f;  // a * D(psi) terms
-        bool zp = false, xp = false;
+    const int gz = z0 - 4 + 4 * q;
+    for (int c = h; c < SC; c += NTHREADS / 16) {
+      const int gx = x0 - 2 + c;
+      const int off = min(gx, xmax) * P + gz;
+      F4 vz = ld4(ai + F_VZ * pl + off), vx = ld4(ai + F_VX * pl + off);
+      const bool owner = q >= 1 && q <= TILE_Z / 4 && c >= 2 && c < TILE_X + 2 && gx < g.nx && gz < g.nz;
+      if (gx >= 2 && gx <= g.ax_hi && gz + 3 >= 2 && gz <= g.az_hi) {
+        const float *zz = s_zz + (c + 1) * VP + 4 * (q + 1);
+        const float *xx = s_xx + (c + 1) * VP + 4 * (q + 1);
+        const float *xz = s_xz + (c + 1) * VP + 4 * (q + 1);
+        const int cm2 = (c > 0 ? 2 : 1) * VP, cp2 = (c < SC - 1 ? 2 : 1) * VP;  // keep halo-column reads in the tile
+        float dszz_dx[4], dsxx_dx[4], dsxz_dz[4], dszz_dz[4], dsxx_dz[4], dsxz_dx[4];
+        const F4 zzB = ld4(zz), xxB = ld4(xx), xzB = ld4(xz);
+        adx4(ld4(zz - VP), zzB, ld4(zz + VP), ld4(zz + cp2), rdx, dszz_dx);   // ad_plus_x
+        adx4(ld4(xx - VP), xxB, ld4(xx + VP), ld4(xx + cp2), rdx, dsxx_dx);
+        adx4(ld4(xz - cm2), ld4(xz - VP), xzB, ld4(xz + VP), rdx, dsxz_dx);   // ad_minus_x
+        adz_plus4(ld4(zz - 4), zzB, ld4(zz + 4), rdz, dszz_dz);
+        adz_plus4(ld4(xx - 4), xxB, ld4(xx + 4), rdz, dsxx_dz);
+        adz_minus4(ld4(xz - 4), xzB, ld4(xz + 4), rdz, dsxz_dz);
+        const F4 lam = ld4(a.m.lam + off), mu = ld4(a.m.mu + off), amu = ld4(a.m.amu + off);
+        float tpx1[4] = {0, 0, 0, 0}, tpx2[4] = {0, 0, 0, 0}, tpz1[4] = {0, 0, 0, 0}, tpz2[4] = {0, 0, 0, 0};
+        float rKx = 1.0f, rKxh = 1.0f;
+        F4 rKz{{1, 1, 1, 1}}, rKzh{{1, 1, 1, 1}};
+        bool xp = false, zq_pml = false;
         if (pml_tile) {
-          const float *zpf = a.pr.z + gz;
           const float *xpf = a.pr.x + gx + XM;
-          zp = z_in_pml(g, gz);
-          xp = x_in_pml_s(g, gx);
           rKx = xpf[PR_RK * nxp];
           rKxh = xpf[PR_RKH * nxp];
-          rKz = zpf[PR_RK * P];
-          rKzh = zpf[PR_RKH * P];
-          const float ax = xpf[PR_A * nxp], axh = xpf[PR_AH * nxp], az = zpf[PR_A * P], azh = zpf[PR_AH * P];
-          if (ax != 0.0f) tpx1 = ax * ad_plus(plane_of(a.state, g, shot, pin + PSI_VX_X) + off, P, rdx);
-          if (azh != 0.0f) tpx2 = azh * ad_minus(plane_of(a.state, g, shot, pin + PSI_VX_Z) + off, 1, rdz);
-          if (az != 0.0f) tpz1 = az * ad_plus(plane_of(a.state, g, shot, pin + PSI_VZ_Z) + off, 1, rdz);
-          if (axh != 0.0f) tpz2 = axh * ad_minus(plane_of(a.state, g, shot, pin + PSI_VZ_X) + off, P, rdx);
+          const float ax = xpf[PR_A * nxp], axh = xpf[PR_AH * nxp];
+          xp = x_in_pml_s(g, gx);
+          zq_pml = gz < g.nPml || gz + 3 > zp_hi;
+          if (ax != 0.0f) {  // a_x * D+x(psi_xx)
+            const float *p = psi_i + PSI_VX_X * pl + off;
+            float d[4];
+            adx4(ld4(p - P), ld4(p), ld4(p + P), ld4(p + 2 * P), rdx, d);
+#pragma unroll
+            for (int k = 0; k < 4; k++) tpx1[k] = ax * d[k];
+          }
+          if (axh != 0.0f) {  // a_x_half * D-x(psi_zx)
+            const float *p = psi_i + PSI_VZ_X * pl + off;
+            float d[4];
+            adx4(ld4(p - 2 * P), ld4(p - P), ld4(p), ld4(p + P), rdx, d);
+#pragma unroll
+            for (int k = 0; k < 4; k++) tpz2[k] = axh * d[k];
+          }
+          if (zq_pml) {
+            rKz = ld4(a.pr.z + PR_RK * P + gz);
+            rKzh = ld4(a.pr.z + PR_RKH * P + gz);
+            const F4 az = ld4(a.pr.z + PR_A * P + gz), azh = ld4(a.pr.z + PR_AH * P + gz);
+            const float *p1 = psi_i + PSI_VX_Z * pl + off;  // a_z_half * D-z(psi_xz)
+            const float *p2 = psi_i + PSI_VZ_Z * pl + off;  // a_z * D+z(psi_zz)
+            float d[4];
+            adz_minus4(ld4(p1 - 4), ld4(p1), ld4(p1 + 4), rdz, d);
+#pragma unroll
+            for (int k = 0; k < 4; k++) tpx2[k] = azh.v[k] * d[k];
+            adz_plus4(ld4(p2 - 4), ld4(p2), ld4(p2 + 4), rdz, d);
+#pragma unroll
+            for (int k = 0; k < 4; k++) tpz1[k] = az.v[k] * d[k];
+          }
         }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const int z = gz + k;
+          if (z >= 2 && z <= g.az_hi) {
 #if FWI_FP64_PROMOTE
-        const double l2m = (double)lam + 2.0 * (double)mu;
-        {
-          const float t12 = tpx1 + lam * dszz_dx * rKx * dt;
-          const double t3 = l2m * (double)dsxx_dx * (double)rKx * (double)dt;
-          const double sum = (double)t12 + t3 + (double)tpx2 + (double)(amu * rKzh * dsxz_dz * dt);
-          vx = (float)((double)vx + sum);
-        }
-        {
-          const double t2 = l2m * (double)dszz_dz * (double)rKz * (double)dt;
-          const double sum = (double)tpz1 + t2 + (double)(lam * dsxx_dz * rKz * dt) + (double)tpz2 +
-                             (double)(amu * rKxh * dsxz_dx * dt);
-          vz = (float)((double)vz + sum);
-        }
+            const double l2m = (double)lam.v[k] + 2.0 * (double)mu.v[k];
+            {
+              const float t12 = tpx1[k] + lam.v[k] * dszz_dx[k] * rKx * dt;
+              const double t3 = l2m * (double)dsxx_dx[k] * (double)rKx * (double)dt;
+              vx.v[k] = (float)((double)vx.v[k] + ((double)t12 + t3 + (double)tpx2[k] +
+                                                   (double)(amu.v[k] * rKzh.v[k] * dsxz_dz[k] * dt)));
+            }
+            {
+              const double t2 = l2m * (double)dszz_dz[k] * (double)rKz.v[k] * (double)dt;
+              vz.v[k] = (float)((double)vz.v[k] + ((double)tpz1[k] + t2 + (double)(lam.v[k] * dsxx_dz[k] * rKz.v[k] * dt) +
+                                                   (double)tpz2[k] + (double)(amu.v[k] * rKxh * dsxz_dx[k] * dt)));
+            }
 #else
-        const float l2m = lam + 2.0f * mu;
-        vx += tpx1 + lam * dszz_dx * rKx * dt + l2m * dsxx_dx * rKx * dt + tpx2 + amu * rKzh * dsxz_dz * dt;
-        vz += tpz1 + l2m * dszz_dz * rKz * dt + lam * dsxx_dz * rKz * dt + tpz2 + amu * rKxh * dsxz_dx * dt;
+            const float l2m = lam.v[k] + 2.0f * mu.v[k];
+            vx.v[k] += tpx1[k] + lam.v[k] * dszz_dx[k] * rKx * dt + l2m * dsxx_dx[k] * rKx * dt + tpx2[k] +
+                       amu.v[k] * rKzh.v[k] * dsxz_dz[k] * dt;
+            vz.v[k] += tpz1[k] + l2m * dszz_dz[k] * rKz.v[k] * dt + lam.v[k] * dsxx_dz[k] * rKz.v[k] * dt + tpz2[k] +
+                       amu.v[k] * rKxh * dsxz_dx[k] * dt;
 #endif
-        if (owner && (xp || zp)) {  // phi memory, PML only (el_velocity_adj.cu:74-79,95-100)
-          const float bya = a.m.bya[off], byb = a.m.byb[off];
+          }
+        }
+        if (owner && (xp || zq_pml)) {  // phi memory, PML cells only (el_velocity_adj.cu:74-79,95-100)
+          const F4 bya = ld4(a.m.bya + off), byb = ld4(a.m.byb + off);
           if (xp) {
             const float *xpf = a.pr.x + gx + XM;
-            plane_of(a.state, g, shot, qout + PHI_SXX_X)[off] =
-                xpf[PR_BH * nxp] * plane_of(a.state, g, shot, qin + PHI_SXX_X)[off] + byb * vx * dt;
-            plane_of(a.state, g, shot, qout + PHI_SXZ_X)[off] =
-                xpf[PR_B * nxp] * plane_of(a.state, g, shot, qin + PHI_SXZ_X)[off] + bya * vz * dt;
+            const float bx = xpf[PR_B * nxp], bxh = xpf[PR_BH * nxp];
+            F4 f1 = ld4(phi_i + PHI_SXX_X * pl + off), f2 = ld4(phi_i + PHI_SXZ_X * pl + off);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+              const int z = gz + k;
+              if (z >= 2 && z <= g.az_hi) {
+                f1.v[k] = bxh * f1.v[k] + byb.v[k] * vx.v[k] * dt;
+                f2.v[k] = bx * f2.v[k] + bya.v[k] * vz.v[k] * dt;
+              }
+            }
+            st4(phi_o + PHI_SXX_X * pl + off, f1);
+            st4(phi_o + PHI_SXZ_X * pl + off, f2);
           }
-          if (zp) {
-            const float *zpf = a.pr.z + gz;
-            plane_of(a.state, g, shot, qout + PHI_SXZ_Z)[off] =
-                zpf[PR_B * P] * plane_of(a.state, g, shot, qin + PHI_SXZ_Z)[off] + byb * vx * dt;
-            plane_of(a.state, g, shot, qout + PHI_SZZ_Z)[off] =
-                zpf[PR_BH * P] * plane_of(a.state, g, shot, qin + PHI_SZZ_Z)[off] + bya * vz * dt;
+          if (zq_pml) {
+            const F4 bz = ld4(a.pr.z + PR_B * P + gz), bzh = ld4(a.pr.z + PR_BH * P + gz);
+            F4 f1 = ld4(phi_i + PHI_SXZ_Z * pl + off), f2 = ld4(phi_i + PHI_SZZ_Z * pl + off);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+              const int z = gz + k;
+              if ((z < g.nPml || z > zp_hi) && z >= 2 && z <= g.az_hi) {
+                f1.v[k] = bz.v[k] * f1.v[k] + byb.v[k] * vx.v[k] * dt;
+                f2.v[k] = bzh.v[k] * f2.v[k] + bya.v[k] * vz.v[k] * dt;
+              }
+            }
+            st4(phi_o + PHI_SXZ_Z * pl + off, f1);
+            st4(phi_o + PHI_SZZ_Z * pl + off, f2);
           }
         }
       }
-      s_vz[i] = vz;
-      s_vx[i] = vx;
+      st4(s_vz + c * SP + 4 * q, vz);
+      st4(s_vx + c * SP + 4 * q, vx);
       if (owner) {
-        vz_o[off] = vz;
-        vx_o[off] = vx;
+        st4(ao + F_VZ * pl + off, vz);
+        st4(ao + F_VX * pl + off, vx);
       }
     }
   }
@@ -629,111 +798,166 @@ __global__ void __launch_bounds__(NTHREADS) adj_step_kernel(const __grid_constan
     const int loc = a.st.rec_loc[shot * a.st.nrp + k];
     const int lz = loc & 0xffff, lx = loc >> 16;
     const float r = a.res[((long long)shot * g.nSteps + a.it) * a.st.nrp + a.st.rec_id[shot * a.st.nrp + k]];
-    const int j = (lx + 3) * AS_Z + lz + 3;
+    const int j = (lx + 3) * VP + lz + 8;
     atomicAdd(&s_zz[j], r);
     atomicAdd(&s_xx[j], 3.0f * r);
   }
   __syncthreads();
 
-  // ---- phase 3: adjoint stress on the owner tile (el_stress_adj.cu:52-95) ----
-  {
-    float *szz_o = plane_of(a.state, g, shot, aout + F_SZZ);
-    float *sxx_o = plane_of(a.state, g, shot, aout + F_SXX);
-    float *sxz_o = plane_of(a.state, g, shot, aout + F_SXZ);
-    for (int i = tid; i < TILE_Z * TILE_X; i += NTHREADS) {
-      const int lx = i / TILE_Z, lz = i - lx * TILE_Z;
-      const int gz = z0 + lz, gx = x0 + lx;
-      if (gz >= g.nz || gx >= g.nx) continue;
-      const long long off = (long long)gx * P + gz;
-      const int j = (lx + 3) * AS_Z + lz + 3;
-      float szz = s_zz[j], sxx = s_xx[j], sxz = s_xz[j];
-      if (is_active(g, gz, gx)) {
-        const float *pz = s_vz + (lx + 2) * AV_Z + lz + 2;
-        const float *px = s_vx + (lx + 2) * AV_Z + lz + 2;
-        const float dvz_dx = ad_plus(pz, AV_Z, rdx);
-        const float dvx_dz = ad_plus(px, 1, rdz);
-        const float dvx_dx = ad_minus(px, AV_Z, rdx);
-        const float dvz_dz = ad_minus(pz, 1, rdz);
-        const float bya = a.m.bya[off], byb = a.m.byb[off];
-        float rKx = 1.0f, rKxh = 1.0f, rKz = 1.0f, rKzh = 1.0f;
-        float t_xz_x = 0.0f, t_xz_z = 0.0f, t_xx = 0.0f, t_zz = 0.0f;  // a * D(phi_new) terms
+  // ---- phase 3: adjoint stress on 14 quads x 32 columns (el_stress_adj.cu:52-95) ----
+  if (q < TILE_Z / 4) {
+    const int gz = z0 + 4 * q;
+    for (int c = h; c < TILE_X; c += NTHREADS / 16) {
+      const int gx = x0 + c;
+      if (gx >= g.nx || gz >= g.nz) continue;
+      const int off = gx * P + gz;
+      const int j = (c + 3) * VP + 4 * (q + 2);
+      F4 szz = ld4(s_zz + j), sxx = ld4(s_xx + j), sxz = ld4(s_xz + j);
+      if (gx >= 2 && gx <= g.ax_hi && gz + 3 >= 2 && gz <= g.az_hi) {
+        const float *pz = s_vz + (c + 2) * SP + 4 * (q + 1);
+        const float *px = s_vx + (c + 2) * SP + 4 * (q + 1);
+        // velocity quads: z-neighbours (A,B,C) and the x-neighbour columns, kept for the phi recomputation
+        const F4 zA = ld4(pz - 4), zB = ld4(pz), zC = ld4(pz + 4), zXm = ld4(pz - SP), zXp = ld4(pz + SP), zXpp = ld4(pz + 2 * SP);
+        const F4 xA = ld4(px - 4), xB = ld4(px), xC = ld4(px + 4), xXmm = ld4(px - 2 * SP), xXm = ld4(px - SP), xXp = ld4(px + SP);
+        float dvz_dx[4], dvx_dz[4], dvx_dx[4], dvz_dz[4];
+        adx4(zXm, zB, zXp, zXpp, rdx, dvz_dx);    // ad_plus_x(vz)
+        adz_plus4(xA, xB, xC, rdz, dvx_dz);        // ad_plus_z(vx)
+        adx4(xXmm, xXm, xB, xXp, rdx, dvx_dx);    // ad_minus_x(vx)
+        adz_minus4(zA, zB, zC, rdz, dvz_dz);       // ad_minus_z(vz)
+        const F4 bya = ld4(a.m.bya + off), byb = ld4(a.m.byb + off);
+        float rKx = 1.0f, rKxh = 1.0f;
+        F4 rKz{{1, 1, 1, 1}}, rKzh{{1, 1, 1, 1}};
+        float t_xz_x[4] = {0, 0, 0, 0}, t_xz_z[4] = {0, 0, 0, 0}, t_xx[4] = {0, 0, 0, 0}, t_zz[4] = {0, 0, 0, 0};
+        const bool zq_pml = gz < g.nPml || gz + 3 > zp_hi;
         if (pml_tile) {
-          const float *zpf = a.pr.z + gz;
           const float *xpf = a.pr.x + gx + XM;
           rKx = xpf[PR_RK * nxp];
           rKxh = xpf[PR_RKH * nxp];
-          rKz = zpf[PR_RK * P];
-          rKzh = zpf[PR_RKH * P];
-          const float ax = xpf[PR_A * nxp], axh = xpf[PR_AH * nxp], az = zpf[PR_A * P], azh = zpf[PR_AH * P];
-          // phi_new at a stencil point, recomputed from the velocity tile instead of being staged:
+          const float ax = xpf[PR_A * nxp], axh = xpf[PR_AH * nxp];
+          // phi_new at a stencil point is recomputed from the velocity tile instead of being staged:
           //   phi_new = active & in-PML ? b * phi_old + byc * v_new * dt : phi_old
-          auto phi_x = [&](int which, int dxs, const float *bprof, const float *byc, const float *sv) -> float {
+          auto phi_col = [&](int which, int dxs, const float *bprof, const float *byc, const F4 &v) -> F4 {
             const int x2 = gx + dxs;
-            const long long o2 = off + (long long)dxs * P;
-            float ph = plane_of(a.state, g, shot, qin + which)[o2];
-            if (is_active(g, gz, x2) && x_in_pml_s(g, x2)) ph = bprof[x2 + XM] * ph + byc[o2] * sv[dxs * AV_Z] * dt;
+            const int o2 = off + dxs * P;
+            F4 ph = ld4(phi_i + which * pl + o2);
+            if (x2 >= 2 && x2 <= g.ax_hi && x_in_pml_s(g, x2)) {
+              const float b = bprof[x2 + XM];
+              const F4 by = ld4(byc + o2);
+#pragma unroll
+              for (int k = 0; k < 4; k++)
+                if (gz + k >= 2 && gz + k <= g.az_hi) ph.v[k] = b * ph.v[k] + by.v[k] * v.v[k] * dt;
+            }
             return ph;
           };
-          auto phi_z = [&](int which, int dzs, const float *bprof, const float *byc, const float *sv) -> float {
-            const int z2 = gz + dzs;
-            const long long o2 = off + dzs;
-            float ph = plane_of(a.state, g, shot, qin + which)[o2];
-            if (is_active(g, z2, gx) && z_in_pml(g, z2)) ph = bprof[z2] * ph + byc[o2] * sv[dzs] * dt;
-            return ph;
-          };
-          if (ax != 0.0f) {  // D+x of phi_xz_x (b_x, byc_a * vz)
+          if (ax != 0.0f) {  // a_x * D+x(phi_xz_x): b_x, byc_a * vz at x-1 .. x+2
             const float *bp = a.pr.x + PR_B * nxp;
-            t_xz_x = ax * ad_plus4(phi_x(PHI_SXZ_X, -1, bp, a.m.bya, pz), phi_x(PHI_SXZ_X, 0, bp, a.m.bya, pz),
-                                   phi_x(PHI_SXZ_X, 1, bp, a.m.bya, pz), phi_x(PHI_SXZ_X, 2, bp, a.m.bya, pz), rdx);
+            float d[4];
+            adx4(phi_col(PHI_SXZ_X, -1, bp, a.m.bya, zXm), phi_col(PHI_SXZ_X, 0, bp, a.m.bya, zB),
+                 phi_col(PHI_SXZ_X, 1, bp, a.m.bya, zXp), phi_col(PHI_SXZ_X, 2, bp, a.m.bya, zXpp), rdx, d);
+#pragma unroll
+            for (int k = 0; k < 4; k++) t_xz_x[k] = ax * d[k];
           }
-          if (az != 0.0f) {  // D+z of phi_xz_z (b_z, byc_b * vx)
-            const float *bp = a.pr.z + PR_B * P;
-            t_xz_z = az * ad_plus4(phi_z(PHI_SXZ_Z, -1, bp, a.m.byb, px), phi_z(PHI_SXZ_Z, 0, bp, a.m.byb, px),
-                                   phi_z(PHI_SXZ_Z, 1, bp, a.m.byb, px), phi_z(PHI_SXZ_Z, 2, bp, a.m.byb, px), rdz);
-          }
-          if (axh != 0.0f) {  // D-x of phi_xx_x (b_x_half, byc_b * vx)
+          if (axh != 0.0f) {  // a_x_half * D-x(phi_xx_x): b_x_half, byc_b * vx at x-2 .. x+1
             const float *bp = a.pr.x + PR_BH * nxp;
-            t_xx = axh * ad_minus4(phi_x(PHI_SXX_X, -2, bp, a.m.byb, px), phi_x(PHI_SXX_X, -1, bp, a.m.byb, px),
-                                   phi_x(PHI_SXX_X, 0, bp, a.m.byb, px), phi_x(PHI_SXX_X, 1, bp, a.m.byb, px), rdx);
+            float d[4];
+            adx4(phi_col(PHI_SXX_X, -2, bp, a.m.byb, xXmm), phi_col(PHI_SXX_X, -1, bp, a.m.byb, xXm),
+                 phi_col(PHI_SXX_X, 0, bp, a.m.byb, xB), phi_col(PHI_SXX_X, 1, bp, a.m.byb, xXp), rdx, d);
+#pragma unroll
+            for (int k = 0; k < 4; k++) t_xx[k] = axh * d[k];
           }
-          if (azh != 0.0f) {  // D-z of phi_zz_z (b_z_half, byc_a * vz)
-            const float *bp = a.pr.z + PR_BH * P;
-            t_zz = azh * ad_minus4(phi_z(PHI_SZZ_Z, -2, bp, a.m.bya, pz), phi_z(PHI_SZZ_Z, -1, bp, a.m.bya, pz),
-                                   phi_z(PHI_SZZ_Z, 0, bp, a.m.bya, pz), phi_z(PHI_SZZ_Z, 1, bp, a.m.bya, pz), rdz);
+          if (zq_pml) {
+            rKz = ld4(a.pr.z + PR_RK * P + gz);
+            rKzh = ld4(a.pr.z + PR_RKH * P + gz);
+            const F4 az = ld4(a.pr.z + PR_A * P + gz), azh = ld4(a.pr.z + PR_AH * P + gz);
+            auto phi_quad = [&](int which, int dq, const float *bprof, const float *byc, const F4 &v) -> F4 {
+              const int zq = gz + 4 * dq;
+              const int o2 = off + 4 * dq;
+              F4 ph = ld4(phi_i + which * pl + o2);
+              const F4 b = ld4(bprof + zq), by = ld4(byc + o2);
+#pragma unroll
+              for (int k = 0; k < 4; k++) {
+                const int z = zq + k;
+                if ((z < g.nPml || z > zp_hi) && z >= 2 && z <= g.az_hi) ph.v[k] = b.v[k] * ph.v[k] + by.v[k] * v.v[k] * dt;
+              }
+              return ph;
+            };
+            float d[4];
+            {  // a_z * D+z(phi_xz_z): b_z, byc_b * vx
+              const float *bp = a.pr.z + PR_B * P;
+              adz_plus4(phi_quad(PHI_SXZ_Z, -1, bp, a.m.byb, xA), phi_quad(PHI_SXZ_Z, 0, bp, a.m.byb, xB),
+                        phi_quad(PHI_SXZ_Z, 1, bp, a.m.byb, xC), rdz, d);
+#pragma unroll
+              for (int k = 0; k < 4; k++) t_xz_z[k] = az.v[k] * d[k];
+            }
+            {  // a_z_half * D-z(phi_zz_z): b_z_half, byc_a * vz
+              const float *bp = a.pr.z + PR_BH * P;
+              adz_minus4(phi_quad(PHI_SZZ_Z, -1, bp, a.m.bya, zA), phi_quad(PHI_SZZ_Z, 0, bp, a.m.bya, zB),
+                         phi_quad(PHI_SZZ_Z, 1, bp, a.m.bya, zC), rdz, d);
+#pragma unroll
+              for (int k = 0; k < 4; k++) t_zz[k] = azh.v[k] * d[k];
+            }
           }
         }
-        sxz += t_xz_x + dvz_dx * rKx * bya * dt + t_xz_z + dvx_dz * rKz * byb * dt;
-        sxx += t_xx + byb * dvx_dx * rKxh * dt;
-        szz += t_zz + bya * dvz_dz * rKzh * dt;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const int z = gz + k;
+          if (z >= 2 && z <= g.az_hi) {
+            sxz.v[k] += t_xz_x[k] + dvz_dx[k] * rKx * bya.v[k] * dt + t_xz_z[k] + dvx_dz[k] * rKz.v[k] * byb.v[k] * dt;
+            sxx.v[k] += t_xx[k] + byb.v[k] * dvx_dx[k] * rKxh * dt;
+            szz.v[k] += t_zz[k] + bya.v[k] * dvz_dz[k] * rKzh.v[k] * dt;
+          }
+        }
         if (pml_tile) {
           const bool xq = gx < xq_lo || gx > xq_hi;
-          const bool zq = gz < zq_lo || gz > zq_hi;
+          const bool zq = gz < zq_lo || gz + 3 > zq_hi;
           if (xq || zq) {
-            const float lam = a.m.lam[off], mu = a.m.mu[off], amu = a.m.amu[off];
-            const float *zpf = a.pr.z + gz;
-            const float *xpf = a.pr.x + gx + XM;
-            const double l2m = (double)lam + 2.0 * (double)mu;
+            const F4 lam = ld4(a.m.lam + off), mu = ld4(a.m.mu + off), amu = ld4(a.m.amu + off);
             if (xq) {
-              plane_of(a.state, g, shot, pout + PSI_VZ_X)[off] =
-                  xpf[PR_BH * nxp] * plane_of(a.state, g, shot, pin + PSI_VZ_X)[off] + sxz * amu * dt;
-              plane_of(a.state, g, shot, pout + PSI_VX_X)[off] =
-                  (float)((double)(xpf[PR_B * nxp] * plane_of(a.state, g, shot, pin + PSI_VX_X)[off] +
-                                   lam * szz * dt) +
-                          l2m * (double)sxx * (double)dt);
+              const float *xpf = a.pr.x + gx + XM;
+              const float bx = xpf[PR_B * nxp], bxh = xpf[PR_BH * nxp];
+              F4 p1 = ld4(psi_i + PSI_VZ_X * pl + off), p2 = ld4(psi_i + PSI_VX_X * pl + off);
+#pragma unroll
+              for (int k = 0; k < 4; k++) {
+                const int z = gz + k;
+                if (z >= 2 && z <= g.az_hi) {
+                  p1.v[k] = bxh * p1.v[k] + sxz.v[k] * amu.v[k] * dt;
+#if FWI_FP64_PROMOTE
+                  p2.v[k] = (float)((double)(bx * p2.v[k] + lam.v[k] * szz.v[k] * dt) +
+                                    ((double)lam.v[k] + 2.0 * (double)mu.v[k]) * (double)sxx.v[k] * (double)dt);
+#else
+                  p2.v[k] = bx * p2.v[k] + lam.v[k] * szz.v[k] * dt + (lam.v[k] + 2.0f * mu.v[k]) * sxx.v[k] * dt;
+#endif
+                }
+              }
+              st4(psi_o + PSI_VZ_X * pl + off, p1);
+              st4(psi_o + PSI_VX_X * pl + off, p2);
             }
             if (zq) {
-              plane_of(a.state, g, shot, pout + PSI_VX_Z)[off] =
-                  zpf[PR_BH * P] * plane_of(a.state, g, shot, pin + PSI_VX_Z)[off] + sxz * amu * dt;
-              plane_of(a.state, g, shot, pout + PSI_VZ_Z)[off] =
-                  (float)((double)(zpf[PR_B * P] * plane_of(a.state, g, shot, pin + PSI_VZ_Z)[off]) +
-                          l2m * (double)szz * (double)dt + (double)(lam * sxx * dt));
+              const F4 bz = ld4(a.pr.z + PR_B * P + gz), bzh = ld4(a.pr.z + PR_BH * P + gz);
+              F4 p1 = ld4(psi_i + PSI_VX_Z * pl + off), p2 = ld4(psi_i + PSI_VZ_Z * pl + off);
+#pragma unroll
+              for (int k = 0; k < 4; k++) {
+                const int z = gz + k;
+                if ((z < zq_lo || z > zq_hi) && z >= 2 && z <= g.az_hi) {
+                  p1.v[k] = bzh.v[k] * p1.v[k] + sxz.v[k] * amu.v[k] * dt;
+#if FWI_FP64_PROMOTE
+                  p2.v[k] = (float)((double)(bz.v[k] * p2.v[k]) +
+                                    ((double)lam.v[k] + 2.0 * (double)mu.v[k]) * (double)szz.v[k] * (double)dt +
+                                    (double)(lam.v[k] * sxx.v[k] * dt));
+#else
+                  p2.v[k] = bz.v[k] * p2.v[k] + (lam.v[k] + 2.0f * mu.v[k]) * szz.v[k] * dt + lam.v[k] * sxx.v[k] * dt;
+#endif
+                }
+              }
+              st4(psi_o + PSI_VX_Z * pl + off, p1);
+              st4(psi_o + PSI_VZ_Z * pl + off, p2);
             }
           }
         }
       }
-      szz_o[off] = szz;
-      sxx_o[off] = sxx;
-      sxz_o[off] = sxz;
+      st4(ao + F_SZZ * pl + off, szz);
+      st4(ao + F_SXX * pl + off, sxx);
+      st4(ao + F_SXZ * pl + off, sxz);
     }
   }
 }
@@ -882,23 +1106,44 @@ __global__ void traces_to_rt_kernel(const float *tr, float *rt, int nrec, int nr
   }
 }
 
-// result planes are row-major [z][x] (libCUFD.cu:480-486); sums the per-slot accumulators in slot order
-__global__ void finalize_kernel(Grid g, const float *gacc, int nslots, const float *misfit_half, float *result) {
-  __shared__ float t[32][33];
-  const int zb = blockIdx.x * 32, xb = blockIdx.y * 32, k = blockIdx.z;
+// result planes are row-major [z][x] (libCUFD.cu:480-486).  Sums the per-slot accumulators in slot order and
+// applies the reference's 4-point spray of the mu / rho imaging terms as a gather (el_stress.cu:113-124,
+// el_velocity.cu:105-110, incl. the always-true x+1 guard that lands in column xhi+1).
+__global__ void finalize_kernel(Grid g, const float *gacc, int nslots, const float *mu, const float *misfit_half,
+                                float *result) {
+  __shared__ float t[3][32][33];
+  const int zb = blockIdx.x * 32, xb = blockIdx.y * 32;
+  auto S = [&](int which, int z, int x) -> float {
+    float s = 0.0f;
+    const long long o = g.origin + (long long)x * g.P + z;
+    for (int q = 0; q < nslots; q++) s += gacc[((long long)q * G_COUNT + which) * g.plane + o];
+    return s;
+  };
   for (int r = threadIdx.y; r < 32; r += blockDim.y) {
     const int x = xb + r, z = zb + threadIdx.x;
-    float s = 0.0f;
-    if (x < g.nx && z < g.nz)
-      for (int q = 0; q < nslots; q++) s += gacc[((long long)q * 3 + k) * g.plane + g.origin + (long long)x * g.P + z];
-    t[r][threadIdx.x] = s;
+    float gl = 0.0f, gm = 0.0f, gd = 0.0f;
+    if (z >= g.zlo && z <= g.zhi && x >= g.xlo && x <= g.xhi + 1) {
+      gl = S(G_LAM, z, x);
+      gm = S(G_MU, z, x);
+      float G = S(G_MUS, z, x) + S(G_MUS, z - 1, x) + S(G_MUS, z, x - 1);
+      if (x <= g.xhi) G += S(G_MUS, z - 1, x - 1);
+      if (G != 0.0f) {
+        const float m = mu[(long long)x * g.P + z];
+        gm += G / (m * m);
+      }
+      gd = S(G_RHO_A, z, x) + S(G_RHO_B, z, x) + S(G_RHO_A, z - 1, x) + S(G_RHO_B, z, x - 1);
+    }
+    t[0][r][threadIdx.x] = gl;
+    t[1][r][threadIdx.x] = gm;
+    t[2][r][threadIdx.x] = gd;
   }
   __syncthreads();
   for (int r = threadIdx.y; r < 32; r += blockDim.y) {
     const int z = zb + r, x = xb + threadIdx.x;
-    if (z < g.nz && x < g.nx) result[((long long)k * g.nz + z) * g.nx + x] = t[threadIdx.x][r];
+    if (z < g.nz && x < g.nx)
+      for (int k = 0; k < 3; k++) result[((long long)k * g.nz + z) * g.nx + x] = t[k][threadIdx.x][r];
   }
-  if (blockIdx.x == 0 && blockIdx.y == 0 && k == 0 && threadIdx.x == 0 && threadIdx.y == 0)
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && threadIdx.y == 0)
     result[3LL * g.nz * g.nx] = *misfit_half;
 }
 
@@ -912,6 +1157,7 @@ size_t reverse_smem_bytes() { return REV_SMEM; }
 size_t adjoint_smem_bytes() { return ADJ_SMEM; }
 
 void configure_kernels() {
+
   cudaFuncSetAttribute(fwd_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM);
   cudaFuncSetAttribute(fwd_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM);
   cudaFuncSetAttribute(rev_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)REV_SMEM);
@@ -970,11 +1216,11 @@ void launch_traces_to_rt(const float *tr, float *rt, int nrec, int nrp, int nSte
   traces_to_rt_kernel<<<tg, tb, 0, s>>>(tr, rt, nrec, nrp, nSteps);
 }
 
-void launch_finalize(const Grid &g, const float *gacc, int nslots, const float *misfit_half, float *result,
-                     cudaStream_t s) {
+void launch_finalize(const Grid &g, const float *gacc, int nslots, const float *mu, const float *misfit_half,
+                     float *result, cudaStream_t s) {
   dim3 tb(32, 8);
-  dim3 tg((g.nz + 31) / 32, (g.nx + 31) / 32, 3);
-  finalize_kernel<<<tg, tb, 0, s>>>(g, gacc, nslots, misfit_half, result);
+  dim3 tg((g.nz + 31) / 32, (g.nx + 31) / 32);
+  finalize_kernel<<<tg, tb, 0, s>>>(g, gacc, nslots, mu, misfit_half, result);
 }
 
 }  // namespace fwi

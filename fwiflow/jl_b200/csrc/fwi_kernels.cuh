@@ -17,7 +17,7 @@ namespace fwi {
 
 constexpr int XM = 4;        // margin columns in x
 constexpr int SLACK = 256;   // floats before / after each plane
-constexpr int TILE_Z = 64;   // owner tile (z fastest)
+constexpr int TILE_Z = 56;   // owner tile (z fastest): 14 float4 quads, 7 sectors of 32 B
 constexpr int TILE_X = 32;
 constexpr int NTHREADS = 256;
 
@@ -33,6 +33,8 @@ enum Slot : int {
   S_PHI_B = 32,
   S_COUNT = 36
 };
+// gradient accumulator planes (per concurrent shot)
+enum Grad : int { G_LAM = 0, G_MU = 1, G_MUS = 2, G_RHO_A = 3, G_RHO_B = 4, G_COUNT = 5 };
 enum Field : int { F_VZ = 0, F_VX = 1, F_SZZ = 2, F_SXX = 3, F_SXZ = 4 };
 enum Psi : int { PSI_VZ_Z = 0, PSI_VX_X = 1, PSI_VX_Z = 2, PSI_VZ_X = 3 };
 enum Phi : int { PHI_SZZ_Z = 0, PHI_SXZ_X = 1, PHI_SXZ_Z = 2, PHI_SXX_X = 3 };
@@ -93,7 +95,7 @@ struct BwdArgs {
   float *state;
   const float *res;    // [batch][nSteps][nrp] tapered residual
   const float *frames;
-  float *gacc;         // [batch][3][plane] gradient accumulators (lambda, mu, den)
+  float *gacc;         // [batch][G_COUNT][plane] imaging accumulators
   float *stf_grad;     // [batch][nSteps]
   int batch;
   int it;
@@ -132,8 +134,8 @@ void launch_misfit(const float *j_shot, int n, float *misfit_half, cudaStream_t 
 void launch_traces_to_rt(const float *tr, float *rt, int nrec, int nrp, int nSteps, cudaStream_t s);
 
 // result = [gl|gm|gd|misfit] row-major [z][x] float: sums the per-slot accumulators
-void launch_finalize(const Grid &g, const float *gacc, int nslots, const float *misfit_half, float *result,
-                     cudaStream_t s);
+void launch_finalize(const Grid &g, const float *gacc, int nslots, const float *mu, const float *misfit_half,
+                     float *result, cudaStream_t s);
 
 size_t forward_smem_bytes();
 size_t reverse_smem_bytes();

@@ -147,9 +147,11 @@ void upload_profiles(fwi_b200_plan &pl) {
     x[PR_RK * nxp + i + XM] = 1.0f / hx.K[i];  x[PR_A * nxp + i + XM] = hx.a[i];  x[PR_B * nxp + i + XM] = hx.b[i];
     x[PR_RKH * nxp + i + XM] = 1.0f / hx.Kh[i]; x[PR_AH * nxp + i + XM] = hx.ah[i]; x[PR_BH * nxp + i + XM] = hx.bh[i];
   }
-  pl.zprof.alloc(z.size());
+  // one spare row before and after: quads that straddle z < 0 or z >= P read (and discard) them
+  pl.zprof.alloc(z.size() + 2 * (size_t)g.P);
   pl.xprof.alloc(x.size());
-  CUDA_OK(cudaMemcpy(pl.zprof.p, z.data(), z.size() * sizeof(float), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemset(pl.zprof.p, 0, pl.zprof.bytes()));
+  CUDA_OK(cudaMemcpy(pl.zprof.p + g.P, z.data(), z.size() * sizeof(float), cudaMemcpyHostToDevice));
   CUDA_OK(cudaMemcpy(pl.xprof.p, x.data(), x.size() * sizeof(float), cudaMemcpyHostToDevice));
   std::vector<float> w2;
   if (!taper_weights(p.nSteps, p.dt, 0.005f, w2)) w2.assign(p.nSteps, 1.0f);  // libCUFD.cu:63,268-270
@@ -205,7 +207,7 @@ void upload_tables(fwi_b200_plan &pl) {
 
 size_t per_shot_bytes(const fwi_b200_plan &pl, bool with_frames) {
   const Grid &g = pl.g;
-  size_t b = (size_t)(S_COUNT + 3) * g.plane * sizeof(float);
+  size_t b = (size_t)(S_COUNT + G_COUNT) * g.plane * sizeof(float);
   b += (size_t)2 * g.nSteps * pl.nrp * sizeof(float);
   if (with_frames) b += (size_t)5 * g.f_len * g.nSteps * sizeof(float);
   return b;
@@ -237,7 +239,7 @@ void alloc_run_buffers(fwi_b200_plan &pl, int calc_id) {
     pl.partial.alloc((size_t)pl.batch * nb);
   }
   if (calc_id == 1) {
-    pl.gacc.alloc((size_t)pl.batch * 3 * g.plane);
+    pl.gacc.alloc((size_t)pl.batch * G_COUNT * g.plane);
     pl.frames.alloc((size_t)pl.batch * g.nSteps * 5 * g.f_len);
   }
   if (calc_id == 2 || pl.para.save_scratch) pl.syn_rt.alloc((size_t)pl.group * pl.trace_stride);
@@ -282,7 +284,7 @@ void run_locked(fwi_b200_plan &pl, int calc_id, cudaStream_t s) {
   Model m = model_of(pl);
   FwdArgs fa{};
   fa.g = g; fa.m = m;
-  fa.pr.z = pl.zprof.p; fa.pr.x = pl.xprof.p; fa.pr.nxp = g.nx + 2 * XM;
+  fa.pr.z = pl.zprof.p + g.P; fa.pr.x = pl.xprof.p; fa.pr.nxp = g.nx + 2 * XM;
   BwdArgs ba{};
   ba.g = g; ba.m = m; ba.pr = fa.pr;
 
@@ -364,7 +366,7 @@ void run_locked(fwi_b200_plan &pl, int calc_id, cudaStream_t s) {
     pl.launches++;
   }
   if (with_adj) {
-    launch_finalize(g, pl.gacc.p, std::min(pl.batch, pl.group), pl.misfit_half.p, pl.result.p, s);
+    launch_finalize(g, pl.gacc.p, std::min(pl.batch, pl.group), m.mu, pl.misfit_half.p, pl.result.p, s);
     pl.launches++;
   } else if (if_res) {
     CUDA_OK(cudaMemcpyAsync(pl.result.p + 3LL * g.nz * g.nx, pl.misfit_half.p, sizeof(float), cudaMemcpyDeviceToDevice, s));
@@ -643,7 +645,7 @@ extern "C" int fwi_b200_plan_time_kernel(fwi_b200_plan *pl, int which, int iters
     const int nb = std::min(pl->batch, pl->group);
     FwdArgs fa{};
     fa.g = g; fa.m = model_of(*pl);
-    fa.pr.z = pl->zprof.p; fa.pr.x = pl->xprof.p; fa.pr.nxp = g.nx + 2 * XM;
+    fa.pr.z = pl->zprof.p + g.P; fa.pr.x = pl->xprof.p; fa.pr.nxp = g.nx + 2 * XM;
     fa.st = tables_for(*pl, 0); fa.state = pl->state.p; fa.traces = pl->syn_tr.p; fa.frames = pl->frames.p; fa.batch = nb;
     BwdArgs ba{};
     ba.g = g; ba.m = fa.m; ba.pr = fa.pr; ba.st = fa.st; ba.state = pl->state.p; ba.res = pl->res_tr.p;
@@ -675,7 +677,7 @@ extern "C" int fwi_b200_plan_time_kernel(fwi_b200_plan *pl, int which, int iters
       const double fz = 2.0 * g.nPml / g.nz, fx = 2.0 * g.nPml / g.nx;
       double b = 0;
       if (which <= 1) b = cells * (60.0 + 32.0 * (fz + fx));
-      else if (which == 2) b = box * 104.0;        // 10 R + 5 W state, 5 coeff, 3 R+W gradients
+      else if (which == 2) b = box * 140.0;        // 10 R + 5 W state, 5 coeff, 5 R+W imaging accumulators
       else b = cells * (60.0 + 64.0 * (fz + fx));  // 5 R + 5 W adjoint state, 5 coeff, psi/phi in the strips
       if (which == 1) b += (double)nb * 5 * g.f_len * 4.0;
       *alg_bytes = b;
