@@ -1,0 +1,88 @@
+// Device-side building blocks shared by the sm_100a step kernels: float4 "quads", the 4th-order staggered
+// differences on quads, and the TMA (cp.async.bulk.tensor) + mbarrier primitives the persistent kernels use to
+// stream halo tiles from HBM into shared memory while the previous tile is being computed.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#include "fwi_kernels.cuh"
+
+namespace fwi {
+namespace dev {
+
+constexpr float C1 = 1.125f;                     // 9/8   (el_stress.cu:45)
+constexpr float C2 = (float)(1.0 / 24.0);        // 1/24  (el_stress.cu:46)
+constexpr float SRC_SCALE = 2250000.0f;          // pow(1500,2)  utilities.cu:528
+
+struct F4 {
+  float v[4];
+};
+__device__ __forceinline__ F4 ld4(const float *p) {
+  const float4 t = *reinterpret_cast<const float4 *>(p);
+  return F4{{t.x, t.y, t.z, t.w}};
+}
+__device__ __forceinline__ void st4(float *p, const F4 &a) {
+  *reinterpret_cast<float4 *>(p) = make_float4(a.v[0], a.v[1], a.v[2], a.v[3]);
+}
+__device__ __forceinline__ F4 zero4() { return F4{{0.f, 0.f, 0.f, 0.f}}; }
+
+// 7 consecutive samples w[0..6] = f[z-2 .. z+4]  ->  D-z at the 4 cells z..z+3   (el_stress.cu:54)
+//   (c1 (f[z]-f[z-1]) - c2 (f[z+1]-f[z-2])) / h, with c1/h and c2/h folded into k1, k2
+__device__ __forceinline__ void dz_minus4(const F4 &A, const F4 &B, const F4 &C, float k1, float k2, float *out) {
+  const float w[7] = {A.v[2], A.v[3], B.v[0], B.v[1], B.v[2], B.v[3], C.v[0]};
+#pragma unroll
+  for (int k = 0; k < 4; k++) out[k] = k1 * (w[k + 2] - w[k + 1]) - k2 * (w[k + 3] - w[k]);
+}
+// samples u[0..6] = f[z-1 .. z+5]  ->  D+z at the 4 cells   (el_stress.cu:71)
+__device__ __forceinline__ void dz_plus4(const F4 &A, const F4 &B, const F4 &C, float k1, float k2, float *out) {
+  const float u[7] = {A.v[3], B.v[0], B.v[1], B.v[2], B.v[3], C.v[0], C.v[1]};
+#pragma unroll
+  for (int k = 0; k < 4; k++) out[k] = k1 * (u[k + 2] - u[k + 1]) - k2 * (u[k + 3] - u[k]);
+}
+// columns x-2, x-1, x, x+1 -> D-x ;  columns x-1, x, x+1, x+2 -> D+x   (same expression shape)
+__device__ __forceinline__ void dx4(const F4 &m2, const F4 &m1, const F4 &c0, const F4 &p1, float k1, float k2, float *out) {
+#pragma unroll
+  for (int k = 0; k < 4; k++) out[k] = k1 * (c0.v[k] - m1.v[k]) - k2 * (p1.v[k] - m2.v[k]);
+}
+
+// ---- shared-memory addresses, mbarrier, TMA ------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+// make the barrier initialisation visible to the async (TMA) proxy
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n"
+        "  .reg .pred p;\n"
+        "  mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "  selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+// one 3-D box (z, x, plane) HBM -> shared memory; completion is signalled on `bar` in bytes.
+// Out-of-range coordinates (negative z in the first tile row, x beyond the margins) are zero-filled by the TMA unit.
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, int c0, int c1, int c2, uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+}  // namespace dev
+}  // namespace fwi

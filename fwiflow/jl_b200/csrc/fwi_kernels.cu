@@ -23,7 +23,7 @@
 #include "fwi_kernels.cuh"
 
 #ifndef FWI_FP64_PROMOTE
-#define FWI_FP64_PROMOTE 1
+#define FWI_FP64_PROMOTE 0
 #endif
 
 namespace fwi {
@@ -131,254 +131,7 @@ constexpr int QS = (TILE_Z + 8) / 4;      // 16 quads: sigma-tile rows z0-4 .. z
 constexpr int QV = (TILE_Z + 16) / 4;     // 18 quads: velocity-tile rows z0-8 .. z0+TILE_Z+7
 constexpr int VP = QV * 4, SP = QS * 4;   // row pitches (floats)
 constexpr int VC = TILE_X + 6, SC = TILE_X + 4;
-constexpr size_t FWD_SMEM = (size_t)(2 * VC * VP + 3 * SC * SP) * sizeof(float);
 static_assert(TILE_Z % 4 == 0 && QS == 16, "half-warp per sigma column");
-
-template <bool SAVE>
-__global__ void __launch_bounds__(NTHREADS) fwd_step_kernel(const __grid_constant__ FwdArgs a) {
-  extern __shared__ __align__(16) float smem[];
-  float *s_vz = smem;
-  float *s_vx = s_vz + VC * VP;
-  float *s_zz = s_vx + VC * VP;
-  float *s_xx = s_zz + SC * SP;
-  float *s_xz = s_xx + SC * SP;
-  const Grid &g = a.g;
-  const int tid = threadIdx.x;
-  const int shot = blockIdx.x % a.batch;
-  const int tile = blockIdx.x / a.batch;
-  const int tz = tile % g.tiles_z, tx = tile / g.tiles_z;
-  const int z0 = tz * TILE_Z, x0 = tx * TILE_X;
-  const int ntiles = g.tiles_z * g.tiles_x;
-  const int r0 = a.st.rec_ptr[shot * (ntiles + 1) + tile];
-  const int r1 = a.st.rec_ptr[shot * (ntiles + 1) + tile + 1];
-  const int sz = a.st.src_z[shot], sx = a.st.src_x[shot];
-  const bool src_here = sz >= z0 - 4 && sz < z0 + TILE_Z + 4 && sx >= x0 - 2 && sx < x0 + TILE_X + 2;
-  if (z0 - 4 > g.az_hi && r1 == r0 && !src_here) return;  // nothing ever changes in this tile
-
-  const int P = g.P;
-  const int xmax = g.nx + XM - 1;
-  const float dt = g.dt, rdz = g.rdz, rdx = g.rdx;
-  float *sbase = a.state + (long long)shot * S_COUNT * g.plane + g.origin;
-  const long long pl = g.plane;
-  const int fin = a.cur ? S_FB : S_FA, fout = a.cur ? S_FA : S_FB;
-  const int pin = a.cur ? S_PSI_B : S_PSI_A, pout = a.cur ? S_PSI_A : S_PSI_B;
-  const float *fi = sbase + fin * pl;
-  float *fo = sbase + fout * pl;
-
-  // ---- phase 1: velocity tile (18 quads x 38 columns) -> shared, asynchronously ----
-  for (int i = tid; i < VC * QV; i += NTHREADS) {
-    const int col = i / QV, q = i - col * QV;
-    const int gx = min(x0 - 3 + col, xmax);
-    const int off = gx * P + (z0 - 8 + 4 * q);
-    cp_async16(s_vz + col * VP + 4 * q, fi + F_VZ * pl + off);
-    cp_async16(s_vx + col * VP + 4 * q, fi + F_VX * pl + off);
-  }
-  cp_async_wait_all();
-  __syncthreads();
-
-  const int zp_hi = g.nz - g.nPml - g.nPad - 1;  // z > zp_hi is bottom PML
-  const bool pml_tile = (z0 - 4 < g.nPml) || (z0 + TILE_Z + 3 > zp_hi) || (x0 - 2 < g.nPml) ||
-                        (x0 + TILE_X + 1 > g.nx - g.nPml - 1);
-  bool frame_tile = false;
-  float *frm = nullptr;
-  if (SAVE) {
-    frame_tile = !(z0 > g.zhi + 2 || z0 + TILE_Z - 1 < g.zlo - 2 || x0 > g.xhi + 2 || x0 + TILE_X - 1 < g.xlo - 2) &&
-                 !(z0 > g.zlo + 2 && z0 + TILE_Z - 1 < g.zhi - 2 && x0 > g.xlo + 2 && x0 + TILE_X - 1 < g.xhi - 2);
-    frm = a.frames + ((long long)shot * g.nSteps + a.it) * 5 * g.f_len;
-  }
-  const int h = tid >> 4, q = tid & 15;
-
-  // ---- phase 2: stress on 16 quads x 36 columns ----
-  {
-    const int gz = z0 - 4 + 4 * q;
-    for (int c = h; c < SC; c += NTHREADS / 16) {
-      const int gx = x0 - 2 + c;
-      const int off = min(gx, xmax) * P + gz;
-      const float *vzc = s_vz + (c + 1) * VP + 4 * (q + 1);
-      const float *vxc = s_vx + (c + 1) * VP + 4 * (q + 1);
-      float dvz_dz[4], dvx_dz[4], dvx_dx[4], dvz_dx[4];
-      const F4 zB = ld4(vzc), xB = ld4(vxc);
-      dz_minus4(ld4(vzc - 4), zB, ld4(vzc + 4), rdz, dvz_dz);
-      dz_plus4(ld4(vxc - 4), xB, ld4(vxc + 4), rdz, dvx_dz);
-      // the outermost halo columns only need one of the two x-derivatives; keep their reads inside the tile
-      dx4(ld4(vxc - (c > 0 ? 2 : 1) * VP), ld4(vxc - VP), xB, ld4(vxc + VP), rdx, dvx_dx);
-      dx4(ld4(vzc - VP), zB, ld4(vzc + VP), ld4(vzc + (c < SC - 1 ? 2 : 1) * VP), rdx, dvz_dx);
-      F4 szz = ld4(fi + F_SZZ * pl + off), sxx = ld4(fi + F_SXX * pl + off), sxz = ld4(fi + F_SXZ * pl + off);
-      const bool owner = q >= 1 && q <= TILE_Z / 4 && c >= 2 && c < TILE_X + 2 && gx < g.nx && gz < g.nz;
-      if (SAVE && frame_tile && owner) {
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-          const int fidx = frame_index(g, gz + k, gx);
-          if (fidx >= 0) {
-            frm[F_SZZ * g.f_len + fidx] = szz.v[k];
-            frm[F_SXX * g.f_len + fidx] = sxx.v[k];
-            frm[F_SXZ * g.f_len + fidx] = sxz.v[k];
-            frm[F_VZ * g.f_len + fidx] = zB.v[k];
-            frm[F_VX * g.f_len + fidx] = xB.v[k];
-          }
-        }
-      }
-      const bool col_act = gx >= 2 && gx <= g.ax_hi;
-      if (col_act && gz + 3 >= 2 && gz <= g.az_hi) {
-        if (pml_tile) {
-          if (gz < g.nPml || gz + 3 > zp_hi) {  // quad touches the z-PML
-            F4 m1 = ld4(sbase + (pin + PSI_VZ_Z) * pl + off), m2 = ld4(sbase + (pin + PSI_VX_Z) * pl + off);
-            const int zc = min(gz, P - 4);
-            const F4 b = ld4(a.pr.z + PR_B * P + zc), aa = ld4(a.pr.z + PR_A * P + zc), rk = ld4(a.pr.z + PR_RK * P + zc);
-            const F4 bh = ld4(a.pr.z + PR_BH * P + zc), ah = ld4(a.pr.z + PR_AH * P + zc), rkh = ld4(a.pr.z + PR_RKH * P + zc);
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-              const int z = gz + k;
-              if ((z < g.nPml || z > zp_hi) && z >= 2 && z <= g.az_hi) {
-                m1.v[k] = b.v[k] * m1.v[k] + aa.v[k] * dvz_dz[k];
-                dvz_dz[k] = dvz_dz[k] * rk.v[k] + m1.v[k];
-                m2.v[k] = bh.v[k] * m2.v[k] + ah.v[k] * dvx_dz[k];
-                dvx_dz[k] = dvx_dz[k] * rkh.v[k] + m2.v[k];
-              }
-            }
-            if (owner) {
-              st4(sbase + (pout + PSI_VZ_Z) * pl + off, m1);
-              st4(sbase + (pout + PSI_VX_Z) * pl + off, m2);
-            }
-          }
-          if (gx < g.nPml || gx > g.nx - g.nPml - 1) {  // column in the x-PML (stress flavour)
-            F4 m1 = ld4(sbase + (pin + PSI_VX_X) * pl + off), m2 = ld4(sbase + (pin + PSI_VZ_X) * pl + off);
-            const float *xp = a.pr.x + gx + XM;
-            const int n = a.pr.nxp;
-            const float b = xp[PR_B * n], aa = xp[PR_A * n], rk = xp[PR_RK * n];
-            const float bh = xp[PR_BH * n], ah = xp[PR_AH * n], rkh = xp[PR_RKH * n];
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-              const int z = gz + k;
-              if (z >= 2 && z <= g.az_hi) {
-                m1.v[k] = b * m1.v[k] + aa * dvx_dx[k];
-                dvx_dx[k] = dvx_dx[k] * rk + m1.v[k];
-                m2.v[k] = bh * m2.v[k] + ah * dvz_dx[k];
-                dvz_dx[k] = dvz_dx[k] * rkh + m2.v[k];
-              }
-            }
-            if (owner) {
-              st4(sbase + (pout + PSI_VX_X) * pl + off, m1);
-              st4(sbase + (pout + PSI_VZ_X) * pl + off, m2);
-            }
-          }
-        }
-        const F4 lam = ld4(a.m.lam + off), mu = ld4(a.m.mu + off), amu = ld4(a.m.amu + off);
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-          const int z = gz + k;
-          if (z >= 2 && z <= g.az_hi) {
-            szz.v[k] = stress_inc(szz.v[k], lam.v[k], mu.v[k], dvz_dz[k], dvx_dx[k], dt, 1.0f);
-            sxx.v[k] = stress_inc(sxx.v[k], lam.v[k], mu.v[k], dvx_dx[k], dvz_dz[k], dt, 1.0f);
-            sxz.v[k] = sxz.v[k] + amu.v[k] * (dvx_dz[k] + dvz_dx[k]) * dt;
-          }
-        }
-      }
-      if (gx == sx && sz >= gz && sz < gz + 4) {  // add_source (utilities.cu:521-537), point stamp
-        const float amp = a.st.stf[shot * g.nSteps + a.it];
-        const int k = sz - gz;
-#pragma unroll
-        for (int kk = 0; kk < 4; kk++)
-          if (kk == k) {
-            szz.v[kk] += SRC_SCALE * amp * dt;
-            sxx.v[kk] = (float)((double)sxx.v[kk] + 3.0 * (double)SRC_SCALE * (double)amp * (double)dt);
-          }
-      }
-      st4(s_zz + c * SP + 4 * q, szz);
-      st4(s_xx + c * SP + 4 * q, sxx);
-      st4(s_xz + c * SP + 4 * q, sxz);
-      if (owner) {
-        st4(fo + F_SZZ * pl + off, szz);
-        st4(fo + F_SXX * pl + off, sxx);
-        st4(fo + F_SXZ * pl + off, sxz);
-      }
-    }
-  }
-  __syncthreads();
-
-  // ---- recording at time index it+1 (utilities.cu:557-567) ----
-  for (int k = r0 + tid; k < r1; k += NTHREADS) {
-    const int loc = a.st.rec_loc[shot * a.st.nrp + k];
-    const int lz = loc & 0xffff, lx = loc >> 16;
-    const int j = (lx + 2) * SP + lz + 4;
-    a.traces[((long long)shot * g.nSteps + a.it + 1) * a.st.nrp + a.st.rec_id[shot * a.st.nrp + k]] =
-        (float)((double)s_zz[j] + 3.0 * (double)s_xx[j]);
-  }
-
-  // ---- phase 3: velocity on 14 quads x 32 columns ----
-  if (q < TILE_Z / 4) {
-    const int gz = z0 + 4 * q;
-    for (int c = h; c < TILE_X; c += NTHREADS / 16) {
-      const int gx = x0 + c;
-      if (gx >= g.nx || gz >= g.nz) continue;
-      const int off = gx * P + gz;
-      const float *zz = s_zz + (c + 2) * SP + 4 * (q + 1);
-      const float *xx = s_xx + (c + 2) * SP + 4 * (q + 1);
-      const float *xz = s_xz + (c + 2) * SP + 4 * (q + 1);
-      F4 vz = ld4(s_vz + (c + 3) * VP + 4 * (q + 2)), vx = ld4(s_vx + (c + 3) * VP + 4 * (q + 2));
-      if (gx >= 2 && gx <= g.ax_hi && gz + 3 >= 2 && gz <= g.az_hi) {
-        float dszz_dz[4], dsxz_dz[4], dsxz_dx[4], dsxx_dx[4];
-        const F4 xzB = ld4(xz);
-        dz_plus4(ld4(zz - 4), ld4(zz), ld4(zz + 4), rdz, dszz_dz);
-        dz_minus4(ld4(xz - 4), xzB, ld4(xz + 4), rdz, dsxz_dz);
-        dx4(ld4(xz - 2 * SP), ld4(xz - SP), xzB, ld4(xz + SP), rdx, dsxz_dx);
-        dx4(ld4(xx - SP), ld4(xx), ld4(xx + SP), ld4(xx + 2 * SP), rdx, dsxx_dx);
-        if (pml_tile) {
-          if (gz < g.nPml || gz + 3 > zp_hi) {
-            float *q1 = sbase + (S_PHI_A + PHI_SZZ_Z) * pl + off, *q2 = sbase + (S_PHI_A + PHI_SXZ_Z) * pl + off;
-            F4 m1 = ld4(q1), m2 = ld4(q2);
-            const int zc = min(gz, P - 4);
-            const F4 b = ld4(a.pr.z + PR_B * P + zc), aa = ld4(a.pr.z + PR_A * P + zc), rk = ld4(a.pr.z + PR_RK * P + zc);
-            const F4 bh = ld4(a.pr.z + PR_BH * P + zc), ah = ld4(a.pr.z + PR_AH * P + zc), rkh = ld4(a.pr.z + PR_RKH * P + zc);
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-              const int z = gz + k;
-              if ((z < g.nPml || z > zp_hi) && z >= 2 && z <= g.az_hi) {
-                m1.v[k] = bh.v[k] * m1.v[k] + ah.v[k] * dszz_dz[k];
-                dszz_dz[k] = dszz_dz[k] * rkh.v[k] + m1.v[k];
-                m2.v[k] = b.v[k] * m2.v[k] + aa.v[k] * dsxz_dz[k];
-                dsxz_dz[k] = dsxz_dz[k] * rk.v[k] + m2.v[k];
-              }
-            }
-            st4(q1, m1);
-            st4(q2, m2);
-          }
-          if (gx < g.nPml || gx > g.nx - g.nPml) {  // velocity flavour of the x-PML test (el_velocity.cu:56)
-            float *q1 = sbase + (S_PHI_A + PHI_SXZ_X) * pl + off, *q2 = sbase + (S_PHI_A + PHI_SXX_X) * pl + off;
-            F4 m1 = ld4(q1), m2 = ld4(q2);
-            const float *xp = a.pr.x + gx + XM;
-            const int n = a.pr.nxp;
-            const float b = xp[PR_B * n], aa = xp[PR_A * n], rk = xp[PR_RK * n];
-            const float bh = xp[PR_BH * n], ah = xp[PR_AH * n], rkh = xp[PR_RKH * n];
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-              const int z = gz + k;
-              if (z >= 2 && z <= g.az_hi) {
-                m1.v[k] = b * m1.v[k] + aa * dsxz_dx[k];
-                dsxz_dx[k] = dsxz_dx[k] * rk + m1.v[k];
-                m2.v[k] = bh * m2.v[k] + ah * dsxx_dx[k];
-                dsxx_dx[k] = dsxx_dx[k] * rkh + m2.v[k];
-              }
-            }
-            st4(q1, m1);
-            st4(q2, m2);
-          }
-        }
-        const F4 bya = ld4(a.m.bya + off), byb = ld4(a.m.byb + off);
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-          const int z = gz + k;
-          if (z >= 2 && z <= g.az_hi) {
-            vz.v[k] += (dszz_dz[k] + dsxz_dx[k]) * bya.v[k] * dt;
-            vx.v[k] += (dsxz_dz[k] + dsxx_dx[k]) * byb.v[k] * dt;
-          }
-        }
-      }
-      st4(fo + F_VZ * pl + off, vz);
-      st4(fo + F_VX * pl + off, vx);
-    }
-  }
-}
 
 // =================================================================================================
 // reverse-time reconstruction + imaging.  The imaging condition only ACCUMULATES the
@@ -389,7 +142,7 @@ __global__ void __launch_bounds__(NTHREADS) fwd_step_kernel(const __grid_constan
 constexpr int RC = TILE_X + 8;  // sigma^{it+1} tile columns (halo 4), rows as the velocity tile (QV quads)
 constexpr size_t REV_SMEM = (size_t)(3 * RC * VP + 2 * SC * SP) * sizeof(float);
 
-__global__ void __launch_bounds__(NTHREADS) rev_image_kernel(const __grid_constant__ BwdArgs a, int tz_first,
+__global__ void __launch_bounds__(NTHREADS, 2) rev_image_kernel(const __grid_constant__ BwdArgs a, int tz_first,
                                                                int tx_first, int ntz) {
   extern __shared__ __align__(16) float smem[];
   float *s_zz = smem;
@@ -603,7 +356,7 @@ __device__ __forceinline__ void adx4(const F4 &m2, const F4 &m1, const F4 &c0, c
 
 constexpr size_t ADJ_SMEM = (size_t)(3 * VC * VP + 2 * SC * SP) * sizeof(float);
 
-__global__ void __launch_bounds__(NTHREADS) adj_step_kernel(const __grid_constant__ BwdArgs a) {
+__global__ void __launch_bounds__(NTHREADS, 2) adj_step_kernel(const __grid_constant__ BwdArgs a) {
   extern __shared__ __align__(16) float smem[];
   float *s_zz = smem;
   float *s_xx = s_zz + VC * VP;
@@ -966,7 +719,7 @@ __global__ void __launch_bounds__(NTHREADS) adj_step_kernel(const __grid_constan
 // model preparation
 // =================================================================================================
 __global__ void model_transpose_kernel(Grid g, const double *__restrict__ lam_in, const double *__restrict__ mu_in,
-                                       const double *__restrict__ den_in, float *lam, float *mu, float *den) {
+                                       const double *__restrict__ den_in, float *model) {
   __shared__ float t[3][32][33];
   const int xb = blockIdx.x * 32, zb = blockIdx.y * 32;
   for (int r = threadIdx.y; r < 32; r += blockDim.y) {
@@ -983,16 +736,17 @@ __global__ void model_transpose_kernel(Grid g, const double *__restrict__ lam_in
     const int x = xb + r, z = zb + threadIdx.x;
     if (z < g.nz && x < g.nx) {
       const long long o = g.origin + (long long)x * g.P + z;
-      lam[o] = t[0][threadIdx.x][r];
-      mu[o] = t[1][threadIdx.x][r];
-      den[o] = t[2][threadIdx.x][r];
+      model[M_LAM * g.plane + o] = t[0][threadIdx.x][r];
+      model[M_MU * g.plane + o] = t[1][threadIdx.x][r];
+      model[M_DEN * g.plane + o] = t[2][threadIdx.x][r];
     }
   }
 }
 
-// mu_bar, averaged buoyancies (utilities.cu:125-152, Model.cu:67-73), max cp (utilities.cu:109-123)
-__global__ void model_derive_kernel(Grid g, const float *lam, const float *mu, const float *den, float *amu, float *bya,
-                                    float *byb, unsigned int *cpmax_bits) {
+// mu_bar, averaged buoyancies (utilities.cu:125-152, Model.cu:67-73), max cp (utilities.cu:109-123), and the
+// dt-scaled coefficient planes the step kernels read: lambda dt, (lambda + 2 mu) dt, mu_bar dt, byc_a dt, byc_b dt
+__global__ void model_derive_kernel(Grid g, float *model, unsigned int *cpmax_bits) {
+  const float *lam = model + M_LAM * g.plane, *mu = model + M_MU * g.plane, *den = model + M_DEN * g.plane;
   const int z = blockIdx.x * blockDim.x + threadIdx.x;
   const int x = blockIdx.y;
   float cp = 0.0f;
@@ -1006,9 +760,18 @@ __global__ void model_derive_kernel(Grid g, const float *lam, const float *mu, c
       ba = (float)(2.0 / (double)(den[o + 1] + den[o]));
       bb = (float)(2.0 / (double)(den[o + g.P] + den[o]));
     }
-    amu[o] = m;
-    bya[o] = ba;
-    byb[o] = bb;
+    model[M_AMU * g.plane + o] = m;
+    model[M_BYA * g.plane + o] = ba;
+    model[M_BYB * g.plane + o] = bb;
+    // active region of both half-steps: 2 <= z <= nz-nPad-3, 2 <= x <= nx-3 (el_stress.cu:52, el_velocity.cu:47);
+    // zero coefficients elsewhere make the update a no-op there without any predicate in the step kernels
+    const bool act = z >= 2 && z <= g.az_hi && x >= 2 && x <= g.ax_hi;
+    const double dt = act ? (double)g.dt : 0.0;
+    model[M_LDT * g.plane + o] = (float)((double)lam[o] * dt);
+    model[M_L2MDT * g.plane + o] = (float)(((double)lam[o] + 2.0 * (double)mu[o]) * dt);
+    model[M_AMUDT * g.plane + o] = (float)((double)m * dt);
+    model[M_BYADT * g.plane + o] = (float)((double)ba * dt);
+    model[M_BYBDT * g.plane + o] = (float)((double)bb * dt);
     cp = (float)sqrt(((double)lam[o] + 2.0 * (double)mu[o]) / (double)den[o]);
     if (!(cp > 0.0f)) cp = 0.0f;  // NaN / negative never wins the max
   }
@@ -1152,24 +915,24 @@ __global__ void finalize_kernel(Grid g, const float *gacc, int nslots, const flo
 // =================================================================================================
 // launchers
 // =================================================================================================
-size_t forward_smem_bytes() { return FWD_SMEM; }
 size_t reverse_smem_bytes() { return REV_SMEM; }
 size_t adjoint_smem_bytes() { return ADJ_SMEM; }
 
-void configure_kernels() {
-
-  cudaFuncSetAttribute(fwd_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM);
-  cudaFuncSetAttribute(fwd_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM);
-  cudaFuncSetAttribute(rev_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)REV_SMEM);
-  cudaFuncSetAttribute(adj_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ADJ_SMEM);
+template <typename K>
+static void configure_one(K kernel, size_t smem, const char *env, int carveout) {
+  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  // shared-memory carveout in percent (-1 = driver default).  The rest of the 256 KB stays L1: the kernels that
+  // read coefficients / CPML memory straight from global want it, the register-heavy adjoint step wants 2 CTAs.
+  if (const char *e = getenv(env)) carveout = atoi(e);
+  if (carveout >= 0) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carveout);
 }
 
-void launch_forward_step(const FwdArgs &a, bool save_frames, cudaStream_t s) {
-  const int blocks = a.batch * a.g.tiles_z * a.g.tiles_x;
-  if (save_frames)
-    fwd_step_kernel<true><<<blocks, NTHREADS, FWD_SMEM, s>>>(a);
-  else
-    fwd_step_kernel<false><<<blocks, NTHREADS, FWD_SMEM, s>>>(a);
+void configure_forward_kernels();  // fwi_forward.cu
+
+void configure_kernels() {
+  configure_forward_kernels();
+  configure_one(rev_image_kernel, REV_SMEM, "FWI_B200_CARVEOUT_REV", -1);
+  configure_one(adj_step_kernel, ADJ_SMEM, "FWI_B200_CARVEOUT_ADJ", -1);
 }
 
 void launch_reverse_imaging(const BwdArgs &a, cudaStream_t s) {
@@ -1185,14 +948,13 @@ void launch_adjoint_step(const BwdArgs &a, cudaStream_t s) {
   adj_step_kernel<<<blocks, NTHREADS, ADJ_SMEM, s>>>(a);
 }
 
-void launch_model_prep(const Grid &g, const double *d_lam, const double *d_mu, const double *d_den, float *lam,
-                       float *mu, float *den, float *amu, float *bya, float *byb, unsigned int *cpmax_bits,
-                       cudaStream_t s) {
+void launch_model_prep(const Grid &g, const double *d_lam, const double *d_mu, const double *d_den, float *model,
+                       unsigned int *cpmax_bits, cudaStream_t s) {
   dim3 tb(32, 8);
   dim3 tg((g.nx + 31) / 32, (g.nz + 31) / 32);
-  model_transpose_kernel<<<tg, tb, 0, s>>>(g, d_lam, d_mu, d_den, lam, mu, den);
+  model_transpose_kernel<<<tg, tb, 0, s>>>(g, d_lam, d_mu, d_den, model);
   dim3 dg((g.nz + 127) / 128, g.nx);
-  model_derive_kernel<<<dg, 128, 0, s>>>(g, lam, mu, den, amu, bya, byb, cpmax_bits);
+  model_derive_kernel<<<dg, 128, 0, s>>>(g, model, cpmax_bits);
 }
 
 void launch_residual(const ResidualArgs &a, int *nblocks_out, cudaStream_t s) {

@@ -9,6 +9,7 @@
 //   frames = [shot][step][field 0..4][flen]  saved boundary frames (5 layers)
 //   traces = [shot][step][nrp]  (receiver fastest -> coalesced record / inject)
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cstddef>
 #include <cstdint>
@@ -18,8 +19,9 @@ namespace fwi {
 constexpr int XM = 4;        // margin columns in x
 constexpr int SLACK = 256;   // floats before / after each plane
 constexpr int TILE_Z = 56;   // owner tile (z fastest): 14 float4 quads, 7 sectors of 32 B
-constexpr int TILE_X = 32;
-constexpr int NTHREADS = 256;
+constexpr int TILE_X = 28;   // owner tile columns: stress region 32 columns, velocity-input region 34
+constexpr int NTHREADS = 256;     // two-kernel backward path
+constexpr int NT_STEP = 512;      // persistent TMA-fed step kernels: 16 quads x 32 columns, one quad per thread
 
 // state slots
 enum Slot : int {
@@ -57,6 +59,21 @@ struct Grid {
 
 struct Model {
   const float *lam, *mu, *amu, *bya, *byb;  // plane pointers
+  const float *ldt;  // first of the 5 consecutive dt-scaled planes (M_LDT .. M_BYBDT), zero outside the active region
+};
+// model planes inside the plan's model buffer
+enum ModelPlane : int {
+  M_LAM = 0, M_MU = 1, M_DEN = 2, M_AMU = 3, M_BYA = 4, M_BYB = 5,
+  // time-step-scaled coefficients the step kernels consume (TMA boxes over planes 6..8 and 9..10)
+  M_LDT = 6, M_L2MDT = 7, M_AMUDT = 8, M_BYADT = 9, M_BYBDT = 10, M_COUNT = 11
+};
+
+// TMA descriptors (cuTensorMapEncodeTiled): 3-D tensors (z, x + XM, plane), float32, no swizzle, zero OOB fill.
+struct alignas(64) TmaMaps {
+  CUtensorMap v;    // state planes, box (TILE_Z+16, TILE_X+6, 2): velocity pair with halo 8 / 3
+  CUtensorMap s;    // state planes, box (TILE_Z+8,  TILE_X+4, 3): stress triple with halo 4 / 2
+  CUtensorMap c3;   // coefficient planes M_LDT.., box (TILE_Z+8, TILE_X+4, 3)
+  CUtensorMap c2;   // coefficient planes M_BYADT.., box (TILE_Z, TILE_X, 2)
 };
 
 struct Profiles {
@@ -85,6 +102,7 @@ struct FwdArgs {
   int batch;
   int it;              // time index of the state being advanced (it -> it+1)
   int cur;             // 0: read buffer A, write B; 1: the reverse
+  TmaMaps tm;
 };
 
 struct BwdArgs {
@@ -111,9 +129,9 @@ void launch_reverse_imaging(const BwdArgs &a, cudaStream_t s);
 void launch_adjoint_step(const BwdArgs &a, cudaStream_t s);
 
 // model preparation: double row-major MPa -> float planes (Pa), derived coefficients, max cp
-void launch_model_prep(const Grid &g, const double *d_lam, const double *d_mu, const double *d_den, float *lam,
-                       float *mu, float *den, float *amu, float *bya, float *byb, unsigned int *cpmax_bits,
-                       cudaStream_t s);
+// `model` = base of the M_COUNT model planes
+void launch_model_prep(const Grid &g, const double *d_lam, const double *d_mu, const double *d_den, float *model,
+                       unsigned int *cpmax_bits, cudaStream_t s);
 
 // residual: taper obs & syn, res = obs - syn (t=0 -> 0), partial sums of res^2, taper res
 struct ResidualArgs {
@@ -137,6 +155,8 @@ void launch_traces_to_rt(const float *tr, float *rt, int nrec, int nrp, int nSte
 void launch_finalize(const Grid &g, const float *gacc, int nslots, const float *mu, const float *misfit_half,
                      float *result, cudaStream_t s);
 
+// host: encode the TMA descriptors for a state buffer of `nplanes` planes and the model buffer
+void encode_tma_maps(const Grid &g, float *state, long long nplanes, float *model, TmaMaps *out);
 size_t forward_smem_bytes();
 size_t reverse_smem_bytes();
 size_t adjoint_smem_bytes();

@@ -79,6 +79,9 @@ struct fwi_b200_plan {
   DevBuf<double> partial;
   int partial_per_shot = 0;
   size_t trace_stride = 0;  // max_nrec * nSteps
+  TmaMaps tm{};             // TMA descriptors of the state / model buffers (re-encoded when `state` moves)
+  float *tm_state = nullptr;
+  size_t tm_state_n = 0;
 
   float *mplane(int k) { return model.p + (long long)k * g.plane; }
 
@@ -231,6 +234,11 @@ void choose_batch(fwi_b200_plan &pl, int max_batch) {
 void alloc_run_buffers(fwi_b200_plan &pl, int calc_id) {
   const Grid &g = pl.g;
   pl.state.alloc((size_t)pl.batch * S_COUNT * g.plane);
+  if (pl.tm_state != pl.state.p || pl.tm_state_n != pl.state.n) {
+    encode_tma_maps(g, pl.state.p, (long long)pl.batch * S_COUNT, pl.model.p, &pl.tm);
+    pl.tm_state = pl.state.p;
+    pl.tm_state_n = pl.state.n;
+  }
   pl.syn_tr.alloc((size_t)pl.batch * g.nSteps * pl.nrp);
   if (calc_id != 2) {
     pl.res_tr.alloc((size_t)pl.batch * g.nSteps * pl.nrp);
@@ -263,11 +271,12 @@ ShotTables tables_for(fwi_b200_plan &pl, int first) {
 
 Model model_of(fwi_b200_plan &pl) {
   Model m;
-  m.lam = pl.mplane(0) + pl.g.origin;
-  m.mu = pl.mplane(1) + pl.g.origin;
-  m.amu = pl.mplane(3) + pl.g.origin;
-  m.bya = pl.mplane(4) + pl.g.origin;
-  m.byb = pl.mplane(5) + pl.g.origin;
+  m.lam = pl.mplane(M_LAM) + pl.g.origin;
+  m.mu = pl.mplane(M_MU) + pl.g.origin;
+  m.amu = pl.mplane(M_AMU) + pl.g.origin;
+  m.bya = pl.mplane(M_BYA) + pl.g.origin;
+  m.byb = pl.mplane(M_BYB) + pl.g.origin;
+  m.ldt = pl.mplane(M_LDT) + pl.g.origin;
   return m;
 }
 
@@ -283,7 +292,7 @@ void run_locked(fwi_b200_plan &pl, int calc_id, cudaStream_t s) {
   const bool if_res = calc_id != 2, with_adj = calc_id == 1;
   Model m = model_of(pl);
   FwdArgs fa{};
-  fa.g = g; fa.m = m;
+  fa.g = g; fa.m = m; fa.tm = pl.tm;
   fa.pr.z = pl.zprof.p + g.P; fa.pr.x = pl.xprof.p; fa.pr.nxp = g.nx + 2 * XM;
   BwdArgs ba{};
   ba.g = g; ba.m = m; ba.pr = fa.pr;
@@ -412,7 +421,7 @@ extern "C" int fwi_b200_plan_create(fwi_b200_plan **out, const char *para_fname,
     configure_kernels();
     CUDA_OK(cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking));
     const Grid &g = pl->g;
-    pl->model.alloc((size_t)6 * g.plane);
+    pl->model.alloc((size_t)M_COUNT * g.plane);
     CUDA_OK(cudaMemset(pl->model.p, 0, pl->model.bytes()));
     pl->model_in.alloc((size_t)3 * g.nz * g.nx);
     pl->cpmax.alloc(1);
@@ -446,8 +455,7 @@ extern "C" int fwi_b200_plan_set_model(fwi_b200_plan *pl, const double *Lambda, 
     CUDA_OK(cudaMemcpyAsync(pl->model_in.p + n, Mu, n * sizeof(double), cudaMemcpyHostToDevice, s));
     CUDA_OK(cudaMemcpyAsync(pl->model_in.p + 2 * n, Den, n * sizeof(double), cudaMemcpyHostToDevice, s));
     CUDA_OK(cudaMemsetAsync(pl->cpmax.p, 0, sizeof(unsigned int), s));
-    launch_model_prep(g, pl->model_in.p, pl->model_in.p + n, pl->model_in.p + 2 * n, pl->mplane(0), pl->mplane(1),
-                      pl->mplane(2), pl->mplane(3), pl->mplane(4), pl->mplane(5), pl->cpmax.p, s);
+    launch_model_prep(g, pl->model_in.p, pl->model_in.p + n, pl->model_in.p + 2 * n, pl->model.p, pl->cpmax.p, s);
     pl->launches += 2;
     unsigned int bits = 0;
     CUDA_OK(cudaMemcpyAsync(&bits, pl->cpmax.p, sizeof(bits), cudaMemcpyDeviceToHost, s));
@@ -644,7 +652,7 @@ extern "C" int fwi_b200_plan_time_kernel(fwi_b200_plan *pl, int which, int iters
     cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : pl->stream;
     const int nb = std::min(pl->batch, pl->group);
     FwdArgs fa{};
-    fa.g = g; fa.m = model_of(*pl);
+    fa.g = g; fa.m = model_of(*pl); fa.tm = pl->tm;
     fa.pr.z = pl->zprof.p + g.P; fa.pr.x = pl->xprof.p; fa.pr.nxp = g.nx + 2 * XM;
     fa.st = tables_for(*pl, 0); fa.state = pl->state.p; fa.traces = pl->syn_tr.p; fa.frames = pl->frames.p; fa.batch = nb;
     BwdArgs ba{};
@@ -686,7 +694,7 @@ extern "C" int fwi_b200_plan_time_kernel(fwi_b200_plan *pl, int which, int iters
 }
 
 extern "C" const char *fwi_b200_version(void) {
-  return "{\"name\":\"fwi_b200\",\"abi\":1,\"arch\":\"sm_100a\",\"tile\":[64,32],\"fp64_promote\":true}";
+  return "{\"name\":\"fwi_b200\",\"abi\":1,\"arch\":\"sm_100a\",\"tile\":[56,32],\"fp64_promote\":false}";
 }
 
 extern "C" const char *fwi_b200_last_error(void) { return last_error_cstr(); }

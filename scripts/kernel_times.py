@@ -1,0 +1,24 @@
+"""Time the hot kernels of a plan with CUDA events (C-ABI fwi_b200_plan_time_kernel).
+   python scripts/kernel_times.py [c2|c3] [nshots] [iters]"""
+import os, sys, tempfile, json
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+from fwiflow.jl_b200 import ops, synthetic
+case = sys.argv[1] if len(sys.argv) > 1 else "c2"
+nshots = int(sys.argv[2]) if len(sys.argv) > 2 else 30
+iters = int(sys.argv[3]) if len(sys.argv) > 3 else 200
+c = synthetic.case_c2(nshots=nshots, nSteps=64) if case == "c2" else synthetic.case_c3(nshots=nshots, nSteps=64)
+para = c.write_files(tempfile.mkdtemp(prefix="kt_"))
+ids = np.arange(nshots, dtype=np.int32)
+p = ops.Plan(para, ids)
+p.set_stf(c.stf); p.set_model(*c.moduli("true")); p.run(2); p.write_obs_files()
+p.set_model(*c.moduli("init")); p.load_obs_files(); p.run(1)
+peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+names = {0: "fwd", 1: "fwd+save", 2: "rev_image", 3: "adj"}
+for w in names:
+    try:
+        ms, b = p.time_kernel(w, iters=iters)
+    except Exception as e:
+        print(names[w], "n/a", e); continue
+    print(f"{case} shots={nshots} batch={p.batch} {names[w]:10s} {ms*1e3:8.1f} us  alg {b/1e6:8.1f} MB  {b/ms/1e6:7.0f} GB/s  frac {b/ms/1e6/peak:.3f}")
