@@ -84,5 +84,59 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, i
       : "memory");
 }
 
+// ---- tile geometry shared by the persistent step kernels ----------------------------------------
+constexpr int SQ = (TILE_Z + 8) / 4;     // 16 quads per column of the "stress region": rows z0-4 .. z0+TILE_Z+3
+constexpr int SCOLS = TILE_X + 4;        // 32 columns of the stress region: x0-2 .. x0+TILE_X+1
+constexpr int SPITCH = TILE_Z + 8;       // 64
+constexpr int VCOLS = TILE_X + 6;        // 34 columns with halo 3: x0-3 .. x0+TILE_X+2
+constexpr int WCOLS = TILE_X + 8;        // 36 columns with halo 4: x0-4 .. x0+TILE_X+3
+constexpr int VPITCH = TILE_Z + 16;      // 72: rows z0-8 .. z0+TILE_Z+7
+constexpr int NCOMPUTE = SQ * SCOLS;     // 512 threads: one quad of the stress region each
+constexpr int PRODUCER_TID = NCOMPUTE - 32;  // lane 0 of the warp holding columns 30, 31 (never owners)
+static_assert(SQ == 16 && NCOMPUTE == NT_STEP, "one quad per thread, 16 quads per half-warp");
+
+enum : int { TF_PML = 1, TF_FRAME = 2, TF_SRC = 4 };
+
+struct __align__(16) TileDesc {  // built by the producer lane, read (broadcast) by every thread
+  long long soff;   // element offset of (z0, x0) in this shot's slot-0 plane: shot * S_COUNT * plane + x0 * P + z0
+  int moff;         // x0 * P + z0 (model planes)
+  int flags;
+  int z0, x0, shot, tile;
+  int sz, sx;       // source cell
+  int r0, r1;       // receiver range (CSR over tiles)
+  int pad[4];
+};
+static_assert(sizeof(TileDesc) == 64, "descriptor size");
+
+// Boundary frames: per step and field [left 5 columns | right 5 columns | top 5 rows | bottom 5 rows] of the ring
+// that starts 2 cells outside the inner box (Boundary.cu:17-27, utilities.cu:361-424).  One instance per thread
+// and tile: the column part of the index is computed once, idx(z) is then 3-4 instructions per cell.
+struct FrameCol {
+  int colbase, midbase, zlo2, zhi2, zlo_in, zhi_in;
+  bool xin;
+  __device__ __forceinline__ FrameCol(const Grid &g, int gx) {
+    xin = gx >= g.xlo - 2 && gx <= g.xhi + 2;
+    colbase = -1;
+    if (gx <= g.xlo + 2) colbase = (gx - (g.xlo - 2)) * g.f_nzB;
+    else if (gx >= g.xhi - 2) colbase = (5 + gx - (g.xhi - 2)) * g.f_nzB;
+    midbase = 10 * g.f_nzB + (gx - (g.xlo + 3)) * 10;
+    zlo2 = g.zlo - 2; zhi2 = g.zhi + 2; zlo_in = g.zlo + 2; zhi_in = g.zhi - 2;
+  }
+  __device__ __forceinline__ int idx(int z) const {
+    if (!xin || z < zlo2 || z > zhi2) return -1;
+    if (colbase >= 0) return colbase + z - zlo2;
+    if (z <= zlo_in) return midbase + z - zlo2;
+    if (z >= zhi_in) return midbase + 5 + z - zhi_in;
+    return -1;
+  }
+};
+__device__ __forceinline__ bool tile_touches_frame(const Grid &g, int z0, int x0) {
+  return !(z0 > g.zhi + 2 || z0 + TILE_Z - 1 < g.zlo - 2 || x0 > g.xhi + 2 || x0 + TILE_X - 1 < g.xlo - 2) &&
+         !(z0 > g.zlo + 2 && z0 + TILE_Z - 1 < g.zhi - 2 && x0 > g.xlo + 2 && x0 + TILE_X - 1 < g.xhi - 2);
+}
+
 }  // namespace dev
+
+int sm_count();  // fwi_forward.cu
+
 }  // namespace fwi

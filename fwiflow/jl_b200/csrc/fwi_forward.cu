@@ -31,37 +31,15 @@ using namespace dev;
 
 namespace {
 
-constexpr int SQ = (TILE_Z + 8) / 4;     // 16 stress quads per column: rows z0-4 .. z0+TILE_Z+3
-constexpr int SCOLS = TILE_X + 4;        // 32 stress columns: x0-2 .. x0+TILE_X+1
-constexpr int SPITCH = TILE_Z + 8;       // 64
-constexpr int VCOLS = TILE_X + 6;        // 34 velocity columns: x0-3 .. x0+TILE_X+2
-constexpr int VPITCH = TILE_Z + 16;      // 72: rows z0-8 .. z0+TILE_Z+7
 constexpr int NS = 3;                    // ring stages
-constexpr int NCOMPUTE = SQ * SCOLS;     // 512 compute threads
 constexpr int NTHREADS_FWD = NCOMPUTE;
-constexpr int PRODUCER_TID = NCOMPUTE - 32;   // lane 0 of the warp holding stress columns 30, 31 (never owners)
 constexpr int V_BYTES = 2 * VCOLS * VPITCH * 4;
 constexpr int S_BYTES = 3 * SCOLS * SPITCH * 4;
 constexpr int STAGE_BYTES = V_BYTES + S_BYTES;
 constexpr int SNEW_BYTES = 3 * SCOLS * SPITCH * 4;
 constexpr int DESC_BYTES = 64;
 constexpr size_t FWD_SMEM = (size_t)NS * STAGE_BYTES + 2 * SNEW_BYTES + (NS + 1) * DESC_BYTES + NS * 8 + 128;
-static_assert(SQ == 16 && NCOMPUTE == NT_STEP, "one stress quad per compute thread, 16 quads per half-warp");
 static_assert(V_BYTES % 128 == 0 && S_BYTES % 128 == 0, "TMA destination alignment");
-
-enum : int { TF_PML = 1, TF_FRAME = 2, TF_SRC = 4 };
-
-struct __align__(16) TileDesc {  // built by the producer, read (broadcast) by every compute thread
-  long long soff;   // element offset of (z0, x0) in this shot's slot-0 plane: shot * S_COUNT * plane + x0 * P + z0
-  int moff;         // x0 * P + z0 (model planes)
-  int flags;
-  int z0, x0, shot, tile;
-  int sz, sx;       // source cell
-  int r0, r1;       // receiver range (CSR over tiles)
-  int pad[4];
-};
-static_assert(sizeof(TileDesc) == DESC_BYTES, "descriptor size");
-
 
 template <bool SAVE>
 __global__ void __launch_bounds__(NTHREADS_FWD, 1) fwd_step_kernel(const __grid_constant__ FwdArgs a) {
@@ -102,8 +80,7 @@ __global__ void __launch_bounds__(NTHREADS_FWD, 1) fwd_step_kernel(const __grid_
     d.r1 = a.st.rec_ptr[shot * (ntiles + 1) + tile + 1];
     int fl = 0;
     if ((z0 - 4 < g.nPml) || (z0 + TILE_Z + 3 > zp_hi) || (x0 - 2 < g.nPml) || (x0 + TILE_X + 1 > g.nx - g.nPml - 1)) fl |= TF_PML;
-    if (!(z0 > g.zhi + 2 || z0 + TILE_Z - 1 < g.zlo - 2 || x0 > g.xhi + 2 || x0 + TILE_X - 1 < g.xlo - 2) &&
-        !(z0 > g.zlo + 2 && z0 + TILE_Z - 1 < g.zhi - 2 && x0 > g.xlo + 2 && x0 + TILE_X - 1 < g.xhi - 2)) fl |= TF_FRAME;
+    if (tile_touches_frame(g, z0, x0)) fl |= TF_FRAME;
     if (sz >= z0 - 4 && sz < z0 + TILE_Z + 4 && sx >= x0 - 2 && sx < x0 + TILE_X + 2) fl |= TF_SRC;
     d.flags = fl;
     d.pad[0] = d.pad[1] = d.pad[2] = d.pad[3] = 0;
@@ -182,21 +159,10 @@ __global__ void __launch_bounds__(NTHREADS_FWD, 1) fwd_step_kernel(const __grid_
 
     if (SAVE && (d.flags & TF_FRAME) && owner) {  // from_bnd x5: state at time `it`, before the update (libCUFD.cu:206)
       float *frm = a.frames + ((long long)d.shot * g.nSteps + a.it) * 5 * g.f_len;
-      // the frame is stored as [left 5 columns | right 5 columns | top 5 rows | bottom 5 rows]   (Boundary.cu:17-27)
-      const bool xin = gx >= g.xlo - 2 && gx <= g.xhi + 2;
-      int colbase = -1;
-      if (gx <= g.xlo + 2) colbase = (gx - (g.xlo - 2)) * g.f_nzB;
-      else if (gx >= g.xhi - 2) colbase = (5 + gx - (g.xhi - 2)) * g.f_nzB;
-      const int midbase = 10 * g.f_nzB + (gx - (g.xlo + 3)) * 10;
+      const FrameCol fc(g, gx);
 #pragma unroll
       for (int kk = 0; kk < 4; kk++) {
-        const int z = gz + kk;
-        int fidx = -1;
-        if (xin && z >= g.zlo - 2 && z <= g.zhi + 2) {
-          if (colbase >= 0) fidx = colbase + z - (g.zlo - 2);
-          else if (z <= g.zlo + 2) fidx = midbase + z - (g.zlo - 2);
-          else if (z >= g.zhi - 2) fidx = midbase + 5 + z - (g.zhi - 2);
-        }
+        const int fidx = fc.idx(gz + kk);
         if (fidx >= 0) {
           frm[F_SZZ * g.f_len + fidx] = szz.v[kk];
           frm[F_SXX * g.f_len + fidx] = sxx.v[kk];
@@ -349,6 +315,8 @@ __global__ void __launch_bounds__(NTHREADS_FWD, 1) fwd_step_kernel(const __grid_
   }
 }
 
+}  // namespace
+
 int sm_count() {
   static int n = 0;
   if (n == 0) {
@@ -359,6 +327,8 @@ int sm_count() {
   }
   return n;
 }
+
+namespace {
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -394,8 +364,10 @@ void encode_one(CUtensorMap *m, const Grid &g, float *plane0, long long nplanes,
 void encode_tma_maps(const Grid &g, float *state, long long nplanes, float *model, TmaMaps *out) {
   encode_one(&out->v, g, state, nplanes, VPITCH, VCOLS, 2);
   encode_one(&out->s, g, state, nplanes, SPITCH, SCOLS, 3);
-  encode_one(&out->c3, g, model + (long long)M_LDT * g.plane, 3, SPITCH, SCOLS, 3);
-  encode_one(&out->c2, g, model + (long long)M_BYADT * g.plane, 2, TILE_Z, TILE_X, 2);
+  encode_one(&out->sw, g, state, nplanes, TILE_Z + 16, TILE_X + 8, 3);
+  encode_one(&out->vn, g, state, nplanes, TILE_Z + 8, TILE_X + 4, 2);
+  encode_one(&out->s3, g, state, nplanes, TILE_Z + 16, TILE_X + 6, 3);
+  (void)model;
 }
 
 size_t forward_smem_bytes() { return FWD_SMEM; }

@@ -134,208 +134,6 @@ constexpr int VC = TILE_X + 6, SC = TILE_X + 4;
 static_assert(TILE_Z % 4 == 0 && QS == 16, "half-warp per sigma column");
 
 // =================================================================================================
-// reverse-time reconstruction + imaging.  The imaging condition only ACCUMULATES the
-// per-cell source terms (5 planes: lambda, mu-direct, mu-spray amplitude S, rho-a, rho-b); the
-// reference's 4-point "spray" (el_stress.cu:113-124, el_velocity.cu:101-110) is linear in those, so it
-// is applied once, as a deterministic gather, by finalize_kernel.
-// =================================================================================================
-constexpr int RC = TILE_X + 8;  // sigma^{it+1} tile columns (halo 4), rows as the velocity tile (QV quads)
-constexpr size_t REV_SMEM = (size_t)(3 * RC * VP + 2 * SC * SP) * sizeof(float);
-
-__global__ void __launch_bounds__(NTHREADS, 2) rev_image_kernel(const __grid_constant__ BwdArgs a, int tz_first,
-                                                               int tx_first, int ntz) {
-  extern __shared__ __align__(16) float smem[];
-  float *s_zz = smem;
-  float *s_xx = s_zz + RC * VP;
-  float *s_xz = s_xx + RC * VP;
-  float *s_vz = s_xz + RC * VP;
-  float *s_vx = s_vz + SC * SP;
-  const Grid &g = a.g;
-  const int tid = threadIdx.x;
-  const int shot = blockIdx.x % a.batch;
-  const int tile = blockIdx.x / a.batch;
-  const int tz = tz_first + tile % ntz, tx = tx_first + tile / ntz;
-  const int z0 = tz * TILE_Z, x0 = tx * TILE_X;
-  const int P = g.P;
-  const int xmax = g.nx + XM - 1;
-  const float dt = g.dt, rdz = g.rdz, rdx = g.rdx;
-  const long long pl = g.plane;
-  float *sbase = a.state + (long long)shot * S_COUNT * pl + g.origin;
-  const float *fi = sbase + (a.cur_f ? S_FB : S_FA) * pl;
-  float *fo = sbase + (a.cur_f ? S_FA : S_FB) * pl;
-  const float *ai = sbase + (a.cur_a ? S_AB : S_AA) * pl;
-  float *acc = a.gacc + (long long)shot * G_COUNT * pl + g.origin;
-  const float *frm = a.frames + ((long long)shot * g.nSteps + a.it) * 5 * g.f_len;
-  const int sz = a.st.src_z[shot], sx = a.st.src_x[shot];
-
-  // ---- phase 1: sigma^{it+1}, 18 quads x 40 columns ----
-  for (int i = tid; i < RC * QV; i += NTHREADS) {
-    const int col = i / QV, q = i - col * QV;
-    const int gx = min(x0 - 4 + col, xmax);
-    const int off = gx * P + (z0 - 8 + 4 * q);
-    cp_async16(s_zz + col * VP + 4 * q, fi + F_SZZ * pl + off);
-    cp_async16(s_xx + col * VP + 4 * q, fi + F_SXX * pl + off);
-    cp_async16(s_xz + col * VP + 4 * q, fi + F_SXZ * pl + off);
-  }
-  cp_async_wait_all();
-  __syncthreads();
-
-  const bool frame_tile =
-      !(z0 - 4 > g.zlo + 2 && z0 + TILE_Z + 3 < g.zhi - 2 && x0 - 2 > g.xlo + 2 && x0 + TILE_X + 1 < g.xhi - 2);
-  const int h = tid >> 4, q = tid & 15;
-
-  // ---- phase 2: v^{it} on 16 quads x 36 columns; rho imaging terms on the owner cells ----
-  {
-    const int gz = z0 - 4 + 4 * q;
-    for (int c = h; c < SC; c += NTHREADS / 16) {
-      const int gx = x0 - 2 + c;
-      const int off = min(gx, xmax) * P + gz;
-      F4 vz = ld4(fi + F_VZ * pl + off), vx = ld4(fi + F_VX * pl + off);
-      const bool owner = q >= 1 && q <= TILE_Z / 4 && c >= 2 && c < TILE_X + 2 && gx < g.nx && gz < g.nz;
-      const bool colbox = gx >= g.xlo && gx <= g.xhi;
-      if (colbox && gz + 3 >= g.zlo && gz <= g.zhi) {
-        const float *zz = s_zz + (c + 2) * VP + 4 * (q + 1);
-        const float *xx = s_xx + (c + 2) * VP + 4 * (q + 1);
-        const float *xz = s_xz + (c + 2) * VP + 4 * (q + 1);
-        float d1[4], d2[4], d3[4], d4[4];
-        const F4 xzB = ld4(xz);
-        dz_plus4(ld4(zz - 4), ld4(zz), ld4(zz + 4), rdz, d1);             // dszz_dz
-        dx4(ld4(xz - 2 * VP), ld4(xz - VP), xzB, ld4(xz + VP), rdx, d2);  // dsxz_dx
-        dz_minus4(ld4(xz - 4), xzB, ld4(xz + 4), rdz, d3);                // dsxz_dz
-        dx4(ld4(xx - VP), ld4(xx), ld4(xx + VP), ld4(xx + 2 * VP), rdx, d4);  // dsxx_dx
-        const F4 bya = ld4(a.m.bya + off), byb = ld4(a.m.byb + off);
-        F4 ga{{0, 0, 0, 0}}, gb{{0, 0, 0, 0}};
-        F4 vza{{0, 0, 0, 0}}, vxa{{0, 0, 0, 0}};
-        if (owner) {
-          vza = ld4(ai + F_VZ * pl + off);
-          vxa = ld4(ai + F_VX * pl + off);
-        }
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-          const int z = gz + k;
-          if (z >= g.zlo && z <= g.zhi) {
-            const float ea = d1[k] + d2[k], eb = d3[k] + d4[k];
-            vz.v[k] -= ea * bya.v[k] * dt;
-            vx.v[k] -= eb * byb.v[k] * dt;
-            // el_velocity.cu:101-104
-#if FWI_FP64_PROMOTE
-            ga.v[k] = (float)((double)(-vza.v[k] * ea * dt) * (-((double)bya.v[k] * (double)bya.v[k]) / 2.0));
-            gb.v[k] = (float)((double)(-vxa.v[k] * eb * dt) * (-((double)byb.v[k] * (double)byb.v[k]) / 2.0));
-#else
-            ga.v[k] = (vza.v[k] * ea * dt) * (0.5f * bya.v[k] * bya.v[k]);
-            gb.v[k] = (vxa.v[k] * eb * dt) * (0.5f * byb.v[k] * byb.v[k]);
-#endif
-          }
-        }
-        if (owner) {
-          float *pa = acc + G_RHO_A * pl + off, *pb = acc + G_RHO_B * pl + off;
-          F4 A = ld4(pa), B = ld4(pb);
-#pragma unroll
-          for (int k = 0; k < 4; k++) {
-            A.v[k] += ga.v[k];
-            B.v[k] += gb.v[k];
-          }
-          st4(pa, A);
-          st4(pb, B);
-        }
-      }
-      bool in_rect = gx >= g.xlo - 2 && gx <= g.xhi + 2 && gz + 3 >= g.zlo - 2 && gz <= g.zhi + 2;
-      if (frame_tile && in_rect) {
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-          const int fidx = frame_index(g, gz + k, gx);
-          if (fidx >= 0) {
-            vz.v[k] = frm[F_VZ * g.f_len + fidx];
-            vx.v[k] = frm[F_VX * g.f_len + fidx];
-          }
-        }
-      }
-      st4(s_vz + c * SP + 4 * q, vz);
-      st4(s_vx + c * SP + 4 * q, vx);
-      if (owner && in_rect) {
-        st4(fo + F_VZ * pl + off, vz);
-        st4(fo + F_VX * pl + off, vx);
-      }
-    }
-  }
-  __syncthreads();
-
-  // ---- phase 3: sigma^{it} on 14 quads x 32 columns; lambda / mu imaging terms ----
-  if (q < TILE_Z / 4) {
-    const int gz = z0 + 4 * q;
-    for (int c = h; c < TILE_X; c += NTHREADS / 16) {
-      const int gx = x0 + c;
-      if (gx >= g.nx || gz >= g.nz) continue;
-      if (!(gx >= g.xlo - 2 && gx <= g.xhi + 2 && gz + 3 >= g.zlo - 2 && gz <= g.zhi + 2)) continue;
-      const int off = gx * P + gz;
-      const int j = (c + 4) * VP + 4 * (q + 2);
-      F4 szz = ld4(s_zz + j), sxx = ld4(s_xx + j), sxz = ld4(s_xz + j);
-      if (gx >= g.xlo && gx <= g.xhi && gz + 3 >= g.zlo && gz <= g.zhi) {
-        const float *pz = s_vz + (c + 2) * SP + 4 * (q + 1);
-        const float *px = s_vx + (c + 2) * SP + 4 * (q + 1);
-        float dvz_dz[4], dvx_dz[4], dvx_dx[4], dvz_dx[4];
-        const F4 zB = ld4(pz), xB = ld4(px);
-        dz_minus4(ld4(pz - 4), zB, ld4(pz + 4), rdz, dvz_dz);
-        dz_plus4(ld4(px - 4), xB, ld4(px + 4), rdz, dvx_dz);
-        dx4(ld4(px - 2 * SP), ld4(px - SP), xB, ld4(px + SP), rdx, dvx_dx);
-        dx4(ld4(pz - SP), zB, ld4(pz + SP), ld4(pz + 2 * SP), rdx, dvz_dx);
-        const F4 lam = ld4(a.m.lam + off), mu = ld4(a.m.mu + off), amu = ld4(a.m.amu + off);
-        const F4 za = ld4(ai + F_SZZ * pl + off), xa = ld4(ai + F_SXX * pl + off), xza = ld4(ai + F_SXZ * pl + off);
-        float *pgl = acc + G_LAM * pl + off, *pgm = acc + G_MU * pl + off, *pgs = acc + G_MUS * pl + off;
-        F4 gl = ld4(pgl), gm = ld4(pgm), gs = ld4(pgs);
-        if (gx == sx && sz >= gz && sz < gz + 4) {  // add_source(isFor=false): utilities.cu:538-551
-          const float amp = a.st.stf[shot * g.nSteps + a.it];
-#pragma unroll
-          for (int k = 0; k < 4; k++)
-            if (k == sz - gz) {
-              szz.v[k] -= SRC_SCALE * amp * dt;
-              sxx.v[k] = (float)((double)sxx.v[k] - 3.0 * (double)SRC_SCALE * (double)amp * (double)dt);
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-          const int z = gz + k;
-          if (z >= g.zlo && z <= g.zhi) {
-            szz.v[k] = stress_inc(szz.v[k], lam.v[k], mu.v[k], dvz_dz[k], dvx_dx[k], dt, -1.0f);
-            sxx.v[k] = stress_inc(sxx.v[k], lam.v[k], mu.v[k], dvx_dx[k], dvz_dz[k], dt, -1.0f);
-            const float e = dvx_dz[k] + dvz_dx[k];
-            sxz.v[k] -= amu.v[k] * e * dt;
-            // el_stress.cu:109-116
-#if FWI_FP64_PROMOTE
-            gl.v[k] = (float)((double)gl.v[k] + (double)(-(za.v[k] + xa.v[k]) * (dvz_dz[k] + dvx_dx[k]) * dt) * 1e6);
-            gm.v[k] = (float)((double)gm.v[k] + (-2.0 * (double)za.v[k] * (double)dvz_dz[k] * (double)dt -
-                                                 2.0 * (double)xa.v[k] * (double)dvx_dx[k] * (double)dt) * 1e6);
-#else
-            gl.v[k] += -(za.v[k] + xa.v[k]) * (dvz_dz[k] + dvx_dx[k]) * dt * 1e6f;
-            gm.v[k] += (-2.0f * za.v[k] * dvz_dz[k] * dt - 2.0f * xa.v[k] * dvx_dx[k] * dt) * 1e6f;
-#endif
-            //  amu / sum(1/mu) == amu^2 / 4  (amu = 4 / sum(1/mu)); zero where amu == 0
-            gs.v[k] += -xza.v[k] * e * dt * (250000.0f * amu.v[k]) * amu.v[k];
-          }
-        }
-        st4(pgl, gl);
-        st4(pgm, gm);
-        st4(pgs, gs);
-      }
-      if (frame_tile) {
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-          const int fidx = frame_index(g, gz + k, gx);
-          if (fidx >= 0) {
-            szz.v[k] = frm[F_SZZ * g.f_len + fidx];
-            sxx.v[k] = frm[F_SXX * g.f_len + fidx];
-            sxz.v[k] = frm[F_SXZ * g.f_len + fidx];
-          }
-        }
-      }
-      st4(fo + F_SZZ * pl + off, szz);
-      st4(fo + F_SXX * pl + off, sxx);
-      st4(fo + F_SXZ * pl + off, sxz);
-    }
-  }
-}
-
-// =================================================================================================
 // adjoint step
 // =================================================================================================
 // adjoint-kernel spelling of the differences (el_stress_adj.cu:54-61): (-c1*(..) + c2*(..)) / h
@@ -915,7 +713,6 @@ __global__ void finalize_kernel(Grid g, const float *gacc, int nslots, const flo
 // =================================================================================================
 // launchers
 // =================================================================================================
-size_t reverse_smem_bytes() { return REV_SMEM; }
 size_t adjoint_smem_bytes() { return ADJ_SMEM; }
 
 template <typename K>
@@ -927,20 +724,13 @@ static void configure_one(K kernel, size_t smem, const char *env, int carveout) 
   if (carveout >= 0) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carveout);
 }
 
-void configure_forward_kernels();  // fwi_forward.cu
+void configure_forward_kernels();   // fwi_forward.cu
+void configure_backward_kernels();  // fwi_backward.cu
 
 void configure_kernels() {
   configure_forward_kernels();
-  configure_one(rev_image_kernel, REV_SMEM, "FWI_B200_CARVEOUT_REV", -1);
+  configure_backward_kernels();
   configure_one(adj_step_kernel, ADJ_SMEM, "FWI_B200_CARVEOUT_ADJ", -1);
-}
-
-void launch_reverse_imaging(const BwdArgs &a, cudaStream_t s) {
-  const Grid &g = a.g;
-  const int tz0 = max(g.zlo - 2, 0) / TILE_Z, tz1 = min(g.zhi + 2, g.nz - 1) / TILE_Z;
-  const int tx0 = max(g.xlo - 2, 0) / TILE_X, tx1 = min(g.xhi + 2, g.nx - 1) / TILE_X;
-  const int ntz = tz1 - tz0 + 1, ntx = tx1 - tx0 + 1;
-  rev_image_kernel<<<a.batch * ntz * ntx, NTHREADS, REV_SMEM, s>>>(a, tz0, tx0, ntz);
 }
 
 void launch_adjoint_step(const BwdArgs &a, cudaStream_t s) {

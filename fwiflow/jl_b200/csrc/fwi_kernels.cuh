@@ -72,8 +72,9 @@ enum ModelPlane : int {
 struct alignas(64) TmaMaps {
   CUtensorMap v;    // state planes, box (TILE_Z+16, TILE_X+6, 2): velocity pair with halo 8 / 3
   CUtensorMap s;    // state planes, box (TILE_Z+8,  TILE_X+4, 3): stress triple with halo 4 / 2
-  CUtensorMap c3;   // coefficient planes M_LDT.., box (TILE_Z+8, TILE_X+4, 3)
-  CUtensorMap c2;   // coefficient planes M_BYADT.., box (TILE_Z, TILE_X, 2)
+  CUtensorMap sw;   // state planes, box (TILE_Z+16, TILE_X+8, 3): stress triple with halo 8 / 4 (reverse step)
+  CUtensorMap vn;   // state planes, box (TILE_Z+8,  TILE_X+4, 2): velocity pair with halo 4 / 2 (reverse / adjoint step)
+  CUtensorMap s3;   // state planes, box (TILE_Z+16, TILE_X+6, 3): stress triple with halo 8 / 3 (adjoint step)
 };
 
 struct Profiles {
@@ -119,6 +120,7 @@ struct BwdArgs {
   int it;
   int cur_f;           // forward-field buffer holding state it+1
   int cur_a;           // adjoint buffer holding the pre-update adjoint state
+  TmaMaps tm;
 };
 
 // one forward time step for `batch` shots: stress + source + velocity + record (+ frame save)

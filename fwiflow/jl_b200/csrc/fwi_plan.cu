@@ -295,7 +295,7 @@ void run_locked(fwi_b200_plan &pl, int calc_id, cudaStream_t s) {
   fa.g = g; fa.m = m; fa.tm = pl.tm;
   fa.pr.z = pl.zprof.p + g.P; fa.pr.x = pl.xprof.p; fa.pr.nxp = g.nx + 2 * XM;
   BwdArgs ba{};
-  ba.g = g; ba.m = m; ba.pr = fa.pr;
+  ba.g = g; ba.m = m; ba.pr = fa.pr; ba.tm = pl.tm;
 
   if (with_adj) {
     CUDA_OK(cudaMemsetAsync(pl.gacc.p, 0, pl.gacc.bytes(), s));
@@ -656,7 +656,7 @@ extern "C" int fwi_b200_plan_time_kernel(fwi_b200_plan *pl, int which, int iters
     fa.pr.z = pl->zprof.p + g.P; fa.pr.x = pl->xprof.p; fa.pr.nxp = g.nx + 2 * XM;
     fa.st = tables_for(*pl, 0); fa.state = pl->state.p; fa.traces = pl->syn_tr.p; fa.frames = pl->frames.p; fa.batch = nb;
     BwdArgs ba{};
-    ba.g = g; ba.m = fa.m; ba.pr = fa.pr; ba.st = fa.st; ba.state = pl->state.p; ba.res = pl->res_tr.p;
+    ba.g = g; ba.m = fa.m; ba.pr = fa.pr; ba.tm = pl->tm; ba.st = fa.st; ba.state = pl->state.p; ba.res = pl->res_tr.p;
     ba.frames = pl->frames.p; ba.gacc = pl->gacc.p; ba.stf_grad = pl->stf_grad.p; ba.batch = nb;
     cudaEvent_t e0, e1;
     CUDA_OK(cudaEventCreate(&e0));
