@@ -243,12 +243,372 @@ rev_image_kernel(const __grid_constant__ BwdArgs a, int tz_first, int tx_first, 
   }
 }
 
+
+// =================================================================================================
+// adj_step_kernel: source_grad + adjoint velocity + residual injection + adjoint stress
+//   replaces source_grad / el_velocity_adj / res_injection / el_stress_adj
+//   (reference: libCUFD.cu:376,405-427, el_velocity_adj.cu:22-108, el_stress_adj.cu:22-104, utilities.cu:569-593)
+// Same skeleton: the producer lane streams the adjoint stress triple with halo 8 / 3 (72 x 34) and the adjoint
+// velocity pair (64 x 32) through the TMA ring.  Every thread updates the adjoint velocities of its quad (whole
+// 64 x 32 region), publishes them -- and, in tiles that touch the absorbing layers, the new phi memory variables of
+// its quad -- in shared memory; after the block barrier the owner threads update the adjoint stresses of the same
+// quad.  Residuals are injected through a small shared table (receivers add into it before the barrier, the owner
+// of the cell picks the sum up and clears it).
+// =================================================================================================
+constexpr int AS_BYTES = 3 * VCOLS * VPITCH * 4;                 // adjoint stresses, rows z0-8.., columns x0-3..
+constexpr int AS_PAD = (AS_BYTES + 127) / 128 * 128;
+constexpr int AV_BYTES = 2 * SCOLS * SPITCH * 4;                 // adjoint velocities, rows z0-4.., columns x0-2..
+constexpr int ASTAGE_BYTES = AS_PAD + AV_BYTES;
+constexpr int APHI_BYTES = 4 * SCOLS * SPITCH * 4;               // new phi of the region (tiles touching the CPML)
+constexpr int AINJ_BYTES = SCOLS * SPITCH * 4;                   // residual injection table
+constexpr size_t ADJ_SMEM =
+    (size_t)NS * ASTAGE_BYTES + 2 * AV_BYTES + APHI_BYTES + 2 * AINJ_BYTES + (NS + 1) * sizeof(TileDesc) + NS * 8 + 128;
+static_assert(AV_BYTES % 128 == 0, "TMA destination alignment");
+
+__global__ void __launch_bounds__(NCOMPUTE, 1) adj_step_kernel(const __grid_constant__ BwdArgs a) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char *base = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
+  float *s_v_base = reinterpret_cast<float *>(base + NS * ASTAGE_BYTES);                         // [2][2][SCOLS][SPITCH]
+  float *s_phi = reinterpret_cast<float *>(base + NS * ASTAGE_BYTES + 2 * AV_BYTES);             // [4][SCOLS][SPITCH]
+  float *s_inj_base = reinterpret_cast<float *>(base + NS * ASTAGE_BYTES + 2 * AV_BYTES + APHI_BYTES);   // [2][SCOLS][SPITCH]
+  unsigned char *tail = base + NS * ASTAGE_BYTES + 2 * AV_BYTES + APHI_BYTES + 2 * AINJ_BYTES;
+  TileDesc *sdesc = reinterpret_cast<TileDesc *>(tail);                                          // [NS + 1]
+  uint64_t *full = reinterpret_cast<uint64_t *>(tail + (NS + 1) * sizeof(TileDesc));
+
+  const Grid &g = a.g;
+  const int tid = threadIdx.x;
+  const int ntiles = g.tiles_z * g.tiles_x;
+  const int nitems = a.batch * ntiles;
+  const int stride = gridDim.x;
+  const int ain = a.cur_a ? S_AB : S_AA, aout = a.cur_a ? S_AA : S_AB;
+  const int psi_i = a.cur_a ? S_PSI_B : S_PSI_A, psi_o = a.cur_a ? S_PSI_A : S_PSI_B;
+  const int phi_i = a.cur_a ? S_PHI_B : S_PHI_A, phi_o = a.cur_a ? S_PHI_A : S_PHI_B;
+  const int P = g.P;
+  const long long pl = g.plane;
+  const int nxp = a.pr.nxp;
+  const int zp_hi = g.nz - g.nPml - g.nPad - 1;
+  // psi arrays only matter within 2 cells of the layers
+  const int zq_lo = g.nPml + 2, zq_hi = g.nz - g.nPad - g.nPml - 3;
+  const int xq_lo = g.nPml + 2, xq_hi = g.nx - g.nPml - 3;
+
+  if (tid == 0) {
+    for (int s = 0; s < NS; s++) mbar_init(&full[s], 1);
+    fence_barrier_init();
+  }
+  for (int i = tid; i < 2 * AINJ_BYTES / 16; i += NCOMPUTE) reinterpret_cast<float4 *>(s_inj_base)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncthreads();
+
+  auto produce = [&](int item, int stage, int ds) {
+    const int shot = item / ntiles, tile = item - shot * ntiles;
+    const int z0 = (tile % g.tiles_z) * TILE_Z, x0 = (tile / g.tiles_z) * TILE_X;
+    const int sz = a.st.src_z[shot], sx = a.st.src_x[shot];
+    TileDesc d;
+    d.soff = (long long)shot * S_COUNT * pl + (long long)x0 * P + z0;
+    d.moff = x0 * P + z0;
+    d.z0 = z0; d.x0 = x0; d.shot = shot; d.tile = tile; d.sz = sz; d.sx = sx;
+    d.r0 = a.st.rec_ptr[shot * (ntiles + 1) + tile];
+    d.r1 = a.st.rec_ptr[shot * (ntiles + 1) + tile + 1];
+    int fl = 0;
+    if ((z0 - 4 < zq_lo) || (z0 + TILE_Z + 3 > zq_hi) || (x0 - 2 < xq_lo) || (x0 + TILE_X + 1 > xq_hi)) fl |= TF_PML;
+    if (sz >= z0 && sz < z0 + TILE_Z && sx >= x0 && sx < x0 + TILE_X) fl |= TF_SRC;
+    d.flags = fl;
+    d.pad[0] = d.pad[1] = d.pad[2] = d.pad[3] = 0;
+    sdesc[ds] = d;
+    unsigned char *sb = base + stage * ASTAGE_BYTES;
+    const int p0 = shot * S_COUNT + ain;
+    mbar_arrive_expect_tx(&full[stage], AS_BYTES + AV_BYTES);
+    tma_load_3d(sb, &a.tm.s3, z0 - 8, x0 - 3 + XM, p0 + F_SZZ, &full[stage]);
+    tma_load_3d(sb + AS_PAD, &a.tm.vn, z0 - 4, x0 - 2 + XM, p0 + F_VZ, &full[stage]);
+  };
+  if (tid == PRODUCER_TID)
+    for (int s = 0; s < NS; s++)
+      if (blockIdx.x + s * stride < nitems) produce(blockIdx.x + s * stride, s, s);
+
+  const float dt = g.dt;
+  // adjoint-kernel spelling of the differences: (-c1 (..) + c2 (..)) / h  (el_stress_adj.cu:54-61)
+  const float kz1 = -C1 * g.rdz, kz2 = -C2 * g.rdz, kx1 = -C1 * g.rdx, kx2 = -C2 * g.rdx;
+  const int q = tid & 15, c = tid >> 4;
+  const bool inner = q >= 1 && q <= TILE_Z / 4 && c >= 2 && c < TILE_X + 2;
+  const int sj = c * SPITCH + 4 * q;
+  const int gx_max = g.nx + XM - 1;
+  const int cm2 = (c > 0 ? 2 : 1) * VPITCH, cp2 = (c < SCOLS - 1 ? 2 : 1) * VPITCH;   // keep halo-column reads in the tile
+  const float *zprof = a.pr.z;
+
+  int stage = 0, phase = 0, nb = 0, ds = 0;
+  for (int item = blockIdx.x; item < nitems; item += stride) {
+    mbar_wait(&full[stage], phase);
+    const TileDesc d = sdesc[ds];
+    const int gz = d.z0 - 4 + 4 * q, gx = d.x0 - 2 + c;
+    const bool inb = (unsigned)gx < (unsigned)g.nx && (unsigned)gz < (unsigned)g.nz;
+    const bool owner = inner && inb;
+    float *sq = a.state + g.origin + d.soff + ((long long)(c - 2) * P + 4 * q - 4);   // + slot * pl
+    const float *mq = a.m.ldt + ((long long)min(gx, gx_max) * P + gz);
+    const bool pml_tile = d.flags & TF_PML;
+    // quad with at least one active cell (2 <= z <= nz-nPad-3, 2 <= x <= nx-3): the only ones that touch CPML memory
+    const bool actq = gx >= 2 && gx <= g.ax_hi && gz + 3 >= 2 && gz <= g.az_hi;
+    const F4 ldt = ld4(mq), l2mdt = ld4(mq + pl), amudt = ld4(mq + 2 * pl);
+    const F4 byadt = ld4(mq + 3 * pl), bybdt = ld4(mq + 4 * pl);
+
+    const unsigned char *sb = base + stage * ASTAGE_BYTES;
+    const float *sa = reinterpret_cast<const float *>(sb);              // [3][VCOLS][VPITCH]: adjoint szz sxx sxz
+    const float *sva = reinterpret_cast<const float *>(sb + AS_PAD);    // [2][SCOLS][SPITCH]: adjoint vz vx
+    float *s_v = s_v_base + nb * (AV_BYTES / 4);
+    float *s_inj = s_inj_base + nb * (AINJ_BYTES / 4);
+
+    // ---- adjoint velocity on 16 quads x 32 columns (el_velocity_adj.cu:56-100) ----
+    const float *zz = sa + (c + 1) * VPITCH + 4 * (q + 1);
+    const float *xx = zz + VCOLS * VPITCH;
+    const float *xz = xx + VCOLS * VPITCH;
+    const F4 zzB = ld4(zz), xxB = ld4(xx), xzB = ld4(xz);
+    float dszz_dx[4], dsxx_dx[4], dsxz_dz[4], dszz_dz[4], dsxx_dz[4], dsxz_dx[4];
+    dx4(ld4(zz - VPITCH), zzB, ld4(zz + VPITCH), ld4(zz + cp2), kx1, kx2, dszz_dx);   // ad_plus_x
+    dx4(ld4(xx - VPITCH), xxB, ld4(xx + VPITCH), ld4(xx + cp2), kx1, kx2, dsxx_dx);
+    dx4(ld4(xz - cm2), ld4(xz - VPITCH), xzB, ld4(xz + VPITCH), kx1, kx2, dsxz_dx);   // ad_minus_x
+    dz_plus4(ld4(zz - 4), zzB, ld4(zz + 4), kz1, kz2, dszz_dz);
+    dz_plus4(ld4(xx - 4), xxB, ld4(xx + 4), kz1, kz2, dsxx_dz);
+    dz_minus4(ld4(xz - 4), xzB, ld4(xz + 4), kz1, kz2, dsxz_dz);
+    F4 vz = ld4(sva + sj), vx = ld4(sva + SCOLS * SPITCH + sj);
+
+    // source_grad (utilities.cu:582-593): adjoint stress at the source BEFORE this step's injection and update
+    if ((d.flags & TF_SRC) && owner && gx == d.sx && (unsigned)(d.sz - gz) < 4u) {
+      const int ks = d.sz - gz;
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < 4; kk++)
+        if (kk == ks) { s1 = zzB.v[kk]; s2 = xxB.v[kk]; }
+      a.stf_grad[d.shot * g.nSteps + a.it] = (float)(-((double)s1 + 3.0 * (double)s2) * (double)dt);
+    }
+    // residual injection at time index `it` (utilities.cu:569-580): receivers of this tile add into the table
+    for (int r = d.r0 + tid; r < d.r1; r += NCOMPUTE) {
+      const int loc = a.st.rec_loc[d.shot * a.st.nrp + r];
+      const int lz = loc & 0xffff, lx = loc >> 16;
+      atomicAdd(&s_inj[(lx + 2) * SPITCH + lz + 4],
+                a.res[((long long)d.shot * g.nSteps + a.it) * a.st.nrp + a.st.rec_id[d.shot * a.st.nrp + r]]);
+    }
+
+    float rKx = 1.0f, rKxh = 1.0f, ax = 0.0f, axh = 0.0f;
+    F4 rKz{{1.f, 1.f, 1.f, 1.f}}, rKzh{{1.f, 1.f, 1.f, 1.f}}, az = zero4(), azh = zero4();
+    bool zq_pml = false, xp = false;
+    if (!pml_tile) {
+#pragma unroll
+      for (int kk = 0; kk < 4; kk++) {  // coefficients carry dt and are 0 on inactive cells
+        vx.v[kk] += fmaf(ldt.v[kk], dszz_dx[kk], fmaf(l2mdt.v[kk], dsxx_dx[kk], amudt.v[kk] * dsxz_dz[kk]));
+        vz.v[kk] += fmaf(l2mdt.v[kk], dszz_dz[kk], fmaf(ldt.v[kk], dsxx_dz[kk], amudt.v[kk] * dsxz_dx[kk]));
+      }
+    } else {
+      F4 f_szz_z = zero4(), f_sxz_x = zero4(), f_sxz_z = zero4(), f_sxx_x = zero4();   // new phi of the quad
+      if (actq) {
+        float tpx1[4] = {0, 0, 0, 0}, tpx2[4] = {0, 0, 0, 0}, tpz1[4] = {0, 0, 0, 0}, tpz2[4] = {0, 0, 0, 0};
+        const float *xpf = a.pr.x + gx + XM;
+        rKx = xpf[PR_RK * nxp];
+        rKxh = xpf[PR_RKH * nxp];
+        ax = xpf[PR_A * nxp];
+        axh = xpf[PR_AH * nxp];
+        xp = gx < g.nPml || gx > g.nx - g.nPml - 1;
+        zq_pml = gz < g.nPml || gz + 3 > zp_hi;
+        if (ax != 0.0f) {  // a_x * D+x(psi_xx)
+          const float *p = sq + (psi_i + PSI_VX_X) * pl;
+          float dd[4];
+          dx4(ld4(p - P), ld4(p), ld4(p + P), ld4(p + 2 * P), kx1, kx2, dd);
+#pragma unroll
+          for (int kk = 0; kk < 4; kk++) tpx1[kk] = ax * dd[kk];
+        }
+        if (axh != 0.0f) {  // a_x_half * D-x(psi_zx)
+          const float *p = sq + (psi_i + PSI_VZ_X) * pl;
+          float dd[4];
+          dx4(ld4(p - 2 * P), ld4(p - P), ld4(p), ld4(p + P), kx1, kx2, dd);
+#pragma unroll
+          for (int kk = 0; kk < 4; kk++) tpz2[kk] = axh * dd[kk];
+        }
+        if (zq_pml) {
+          rKz = ld4(zprof + PR_RK * P + gz);
+          rKzh = ld4(zprof + PR_RKH * P + gz);
+          az = ld4(zprof + PR_A * P + gz);
+          azh = ld4(zprof + PR_AH * P + gz);
+          const float *p1 = sq + (psi_i + PSI_VX_Z) * pl;  // a_z_half * D-z(psi_xz)
+          const float *p2 = sq + (psi_i + PSI_VZ_Z) * pl;  // a_z * D+z(psi_zz)
+          float dd[4];
+          dz_minus4(ld4(p1 - 4), ld4(p1), ld4(p1 + 4), kz1, kz2, dd);
+#pragma unroll
+          for (int kk = 0; kk < 4; kk++) tpx2[kk] = azh.v[kk] * dd[kk];
+          dz_plus4(ld4(p2 - 4), ld4(p2), ld4(p2 + 4), kz1, kz2, dd);
+#pragma unroll
+          for (int kk = 0; kk < 4; kk++) tpz1[kk] = az.v[kk] * dd[kk];
+        }
+#pragma unroll
+        for (int kk = 0; kk < 4; kk++) {
+          const int z = gz + kk;
+          if (z >= 2 && z <= g.az_hi) {
+            vx.v[kk] += tpx1[kk] + ldt.v[kk] * dszz_dx[kk] * rKx + l2mdt.v[kk] * dsxx_dx[kk] * rKx + tpx2[kk] +
+                        amudt.v[kk] * rKzh.v[kk] * dsxz_dz[kk];
+            vz.v[kk] += tpz1[kk] + l2mdt.v[kk] * dszz_dz[kk] * rKz.v[kk] + ldt.v[kk] * dsxx_dz[kk] * rKz.v[kk] + tpz2[kk] +
+                        amudt.v[kk] * rKxh * dsxz_dx[kk];
+          }
+        }
+        // phi memory of the quad, CPML cells only (el_velocity_adj.cu:74-79,95-100); buoyancies are 0 on inactive cells
+        if (xp) {
+          const float bx = xpf[PR_B * nxp], bxh = xpf[PR_BH * nxp];
+          f_sxx_x = ld4(sq + (phi_i + PHI_SXX_X) * pl);
+          f_sxz_x = ld4(sq + (phi_i + PHI_SXZ_X) * pl);
+#pragma unroll
+          for (int kk = 0; kk < 4; kk++) {
+            f_sxx_x.v[kk] = fmaf(bxh, f_sxx_x.v[kk], bybdt.v[kk] * vx.v[kk]);
+            f_sxz_x.v[kk] = fmaf(bx, f_sxz_x.v[kk], byadt.v[kk] * vz.v[kk]);
+          }
+          if (owner) {
+            st4(sq + (phi_o + PHI_SXX_X) * pl, f_sxx_x);
+            st4(sq + (phi_o + PHI_SXZ_X) * pl, f_sxz_x);
+          }
+        }
+        if (zq_pml) {
+          const F4 bz = ld4(zprof + PR_B * P + gz), bzh = ld4(zprof + PR_BH * P + gz);
+          f_sxz_z = ld4(sq + (phi_i + PHI_SXZ_Z) * pl);
+          f_szz_z = ld4(sq + (phi_i + PHI_SZZ_Z) * pl);
+#pragma unroll
+          for (int kk = 0; kk < 4; kk++) {
+            const int z = gz + kk;
+            if (z < g.nPml || z > zp_hi) {
+              f_sxz_z.v[kk] = fmaf(bz.v[kk], f_sxz_z.v[kk], bybdt.v[kk] * vx.v[kk]);
+              f_szz_z.v[kk] = fmaf(bzh.v[kk], f_szz_z.v[kk], byadt.v[kk] * vz.v[kk]);
+            }
+          }
+          if (owner) {
+            st4(sq + (phi_o + PHI_SXZ_Z) * pl, f_sxz_z);
+            st4(sq + (phi_o + PHI_SZZ_Z) * pl, f_szz_z);
+          }
+        }
+      }
+      st4(s_phi + PHI_SZZ_Z * SCOLS * SPITCH + sj, f_szz_z);
+      st4(s_phi + PHI_SXZ_X * SCOLS * SPITCH + sj, f_sxz_x);
+      st4(s_phi + PHI_SXZ_Z * SCOLS * SPITCH + sj, f_sxz_z);
+      st4(s_phi + PHI_SXX_X * SCOLS * SPITCH + sj, f_sxx_x);
+    }
+    st4(s_v + sj, vz);
+    st4(s_v + SCOLS * SPITCH + sj, vx);
+    float *ao = sq + aout * pl;
+    if (owner) {
+      st4(ao + F_VZ * pl, vz);
+      st4(ao + F_VX * pl, vx);
+    }
+    __syncthreads();  // s_v / s_phi / s_inj are complete; nobody reads ring slot `stage` any more
+    if (tid == PRODUCER_TID && item + NS * stride < nitems) produce(item + NS * stride, stage, ds == 0 ? NS : ds - 1);
+
+    // ---- adjoint stress of the same quad, owner threads (el_stress_adj.cu:52-95) ----
+    if (owner) {
+      F4 szz = zzB, sxx = xxB, sxz = xzB;
+      if (d.r1 > d.r0) {  // res_injection: szz += res, sxx += 3 res
+        const F4 r = ld4(s_inj + sj);
+        st4(s_inj + sj, zero4());
+#pragma unroll
+        for (int kk = 0; kk < 4; kk++) {
+          szz.v[kk] += r.v[kk];
+          sxx.v[kk] += 3.0f * r.v[kk];
+        }
+      }
+      const float *pz = s_v + sj;
+      const float *px = pz + SCOLS * SPITCH;
+      float dvz_dx[4], dvx_dz[4], dvx_dx[4], dvz_dz[4];
+      dx4(ld4(pz - SPITCH), vz, ld4(pz + SPITCH), ld4(pz + 2 * SPITCH), kx1, kx2, dvz_dx);   // ad_plus_x(vz)
+      dz_plus4(ld4(px - 4), vx, ld4(px + 4), kz1, kz2, dvx_dz);                              // ad_plus_z(vx)
+      dx4(ld4(px - 2 * SPITCH), ld4(px - SPITCH), vx, ld4(px + SPITCH), kx1, kx2, dvx_dx);   // ad_minus_x(vx)
+      dz_minus4(ld4(pz - 4), vz, ld4(pz + 4), kz1, kz2, dvz_dz);                             // ad_minus_z(vz)
+      if (!pml_tile) {
+#pragma unroll
+        for (int kk = 0; kk < 4; kk++) {
+          sxz.v[kk] += fmaf(dvz_dx[kk], byadt.v[kk], dvx_dz[kk] * bybdt.v[kk]);
+          sxx.v[kk] = fmaf(bybdt.v[kk], dvx_dx[kk], sxx.v[kk]);
+          szz.v[kk] = fmaf(byadt.v[kk], dvz_dz[kk], szz.v[kk]);
+        }
+      } else {
+        float t_xz_x[4] = {0, 0, 0, 0}, t_xz_z[4] = {0, 0, 0, 0}, t_xx[4] = {0, 0, 0, 0}, t_zz[4] = {0, 0, 0, 0};
+        if (actq) {
+          float dd[4];
+          if (ax != 0.0f) {  // a_x * D+x(phi_xz_x)
+            const float *p = s_phi + PHI_SXZ_X * SCOLS * SPITCH + sj;
+            dx4(ld4(p - SPITCH), ld4(p), ld4(p + SPITCH), ld4(p + 2 * SPITCH), kx1, kx2, dd);
+#pragma unroll
+            for (int kk = 0; kk < 4; kk++) t_xz_x[kk] = ax * dd[kk];
+          }
+          if (axh != 0.0f) {  // a_x_half * D-x(phi_xx_x)
+            const float *p = s_phi + PHI_SXX_X * SCOLS * SPITCH + sj;
+            dx4(ld4(p - 2 * SPITCH), ld4(p - SPITCH), ld4(p), ld4(p + SPITCH), kx1, kx2, dd);
+#pragma unroll
+            for (int kk = 0; kk < 4; kk++) t_xx[kk] = axh * dd[kk];
+          }
+          if (zq_pml) {
+            const float *p1 = s_phi + PHI_SXZ_Z * SCOLS * SPITCH + sj;   // a_z * D+z(phi_xz_z)
+            dz_plus4(ld4(p1 - 4), ld4(p1), ld4(p1 + 4), kz1, kz2, dd);
+#pragma unroll
+            for (int kk = 0; kk < 4; kk++) t_xz_z[kk] = az.v[kk] * dd[kk];
+            const float *p2 = s_phi + PHI_SZZ_Z * SCOLS * SPITCH + sj;   // a_z_half * D-z(phi_zz_z)
+            dz_minus4(ld4(p2 - 4), ld4(p2), ld4(p2 + 4), kz1, kz2, dd);
+#pragma unroll
+            for (int kk = 0; kk < 4; kk++) t_zz[kk] = azh.v[kk] * dd[kk];
+          }
+        }
+#pragma unroll
+        for (int kk = 0; kk < 4; kk++) {
+          const int z = gz + kk;
+          if (actq && z >= 2 && z <= g.az_hi) {
+            sxz.v[kk] += t_xz_x[kk] + dvz_dx[kk] * rKx * byadt.v[kk] + t_xz_z[kk] + dvx_dz[kk] * rKz.v[kk] * bybdt.v[kk];
+            sxx.v[kk] += t_xx[kk] + bybdt.v[kk] * dvx_dx[kk] * rKxh;
+            szz.v[kk] += t_zz[kk] + byadt.v[kk] * dvz_dz[kk] * rKzh.v[kk];
+          }
+        }
+        // psi memory within 2 cells of the layers (el_stress_adj.cu:68,71,89-94)
+        if (actq && (gx < xq_lo || gx > xq_hi)) {
+          const float *xpf = a.pr.x + gx + XM;
+          const float bx = xpf[PR_B * nxp], bxh = xpf[PR_BH * nxp];
+          F4 p1 = ld4(sq + (psi_i + PSI_VZ_X) * pl), p2 = ld4(sq + (psi_i + PSI_VX_X) * pl);
+#pragma unroll
+          for (int kk = 0; kk < 4; kk++) {
+            p1.v[kk] = fmaf(bxh, p1.v[kk], sxz.v[kk] * amudt.v[kk]);
+            p2.v[kk] = fmaf(bx, p2.v[kk], fmaf(ldt.v[kk], szz.v[kk], l2mdt.v[kk] * sxx.v[kk]));
+          }
+          st4(sq + (psi_o + PSI_VZ_X) * pl, p1);
+          st4(sq + (psi_o + PSI_VX_X) * pl, p2);
+        }
+        if (actq && (gz < zq_lo || gz + 3 > zq_hi)) {
+          const F4 bz = ld4(zprof + PR_B * P + gz), bzh = ld4(zprof + PR_BH * P + gz);
+          F4 p1 = ld4(sq + (psi_i + PSI_VX_Z) * pl), p2 = ld4(sq + (psi_i + PSI_VZ_Z) * pl);
+#pragma unroll
+          for (int kk = 0; kk < 4; kk++) {
+            const int z = gz + kk;
+            if (z < zq_lo || z > zq_hi) {
+              p1.v[kk] = fmaf(bzh.v[kk], p1.v[kk], sxz.v[kk] * amudt.v[kk]);
+              p2.v[kk] = fmaf(bz.v[kk], p2.v[kk], fmaf(l2mdt.v[kk], szz.v[kk], ldt.v[kk] * sxx.v[kk]));
+            }
+          }
+          st4(sq + (psi_o + PSI_VX_Z) * pl, p1);
+          st4(sq + (psi_o + PSI_VZ_Z) * pl, p2);
+        }
+      }
+      st4(ao + F_SZZ * pl, szz);
+      st4(ao + F_SXX * pl, sxx);
+      st4(ao + F_SXZ * pl, sxz);
+    }
+    if (pml_tile) __syncthreads();  // s_phi is single-buffered: everyone is done reading it before the next item writes
+    nb ^= 1;
+    if (++ds == NS + 1) ds = 0;
+    if (++stage == NS) { stage = 0; phase ^= 1; }
+  }
+}
+
 }  // namespace
 
 size_t reverse_smem_bytes() { return REV_SMEM; }
 
+size_t adjoint_smem_bytes() { return ADJ_SMEM; }
+
 void configure_backward_kernels() {
   cudaFuncSetAttribute(rev_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)REV_SMEM);
+  cudaFuncSetAttribute(adj_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ADJ_SMEM);
+}
+
+void launch_adjoint_step(const BwdArgs &a, cudaStream_t s) {
+  const int nitems = a.batch * a.g.tiles_z * a.g.tiles_x;
+  const int blocks = nitems < sm_count() ? nitems : sm_count();
+  adj_step_kernel<<<blocks, NCOMPUTE, ADJ_SMEM, s>>>(a);
 }
 
 void launch_reverse_imaging(const BwdArgs &a, cudaStream_t s) {

@@ -134,386 +134,6 @@ constexpr int VC = TILE_X + 6, SC = TILE_X + 4;
 static_assert(TILE_Z % 4 == 0 && QS == 16, "half-warp per sigma column");
 
 // =================================================================================================
-// adjoint step
-// =================================================================================================
-// adjoint-kernel spelling of the differences (el_stress_adj.cu:54-61): (-c1*(..) + c2*(..)) / h
-__device__ __forceinline__ void adz_minus4(const F4 &A, const F4 &B, const F4 &C, float rh, float *out) {
-  const float w[7] = {A.v[2], A.v[3], B.v[0], B.v[1], B.v[2], B.v[3], C.v[0]};
-#pragma unroll
-  for (int k = 0; k < 4; k++) out[k] = (-C1 * (w[k + 2] - w[k + 1]) + C2 * (w[k + 3] - w[k])) * rh;
-}
-__device__ __forceinline__ void adz_plus4(const F4 &A, const F4 &B, const F4 &C, float rh, float *out) {
-  const float u[7] = {A.v[3], B.v[0], B.v[1], B.v[2], B.v[3], C.v[0], C.v[1]};
-#pragma unroll
-  for (int k = 0; k < 4; k++) out[k] = (-C1 * (u[k + 2] - u[k + 1]) + C2 * (u[k + 3] - u[k])) * rh;
-}
-__device__ __forceinline__ void adx4(const F4 &m2, const F4 &m1, const F4 &c0, const F4 &p1, float rh, float *out) {
-#pragma unroll
-  for (int k = 0; k < 4; k++) out[k] = (-C1 * (c0.v[k] - m1.v[k]) + C2 * (p1.v[k] - m2.v[k])) * rh;
-}
-
-constexpr size_t ADJ_SMEM = (size_t)(3 * VC * VP + 2 * SC * SP) * sizeof(float);
-
-__global__ void __launch_bounds__(NTHREADS, 2) adj_step_kernel(const __grid_constant__ BwdArgs a) {
-  extern __shared__ __align__(16) float smem[];
-  float *s_zz = smem;
-  float *s_xx = s_zz + VC * VP;
-  float *s_xz = s_xx + VC * VP;
-  float *s_vz = s_xz + VC * VP;
-  float *s_vx = s_vz + SC * SP;
-  const Grid &g = a.g;
-  const int tid = threadIdx.x;
-  const int shot = blockIdx.x % a.batch;
-  const int tile = blockIdx.x / a.batch;
-  const int tz = tile % g.tiles_z, tx = tile / g.tiles_z;
-  const int z0 = tz * TILE_Z, x0 = tx * TILE_X;
-  const int ntiles = g.tiles_z * g.tiles_x;
-  const int r0 = a.st.rec_ptr[shot * (ntiles + 1) + tile];
-  const int r1 = a.st.rec_ptr[shot * (ntiles + 1) + tile + 1];
-  const int sz = a.st.src_z[shot], sx = a.st.src_x[shot];
-  const bool src_owner = sz >= z0 && sz < z0 + TILE_Z && sx >= x0 && sx < x0 + TILE_X;
-  if (z0 - 4 > g.az_hi && r1 == r0 && !src_owner) return;
-
-  const int P = g.P;
-  const int xmax = g.nx + XM - 1;
-  const float dt = g.dt, rdz = g.rdz, rdx = g.rdx;
-  const long long pl = g.plane;
-  float *sbase = a.state + (long long)shot * S_COUNT * pl + g.origin;
-  const float *ai = sbase + (a.cur_a ? S_AB : S_AA) * pl;
-  float *ao = sbase + (a.cur_a ? S_AA : S_AB) * pl;
-  const float *psi_i = sbase + (a.cur_a ? S_PSI_B : S_PSI_A) * pl;
-  float *psi_o = sbase + (a.cur_a ? S_PSI_A : S_PSI_B) * pl;
-  const float *phi_i = sbase + (a.cur_a ? S_PHI_B : S_PHI_A) * pl;
-  float *phi_o = sbase + (a.cur_a ? S_PHI_A : S_PHI_B) * pl;
-  const int nxp = a.pr.nxp;
-  const int zp_hi = g.nz - g.nPml - g.nPad - 1;
-
-  // source_grad (utilities.cu:582-593): adjoint stress at the source BEFORE this step's update
-  if (src_owner && tid == 0) {
-    const int off = sx * P + sz;
-    a.stf_grad[shot * g.nSteps + a.it] =
-        (float)(-((double)ai[F_SZZ * pl + off] + 3.0 * (double)ai[F_SXX * pl + off]) * (double)dt);
-  }
-
-  // ---- phase 1: adjoint stress tile, 18 quads x 38 columns ----
-  for (int i = tid; i < VC * QV; i += NTHREADS) {
-    const int col = i / QV, q = i - col * QV;
-    const int gx = min(x0 - 3 + col, xmax);
-    const int off = gx * P + (z0 - 8 + 4 * q);
-    cp_async16(s_zz + col * VP + 4 * q, ai + F_SZZ * pl + off);
-    cp_async16(s_xx + col * VP + 4 * q, ai + F_SXX * pl + off);
-    cp_async16(s_xz + col * VP + 4 * q, ai + F_SXZ * pl + off);
-  }
-  cp_async_wait_all();
-  __syncthreads();
-
-  // psi arrays only matter within 2 cells of the PML
-  const int zq_lo = g.nPml + 2, zq_hi = g.nz - g.nPad - g.nPml - 3;  // z-type psi zone: z < zq_lo || z > zq_hi
-  const int xq_lo = g.nPml + 2, xq_hi = g.nx - g.nPml - 3;
-  const bool pml_tile = (z0 - 4 < zq_lo) || (z0 + TILE_Z + 3 > zq_hi) || (x0 - 2 < xq_lo) || (x0 + TILE_X + 1 > xq_hi);
-  const int h = tid >> 4, q = tid & 15;
-
-  // ---- phase 2: adjoint velocity on 16 quads x 36 columns (el_velocity_adj.cu:56-100) ----
-  {
-    const int gz = z0 - 4 + 4 * q;
-    for (int c = h; c < SC; c += NTHREADS / 16) {
-      const int gx = x0 - 2 + c;
-      const int off = min(gx, xmax) * P + gz;
-      F4 vz = ld4(ai + F_VZ * pl + off), vx = ld4(ai + F_VX * pl + off);
-      const bool owner = q >= 1 && q <= TILE_Z / 4 && c >= 2 && c < TILE_X + 2 && gx < g.nx && gz < g.nz;
-      if (gx >= 2 && gx <= g.ax_hi && gz + 3 >= 2 && gz <= g.az_hi) {
-        const float *zz = s_zz + (c + 1) * VP + 4 * (q + 1);
-        const float *xx = s_xx + (c + 1) * VP + 4 * (q + 1);
-        const float *xz = s_xz + (c + 1) * VP + 4 * (q + 1);
-        const int cm2 = (c > 0 ? 2 : 1) * VP, cp2 = (c < SC - 1 ? 2 : 1) * VP;  // keep halo-column reads in the tile
-        float dszz_dx[4], dsxx_dx[4], dsxz_dz[4], dszz_dz[4], dsxx_dz[4], dsxz_dx[4];
-        const F4 zzB = ld4(zz), xxB = ld4(xx), xzB = ld4(xz);
-        adx4(ld4(zz - VP), zzB, ld4(zz + VP), ld4(zz + cp2), rdx, dszz_dx);   // ad_plus_x
-        adx4(ld4(xx - VP), xxB, ld4(xx + VP), ld4(xx + cp2), rdx, dsxx_dx);
-        adx4(ld4(xz - cm2), ld4(xz - VP), xzB, ld4(xz + VP), rdx, dsxz_dx);   // ad_minus_x
-        adz_plus4(ld4(zz - 4), zzB, ld4(zz + 4), rdz, dszz_dz);
-        adz_plus4(ld4(xx - 4), xxB, ld4(xx + 4), rdz, dsxx_dz);
-        adz_minus4(ld4(xz - 4), xzB, ld4(xz + 4), rdz, dsxz_dz);
-        const F4 lam = ld4(a.m.lam + off), mu = ld4(a.m.mu + off), amu = ld4(a.m.amu + off);
-        float tpx1[4] = {0, 0, 0, 0}, tpx2[4] = {0, 0, 0, 0}, tpz1[4] = {0, 0, 0, 0}, tpz2[4] = {0, 0, 0, 0};
-        float rKx = 1.0f, rKxh = 1.0f;
-        F4 rKz{{1, 1, 1, 1}}, rKzh{{1, 1, 1, 1}};
-        bool xp = false, zq_pml = false;
-        if (pml_tile) {
-          const float *xpf = a.pr.x + gx + XM;
-          rKx = xpf[PR_RK * nxp];
-          rKxh = xpf[PR_RKH * nxp];
-          const float ax = xpf[PR_A * nxp], axh = xpf[PR_AH * nxp];
-          xp = x_in_pml_s(g, gx);
-          zq_pml = gz < g.nPml || gz + 3 > zp_hi;
-          if (ax != 0.0f) {  // a_x * D+x(psi_xx)
-            const float *p = psi_i + PSI_VX_X * pl + off;
-            float d[4];
-            adx4(ld4(p - P), ld4(p), ld4(p + P), ld4(p + 2 * P), rdx, d);
-#pragma unroll
-            for (int k = 0; k < 4; k++) tpx1[k] = ax * d[k];
-          }
-          if (axh != 0.0f) {  // a_x_half * D-x(psi_zx)
-            const float *p = psi_i + PSI_VZ_X * pl + off;
-            float d[4];
-            adx4(ld4(p - 2 * P), ld4(p - P), ld4(p), ld4(p + P), rdx, d);
-#pragma unroll
-            for (int k = 0; k < 4; k++) tpz2[k] = axh * d[k];
-          }
-          if (zq_pml) {
-            rKz = ld4(a.pr.z + PR_RK * P + gz);
-            rKzh = ld4(a.pr.z + PR_RKH * P + gz);
-            const F4 az = ld4(a.pr.z + PR_A * P + gz), azh = ld4(a.pr.z + PR_AH * P + gz);
-            const float *p1 = psi_i + PSI_VX_Z * pl + off;  // a_z_half * D-z(psi_xz)
-            const float *p2 = psi_i + PSI_VZ_Z * pl + off;  // a_z * D+z(psi_zz)
-            float d[4];
-            adz_minus4(ld4(p1 - 4), ld4(p1), ld4(p1 + 4), rdz, d);
-#pragma unroll
-            for (int k = 0; k < 4; k++) tpx2[k] = azh.v[k] * d[k];
-            adz_plus4(ld4(p2 - 4), ld4(p2), ld4(p2 + 4), rdz, d);
-#pragma unroll
-            for (int k = 0; k < 4; k++) tpz1[k] = az.v[k] * d[k];
-          }
-        }
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-          const int z = gz + k;
-          if (z >= 2 && z <= g.az_hi) {
-#if FWI_FP64_PROMOTE
-            const double l2m = (double)lam.v[k] + 2.0 * (double)mu.v[k];
-            {
-              const float t12 = tpx1[k] + lam.v[k] * dszz_dx[k] * rKx * dt;
-              const double t3 = l2m * (double)dsxx_dx[k] * (double)rKx * (double)dt;
-              vx.v[k] = (float)((double)vx.v[k] + ((double)t12 + t3 + (double)tpx2[k] +
-                                                   (double)(amu.v[k] * rKzh.v[k] * dsxz_dz[k] * dt)));
-            }
-            {
-              const double t2 = l2m * (double)dszz_dz[k] * (double)rKz.v[k] * (double)dt;
-              vz.v[k] = (float)((double)vz.v[k] + ((double)tpz1[k] + t2 + (double)(lam.v[k] * dsxx_dz[k] * rKz.v[k] * dt) +
-                                                   (double)tpz2[k] + (double)(amu.v[k] * rKxh * dsxz_dx[k] * dt)));
-            }
-#else
-            const float l2m = lam.v[k] + 2.0f * mu.v[k];
-            vx.v[k] += tpx1[k] + lam.v[k] * dszz_dx[k] * rKx * dt + l2m * dsxx_dx[k] * rKx * dt + tpx2[k] +
-                       amu.v[k] * rKzh.v[k] * dsxz_dz[k] * dt;
-            vz.v[k] += tpz1[k] + l2m * dszz_dz[k] * rKz.v[k] * dt + lam.v[k] * dsxx_dz[k] * rKz.v[k] * dt + tpz2[k] +
-                       amu.v[k] * rKxh * dsxz_dx[k] * dt;
-#endif
-          }
-        }
-        if (owner && (xp || zq_pml)) {  // phi memory, PML cells only (el_velocity_adj.cu:74-79,95-100)
-          const F4 bya = ld4(a.m.bya + off), byb = ld4(a.m.byb + off);
-          if (xp) {
-            const float *xpf = a.pr.x + gx + XM;
-            const float bx = xpf[PR_B * nxp], bxh = xpf[PR_BH * nxp];
-            F4 f1 = ld4(phi_i + PHI_SXX_X * pl + off), f2 = ld4(phi_i + PHI_SXZ_X * pl + off);
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-              const int z = gz + k;
-              if (z >= 2 && z <= g.az_hi) {
-                f1.v[k] = bxh * f1.v[k] + byb.v[k] * vx.v[k] * dt;
-                f2.v[k] = bx * f2.v[k] + bya.v[k] * vz.v[k] * dt;
-              }
-            }
-            st4(phi_o + PHI_SXX_X * pl + off, f1);
-            st4(phi_o + PHI_SXZ_X * pl + off, f2);
-          }
-          if (zq_pml) {
-            const F4 bz = ld4(a.pr.z + PR_B * P + gz), bzh = ld4(a.pr.z + PR_BH * P + gz);
-            F4 f1 = ld4(phi_i + PHI_SXZ_Z * pl + off), f2 = ld4(phi_i + PHI_SZZ_Z * pl + off);
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-              const int z = gz + k;
-              if ((z < g.nPml || z > zp_hi) && z >= 2 && z <= g.az_hi) {
-                f1.v[k] = bz.v[k] * f1.v[k] + byb.v[k] * vx.v[k] * dt;
-                f2.v[k] = bzh.v[k] * f2.v[k] + bya.v[k] * vz.v[k] * dt;
-              }
-            }
-            st4(phi_o + PHI_SXZ_Z * pl + off, f1);
-            st4(phi_o + PHI_SZZ_Z * pl + off, f2);
-          }
-        }
-      }
-      st4(s_vz + c * SP + 4 * q, vz);
-      st4(s_vx + c * SP + 4 * q, vx);
-      if (owner) {
-        st4(ao + F_VZ * pl + off, vz);
-        st4(ao + F_VX * pl + off, vx);
-      }
-    }
-  }
-  __syncthreads();
-
-  // ---- residual injection at time index `it` (utilities.cu:569-580), owner cells only ----
-  for (int k = r0 + tid; k < r1; k += NTHREADS) {
-    const int loc = a.st.rec_loc[shot * a.st.nrp + k];
-    const int lz = loc & 0xffff, lx = loc >> 16;
-    const float r = a.res[((long long)shot * g.nSteps + a.it) * a.st.nrp + a.st.rec_id[shot * a.st.nrp + k]];
-    const int j = (lx + 3) * VP + lz + 8;
-    atomicAdd(&s_zz[j], r);
-    atomicAdd(&s_xx[j], 3.0f * r);
-  }
-  __syncthreads();
-
-  // ---- phase 3: adjoint stress on 14 quads x 32 columns (el_stress_adj.cu:52-95) ----
-  if (q < TILE_Z / 4) {
-    const int gz = z0 + 4 * q;
-    for (int c = h; c < TILE_X; c += NTHREADS / 16) {
-      const int gx = x0 + c;
-      if (gx >= g.nx || gz >= g.nz) continue;
-      const int off = gx * P + gz;
-      const int j = (c + 3) * VP + 4 * (q + 2);
-      F4 szz = ld4(s_zz + j), sxx = ld4(s_xx + j), sxz = ld4(s_xz + j);
-      if (gx >= 2 && gx <= g.ax_hi && gz + 3 >= 2 && gz <= g.az_hi) {
-        const float *pz = s_vz + (c + 2) * SP + 4 * (q + 1);
-        const float *px = s_vx + (c + 2) * SP + 4 * (q + 1);
-        // velocity quads: z-neighbours (A,B,C) and the x-neighbour columns, kept for the phi recomputation
-        const F4 zA = ld4(pz - 4), zB = ld4(pz), zC = ld4(pz + 4), zXm = ld4(pz - SP), zXp = ld4(pz + SP), zXpp = ld4(pz + 2 * SP);
-        const F4 xA = ld4(px - 4), xB = ld4(px), xC = ld4(px + 4), xXmm = ld4(px - 2 * SP), xXm = ld4(px - SP), xXp = ld4(px + SP);
-        float dvz_dx[4], dvx_dz[4], dvx_dx[4], dvz_dz[4];
-        adx4(zXm, zB, zXp, zXpp, rdx, dvz_dx);    // ad_plus_x(vz)
-        adz_plus4(xA, xB, xC, rdz, dvx_dz);        // ad_plus_z(vx)
-        adx4(xXmm, xXm, xB, xXp, rdx, dvx_dx);    // ad_minus_x(vx)
-        adz_minus4(zA, zB, zC, rdz, dvz_dz);       // ad_minus_z(vz)
-        const F4 bya = ld4(a.m.bya + off), byb = ld4(a.m.byb + off);
-        float rKx = 1.0f, rKxh = 1.0f;
-        F4 rKz{{1, 1, 1, 1}}, rKzh{{1, 1, 1, 1}};
-        float t_xz_x[4] = {0, 0, 0, 0}, t_xz_z[4] = {0, 0, 0, 0}, t_xx[4] = {0, 0, 0, 0}, t_zz[4] = {0, 0, 0, 0};
-        const bool zq_pml = gz < g.nPml || gz + 3 > zp_hi;
-        if (pml_tile) {
-          const float *xpf = a.pr.x + gx + XM;
-          rKx = xpf[PR_RK * nxp];
-          rKxh = xpf[PR_RKH * nxp];
-          const float ax = xpf[PR_A * nxp], axh = xpf[PR_AH * nxp];
-          // phi_new at a stencil point is recomputed from the velocity tile instead of being staged:
-          //   phi_new = active & in-PML ? b * phi_old + byc * v_new * dt : phi_old
-          auto phi_col = [&](int which, int dxs, const float *bprof, const float *byc, const F4 &v) -> F4 {
-            const int x2 = gx + dxs;
-            const int o2 = off + dxs * P;
-            F4 ph = ld4(phi_i + which * pl + o2);
-            if (x2 >= 2 && x2 <= g.ax_hi && x_in_pml_s(g, x2)) {
-              const float b = bprof[x2 + XM];
-              const F4 by = ld4(byc + o2);
-#pragma unroll
-              for (int k = 0; k < 4; k++)
-                if (gz + k >= 2 && gz + k <= g.az_hi) ph.v[k] = b * ph.v[k] + by.v[k] * v.v[k] * dt;
-            }
-            return ph;
-          };
-          if (ax != 0.0f) {  // a_x * D+x(phi_xz_x): b_x, byc_a * vz at x-1 .. x+2
-            const float *bp = a.pr.x + PR_B * nxp;
-            float d[4];
-            adx4(phi_col(PHI_SXZ_X, -1, bp, a.m.bya, zXm), phi_col(PHI_SXZ_X, 0, bp, a.m.bya, zB),
-                 phi_col(PHI_SXZ_X, 1, bp, a.m.bya, zXp), phi_col(PHI_SXZ_X, 2, bp, a.m.bya, zXpp), rdx, d);
-#pragma unroll
-            for (int k = 0; k < 4; k++) t_xz_x[k] = ax * d[k];
-          }
-          if (axh != 0.0f) {  // a_x_half * D-x(phi_xx_x): b_x_half, byc_b * vx at x-2 .. x+1
-            const float *bp = a.pr.x + PR_BH * nxp;
-            float d[4];
-            adx4(phi_col(PHI_SXX_X, -2, bp, a.m.byb, xXmm), phi_col(PHI_SXX_X, -1, bp, a.m.byb, xXm),
-                 phi_col(PHI_SXX_X, 0, bp, a.m.byb, xB), phi_col(PHI_SXX_X, 1, bp, a.m.byb, xXp), rdx, d);
-#pragma unroll
-            for (int k = 0; k < 4; k++) t_xx[k] = axh * d[k];
-          }
-          if (zq_pml) {
-            rKz = ld4(a.pr.z + PR_RK * P + gz);
-            rKzh = ld4(a.pr.z + PR_RKH * P + gz);
-            const F4 az = ld4(a.pr.z + PR_A * P + gz), azh = ld4(a.pr.z + PR_AH * P + gz);
-            auto phi_quad = [&](int which, int dq, const float *bprof, const float *byc, const F4 &v) -> F4 {
-              const int zq = gz + 4 * dq;
-              const int o2 = off + 4 * dq;
-              F4 ph = ld4(phi_i + which * pl + o2);
-              const F4 b = ld4(bprof + zq), by = ld4(byc + o2);
-#pragma unroll
-              for (int k = 0; k < 4; k++) {
-                const int z = zq + k;
-                if ((z < g.nPml || z > zp_hi) && z >= 2 && z <= g.az_hi) ph.v[k] = b.v[k] * ph.v[k] + by.v[k] * v.v[k] * dt;
-              }
-              return ph;
-            };
-            float d[4];
-            {  // a_z * D+z(phi_xz_z): b_z, byc_b * vx
-              const float *bp = a.pr.z + PR_B * P;
-              adz_plus4(phi_quad(PHI_SXZ_Z, -1, bp, a.m.byb, xA), phi_quad(PHI_SXZ_Z, 0, bp, a.m.byb, xB),
-                        phi_quad(PHI_SXZ_Z, 1, bp, a.m.byb, xC), rdz, d);
-#pragma unroll
-              for (int k = 0; k < 4; k++) t_xz_z[k] = az.v[k] * d[k];
-            }
-            {  // a_z_half * D-z(phi_zz_z): b_z_half, byc_a * vz
-              const float *bp = a.pr.z + PR_BH * P;
-              adz_minus4(phi_quad(PHI_SZZ_Z, -1, bp, a.m.bya, zA), phi_quad(PHI_SZZ_Z, 0, bp, a.m.bya, zB),
-                         phi_quad(PHI_SZZ_Z, 1, bp, a.m.bya, zC), rdz, d);
-#pragma unroll
-              for (int k = 0; k < 4; k++) t_zz[k] = azh.v[k] * d[k];
-            }
-          }
-        }
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-          const int z = gz + k;
-          if (z >= 2 && z <= g.az_hi) {
-            sxz.v[k] += t_xz_x[k] + dvz_dx[k] * rKx * bya.v[k] * dt + t_xz_z[k] + dvx_dz[k] * rKz.v[k] * byb.v[k] * dt;
-            sxx.v[k] += t_xx[k] + byb.v[k] * dvx_dx[k] * rKxh * dt;
-            szz.v[k] += t_zz[k] + bya.v[k] * dvz_dz[k] * rKzh.v[k] * dt;
-          }
-        }
-        if (pml_tile) {
-          const bool xq = gx < xq_lo || gx > xq_hi;
-          const bool zq = gz < zq_lo || gz + 3 > zq_hi;
-          if (xq || zq) {
-            const F4 lam = ld4(a.m.lam + off), mu = ld4(a.m.mu + off), amu = ld4(a.m.amu + off);
-            if (xq) {
-              const float *xpf = a.pr.x + gx + XM;
-              const float bx = xpf[PR_B * nxp], bxh = xpf[PR_BH * nxp];
-              F4 p1 = ld4(psi_i + PSI_VZ_X * pl + off), p2 = ld4(psi_i + PSI_VX_X * pl + off);
-#pragma unroll
-              for (int k = 0; k < 4; k++) {
-                const int z = gz + k;
-                if (z >= 2 && z <= g.az_hi) {
-                  p1.v[k] = bxh * p1.v[k] + sxz.v[k] * amu.v[k] * dt;
-#if FWI_FP64_PROMOTE
-                  p2.v[k] = (float)((double)(bx * p2.v[k] + lam.v[k] * szz.v[k] * dt) +
-                                    ((double)lam.v[k] + 2.0 * (double)mu.v[k]) * (double)sxx.v[k] * (double)dt);
-#else
-                  p2.v[k] = bx * p2.v[k] + lam.v[k] * szz.v[k] * dt + (lam.v[k] + 2.0f * mu.v[k]) * sxx.v[k] * dt;
-#endif
-                }
-              }
-              st4(psi_o + PSI_VZ_X * pl + off, p1);
-              st4(psi_o + PSI_VX_X * pl + off, p2);
-            }
-            if (zq) {
-              const F4 bz = ld4(a.pr.z + PR_B * P + gz), bzh = ld4(a.pr.z + PR_BH * P + gz);
-              F4 p1 = ld4(psi_i + PSI_VX_Z * pl + off), p2 = ld4(psi_i + PSI_VZ_Z * pl + off);
-#pragma unroll
-              for (int k = 0; k < 4; k++) {
-                const int z = gz + k;
-                if ((z < zq_lo || z > zq_hi) && z >= 2 && z <= g.az_hi) {
-                  p1.v[k] = bzh.v[k] * p1.v[k] + sxz.v[k] * amu.v[k] * dt;
-#if FWI_FP64_PROMOTE
-                  p2.v[k] = (float)((double)(bz.v[k] * p2.v[k]) +
-                                    ((double)lam.v[k] + 2.0 * (double)mu.v[k]) * (double)szz.v[k] * (double)dt +
-                                    (double)(lam.v[k] * sxx.v[k] * dt));
-#else
-                  p2.v[k] = bz.v[k] * p2.v[k] + (lam.v[k] + 2.0f * mu.v[k]) * szz.v[k] * dt + lam.v[k] * sxx.v[k] * dt;
-#endif
-                }
-              }
-              st4(psi_o + PSI_VX_Z * pl + off, p1);
-              st4(psi_o + PSI_VZ_Z * pl + off, p2);
-            }
-          }
-        }
-      }
-      st4(ao + F_SZZ * pl + off, szz);
-      st4(ao + F_SXX * pl + off, sxx);
-      st4(ao + F_SXZ * pl + off, sxz);
-    }
-  }
-}
-
-// =================================================================================================
 // model preparation
 // =================================================================================================
 __global__ void model_transpose_kernel(Grid g, const double *__restrict__ lam_in, const double *__restrict__ mu_in,
@@ -713,7 +333,6 @@ __global__ void finalize_kernel(Grid g, const float *gacc, int nslots, const flo
 // =================================================================================================
 // launchers
 // =================================================================================================
-size_t adjoint_smem_bytes() { return ADJ_SMEM; }
 
 template <typename K>
 static void configure_one(K kernel, size_t smem, const char *env, int carveout) {
@@ -730,12 +349,6 @@ void configure_backward_kernels();  // fwi_backward.cu
 void configure_kernels() {
   configure_forward_kernels();
   configure_backward_kernels();
-  configure_one(adj_step_kernel, ADJ_SMEM, "FWI_B200_CARVEOUT_ADJ", -1);
-}
-
-void launch_adjoint_step(const BwdArgs &a, cudaStream_t s) {
-  const int blocks = a.batch * a.g.tiles_z * a.g.tiles_x;
-  adj_step_kernel<<<blocks, NTHREADS, ADJ_SMEM, s>>>(a);
 }
 
 void launch_model_prep(const Grid &g, const double *d_lam, const double *d_mu, const double *d_den, float *model,
