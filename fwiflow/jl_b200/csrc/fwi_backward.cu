@@ -9,8 +9,8 @@
 //   el_velocity.cu:101-110) is linear in those and is applied once, as a deterministic gather, by finalize_kernel.
 //
 // One CTA of 16 warps per SM loops over (shot, tile) items of the tile range that covers the inner box + frame ring.
-// The producer lane streams, three items ahead, the stress triple of time it+1 with halo 8 / 4 (72 x 36) and the
-// velocity pair with halo 4 / 2 (64 x 32) through a 3-stage TMA ring.  Every thread owns one float4 quad of the
+// The producer lane streams, two items ahead, the stress triple of time it+1 with halo 8 / 4 (72 x 36) and the
+// velocity pair with halo 4 / 2 (64 x 32) through a 2-stage TMA ring.  Every thread owns one float4 quad of the
 // 64 x 32 region: it rewinds the velocities of its quad (all threads; the result goes to a double-buffered shared
 // tile), then -- owner threads -- rewinds the stresses of the same quad from the neighbours' rewound velocities.
 #include "fwi_device.cuh"
@@ -21,12 +21,19 @@ using namespace dev;
 
 namespace {
 
-constexpr int NS = 3;
+#ifndef REV_NS
+#define REV_NS 2
+#endif
+#ifndef ADJ_NS
+#define ADJ_NS 2
+#endif
 constexpr int RW_BYTES = 3 * WCOLS * VPITCH * 4;   // stress triple, rows z0-8.., columns x0-4..
 constexpr int RV_BYTES = 2 * SCOLS * SPITCH * 4;   // velocity pair, rows z0-4.., columns x0-2..
 constexpr int RSTAGE_BYTES = RW_BYTES + RV_BYTES;
 constexpr int SV_BYTES = 2 * SCOLS * SPITCH * 4;   // rewound velocities
-constexpr size_t REV_SMEM = (size_t)NS * RSTAGE_BYTES + 2 * SV_BYTES + (NS + 1) * sizeof(TileDesc) + NS * 8 + 128;
+constexpr int NS = REV_NS;   // ring stages of the reverse kernel
+constexpr int FRM_BYTES = NCOMPUTE * 5 * 16;       // per-thread landing zone of the quad's saved frame values (5 fields)
+constexpr size_t REV_SMEM = (size_t)NS * RSTAGE_BYTES + 2 * SV_BYTES + FRM_BYTES + (NS + 1) * sizeof(TileDesc) + NS * 8 + 128;
 static_assert(RW_BYTES % 128 == 0 && RV_BYTES % 128 == 0, "TMA destination alignment");
 
 __global__ void __launch_bounds__(NCOMPUTE, 1)
@@ -34,8 +41,9 @@ rev_image_kernel(const __grid_constant__ BwdArgs a, int tz_first, int tx_first, 
   extern __shared__ unsigned char smem_raw[];
   unsigned char *base = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
   float *s_v_base = reinterpret_cast<float *>(base + NS * RSTAGE_BYTES);                            // [2][2][SCOLS][SPITCH]
-  TileDesc *sdesc = reinterpret_cast<TileDesc *>(base + NS * RSTAGE_BYTES + 2 * SV_BYTES);          // [NS + 1]
-  uint64_t *full = reinterpret_cast<uint64_t *>(base + NS * RSTAGE_BYTES + 2 * SV_BYTES + (NS + 1) * sizeof(TileDesc));
+  float *s_frm = reinterpret_cast<float *>(base + NS * RSTAGE_BYTES + 2 * SV_BYTES);                // [5][NCOMPUTE] quads
+  TileDesc *sdesc = reinterpret_cast<TileDesc *>(base + NS * RSTAGE_BYTES + 2 * SV_BYTES + FRM_BYTES);   // [NS + 1]
+  uint64_t *full = reinterpret_cast<uint64_t *>(base + NS * RSTAGE_BYTES + 2 * SV_BYTES + FRM_BYTES + (NS + 1) * sizeof(TileDesc));
 
   const Grid &g = a.g;
   const int tid = threadIdx.x;
@@ -53,7 +61,11 @@ rev_image_kernel(const __grid_constant__ BwdArgs a, int tz_first, int tx_first, 
   __syncthreads();
 
   auto produce = [&](int item, int stage, int ds) {
+#ifdef REV_SHOT_SLOW
     const int shot = item / ntiles, t = item - shot * ntiles;
+#else
+    const int t = item / a.batch, shot = item - t * a.batch;   // shot fastest: the shots of a tile share its coefficients in L2
+#endif
     const int z0 = (tz_first + t % ntz) * TILE_Z, x0 = (tx_first + t / ntz) * TILE_X;
     const int sz = a.st.src_z[shot], sx = a.st.src_x[shot];
     TileDesc d;
@@ -76,6 +88,7 @@ rev_image_kernel(const __grid_constant__ BwdArgs a, int tz_first, int tx_first, 
   if (tid == PRODUCER_TID)
     for (int s = 0; s < NS; s++)
       if (blockIdx.x + s * stride < nitems) produce(blockIdx.x + s * stride, s, s);
+  __syncthreads();   // the first descriptors are visible: per-item global loads may start before the TMA data lands
 
   const float dt = g.dt;
   const float kz1 = C1 * g.rdz, kz2 = C2 * g.rdz, kx1 = C1 * g.rdx, kx2 = C2 * g.rdx;
@@ -89,8 +102,7 @@ rev_image_kernel(const __grid_constant__ BwdArgs a, int tz_first, int tx_first, 
 
   int stage = 0, phase = 0, nb = 0, ds = 0;
   for (int item = blockIdx.x; item < nitems; item += stride) {
-    mbar_wait(&full[stage], phase);
-    const TileDesc d = sdesc[ds];
+    const TileDesc d = sdesc[ds];   // written by the producer >= 1 block barrier ago
     const int gz = d.z0 - 4 + 4 * q, gx = d.x0 - 2 + c;
     const bool inb = (unsigned)gx < (unsigned)g.nx && (unsigned)gz < (unsigned)g.nz;
     const bool owner = inner && inb;
@@ -103,19 +115,25 @@ rev_image_kernel(const __grid_constant__ BwdArgs a, int tz_first, int tx_first, 
 #pragma unroll
     for (int kk = 0; kk < 4; kk++) bx[kk] = colbox && (unsigned)(gz + kk - g.zlo) <= (unsigned)(g.zhi - g.zlo);
     const bool in_rect = gx >= g.xlo - 2 && gx <= g.xhi + 2 && gz + 3 >= g.zlo - 2 && gz <= g.zhi + 2;
-    const bool frame_tile = d.flags & TF_FRAME;
-    const float *frm = a.frames + ((long long)d.shot * g.nSteps + a.it) * 5 * g.f_len;
-    const FrameCol fc(g, gx);
+    // saved frame values of the quad (to_bnd, libCUFD.cu:388,403): copied asynchronously into this thread's
+    // landing zone, 5 x 16 bytes, no registers involved until they are needed
+    int fq = -1;
+    if ((d.flags & TF_FRAME) && in_rect) fq = frame_quad(g, gz, gx);
+    float *my_frm = s_frm + 4 * tid;
+    if (fq >= 0) {
+      const float *frm = a.frames + ((long long)d.shot * g.nSteps + a.it) * 5 * g.f_len + 4 * fq;
+#pragma unroll
+      for (int f = 0; f < 5; f++) cp_async16(my_frm + f * 4 * NCOMPUTE, frm + f * g.f_len);
+    }
 
-    // global operands of the velocity half: buoyancies, adjoint velocities and the rho accumulators of the quad
+    // global operands of the velocity half, requested before waiting for the ring: buoyancies, adjoint velocities
     const F4 byadt = ld4(mq + 3 * pl), bybdt = ld4(mq + 4 * pl);
-    F4 vza = zero4(), vxa = zero4(), accA = zero4(), accB = zero4();
+    F4 vza = zero4(), vxa = zero4();
     if (owner) {
       vza = ld4(sq + (ain + F_VZ) * pl);
       vxa = ld4(sq + (ain + F_VX) * pl);
-      accA = ld4(acc + G_RHO_A * pl);
-      accB = ld4(acc + G_RHO_B * pl);
     }
+    mbar_wait(&full[stage], phase);
 
     const unsigned char *sb = base + stage * RSTAGE_BYTES;
     const float *sw = reinterpret_cast<const float *>(sb);              // [3][WCOLS][VPITCH]: szz sxx sxz of time it+1
@@ -140,29 +158,21 @@ rev_image_kernel(const __grid_constant__ BwdArgs a, int tz_first, int tx_first, 
       for (int kk = 0; kk < 4; kk++) eb[kk] = d1[kk] + d2[kk];
     }
     F4 vz = ld4(sv + sj), vx = ld4(sv + SCOLS * SPITCH + sj);
+    F4 ga = zero4(), gb = zero4();
 #pragma unroll
     for (int kk = 0; kk < 4; kk++) {
       if (bx[kk]) {
         vz.v[kk] = fmaf(-ea[kk], byadt.v[kk], vz.v[kk]);
         vx.v[kk] = fmaf(-eb[kk], bybdt.v[kk], vx.v[kk]);
-        // g = -v_adj (d sigma) dt * (-byc^2 / 2)     (el_velocity.cu:101-104)
-        accA.v[kk] += (vza.v[kk] * ea[kk]) * (half_rdt * byadt.v[kk] * byadt.v[kk]);
-        accB.v[kk] += (vxa.v[kk] * eb[kk]) * (half_rdt * bybdt.v[kk] * bybdt.v[kk]);
+        // g = -v_adj (d sigma) dt * (-byc^2 / 2)     (el_velocity.cu:101-104); accumulated with the other planes below
+        ga.v[kk] = (vza.v[kk] * ea[kk]) * (half_rdt * byadt.v[kk] * byadt.v[kk]);
+        gb.v[kk] = (vxa.v[kk] * eb[kk]) * (half_rdt * bybdt.v[kk] * bybdt.v[kk]);
       }
     }
-    if (owner) {
-      st4(acc + G_RHO_A * pl, accA);
-      st4(acc + G_RHO_B * pl, accB);
-    }
-    if (frame_tile && in_rect) {  // to_bnd(v): exact values of time `it` on the 5-cell ring (libCUFD.cu:388)
-#pragma unroll
-      for (int kk = 0; kk < 4; kk++) {
-        const int fidx = fc.idx(gz + kk);
-        if (fidx >= 0) {
-          vz.v[kk] = frm[F_VZ * g.f_len + fidx];
-          vx.v[kk] = frm[F_VX * g.f_len + fidx];
-        }
-      }
+    if (fq >= 0) {  // exact values of time `it` on the ring
+      cp_async_wait_all();
+      vz = ld4(my_frm + F_VZ * 4 * NCOMPUTE);
+      vx = ld4(my_frm + F_VX * 4 * NCOMPUTE);
     }
     st4(s_v + sj, vz);
     st4(s_v + SCOLS * SPITCH + sj, vx);
@@ -173,11 +183,12 @@ rev_image_kernel(const __grid_constant__ BwdArgs a, int tz_first, int tx_first, 
       st4(fo + F_VX * pl, vx);
     }
     // global operands of the stress half, requested before the barrier
-    F4 ldt, l2mdt, amudt, za, xa, xza, gl, gm, gs;
+    F4 ldt, l2mdt, amudt, za, xa, xza, gl, gm, gs, accA, accB;
     if (wr) {
       ldt = ld4(mq); l2mdt = ld4(mq + pl); amudt = ld4(mq + 2 * pl);
       za = ld4(sq + (ain + F_SZZ) * pl); xa = ld4(sq + (ain + F_SXX) * pl); xza = ld4(sq + (ain + F_SXZ) * pl);
       gl = ld4(acc + G_LAM * pl); gm = ld4(acc + G_MU * pl); gs = ld4(acc + G_MUS * pl);
+      accA = ld4(acc + G_RHO_A * pl); accB = ld4(acc + G_RHO_B * pl);
     }
     __syncthreads();  // s_v is complete; nobody reads ring slot `stage` any more
     if (tid == PRODUCER_TID && item + NS * stride < nitems) produce(item + NS * stride, stage, ds == 0 ? NS : ds - 1);
@@ -218,20 +229,21 @@ rev_image_kernel(const __grid_constant__ BwdArgs a, int tz_first, int tx_first, 
             gs.v[kk] += -xza.v[kk] * e * (q_rdt * amudt.v[kk] * amudt.v[kk]);
           }
         }
+#pragma unroll
+        for (int kk = 0; kk < 4; kk++) {
+          accA.v[kk] += ga.v[kk];
+          accB.v[kk] += gb.v[kk];
+        }
         st4(acc + G_LAM * pl, gl);
         st4(acc + G_MU * pl, gm);
         st4(acc + G_MUS * pl, gs);
+        st4(acc + G_RHO_A * pl, accA);
+        st4(acc + G_RHO_B * pl, accB);
       }
-      if (frame_tile) {  // to_bnd(sigma) (libCUFD.cu:403)
-#pragma unroll
-        for (int kk = 0; kk < 4; kk++) {
-          const int fidx = fc.idx(gz + kk);
-          if (fidx >= 0) {
-            szz.v[kk] = frm[F_SZZ * g.f_len + fidx];
-            sxx.v[kk] = frm[F_SXX * g.f_len + fidx];
-            sxz.v[kk] = frm[F_SXZ * g.f_len + fidx];
-          }
-        }
+      if (fq >= 0) {  // to_bnd(sigma) (libCUFD.cu:403)
+        szz = ld4(my_frm + F_SZZ * 4 * NCOMPUTE);
+        sxx = ld4(my_frm + F_SXX * 4 * NCOMPUTE);
+        sxz = ld4(my_frm + F_SXZ * 4 * NCOMPUTE);
       }
       st4(fo + F_SZZ * pl, szz);
       st4(fo + F_SXX * pl, sxx);
@@ -255,6 +267,7 @@ rev_image_kernel(const __grid_constant__ BwdArgs a, int tz_first, int tx_first, 
 // quad.  Residuals are injected through a small shared table (receivers add into it before the barrier, the owner
 // of the cell picks the sum up and clears it).
 // =================================================================================================
+constexpr int ANS = ADJ_NS;   // ring stages of the adjoint kernel
 constexpr int AS_BYTES = 3 * VCOLS * VPITCH * 4;                 // adjoint stresses, rows z0-8.., columns x0-3..
 constexpr int AS_PAD = (AS_BYTES + 127) / 128 * 128;
 constexpr int AV_BYTES = 2 * SCOLS * SPITCH * 4;                 // adjoint velocities, rows z0-4.., columns x0-2..
@@ -262,18 +275,18 @@ constexpr int ASTAGE_BYTES = AS_PAD + AV_BYTES;
 constexpr int APHI_BYTES = 4 * SCOLS * SPITCH * 4;               // new phi of the region (tiles touching the CPML)
 constexpr int AINJ_BYTES = SCOLS * SPITCH * 4;                   // residual injection table
 constexpr size_t ADJ_SMEM =
-    (size_t)NS * ASTAGE_BYTES + 2 * AV_BYTES + APHI_BYTES + 2 * AINJ_BYTES + (NS + 1) * sizeof(TileDesc) + NS * 8 + 128;
+    (size_t)ANS * ASTAGE_BYTES + 2 * AV_BYTES + APHI_BYTES + 2 * AINJ_BYTES + (ANS + 1) * sizeof(TileDesc) + ANS * 8 + 128;
 static_assert(AV_BYTES % 128 == 0, "TMA destination alignment");
 
 __global__ void __launch_bounds__(NCOMPUTE, 1) adj_step_kernel(const __grid_constant__ BwdArgs a) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char *base = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
-  float *s_v_base = reinterpret_cast<float *>(base + NS * ASTAGE_BYTES);                         // [2][2][SCOLS][SPITCH]
-  float *s_phi = reinterpret_cast<float *>(base + NS * ASTAGE_BYTES + 2 * AV_BYTES);             // [4][SCOLS][SPITCH]
-  float *s_inj_base = reinterpret_cast<float *>(base + NS * ASTAGE_BYTES + 2 * AV_BYTES + APHI_BYTES);   // [2][SCOLS][SPITCH]
-  unsigned char *tail = base + NS * ASTAGE_BYTES + 2 * AV_BYTES + APHI_BYTES + 2 * AINJ_BYTES;
-  TileDesc *sdesc = reinterpret_cast<TileDesc *>(tail);                                          // [NS + 1]
-  uint64_t *full = reinterpret_cast<uint64_t *>(tail + (NS + 1) * sizeof(TileDesc));
+  float *s_v_base = reinterpret_cast<float *>(base + ANS * ASTAGE_BYTES);                         // [2][2][SCOLS][SPITCH]
+  float *s_phi = reinterpret_cast<float *>(base + ANS * ASTAGE_BYTES + 2 * AV_BYTES);             // [4][SCOLS][SPITCH]
+  float *s_inj_base = reinterpret_cast<float *>(base + ANS * ASTAGE_BYTES + 2 * AV_BYTES + APHI_BYTES);   // [2][SCOLS][SPITCH]
+  unsigned char *tail = base + ANS * ASTAGE_BYTES + 2 * AV_BYTES + APHI_BYTES + 2 * AINJ_BYTES;
+  TileDesc *sdesc = reinterpret_cast<TileDesc *>(tail);                                          // [ANS + 1]
+  uint64_t *full = reinterpret_cast<uint64_t *>(tail + (ANS + 1) * sizeof(TileDesc));
 
   const Grid &g = a.g;
   const int tid = threadIdx.x;
@@ -292,14 +305,14 @@ __global__ void __launch_bounds__(NCOMPUTE, 1) adj_step_kernel(const __grid_cons
   const int xq_lo = g.nPml + 2, xq_hi = g.nx - g.nPml - 3;
 
   if (tid == 0) {
-    for (int s = 0; s < NS; s++) mbar_init(&full[s], 1);
+    for (int s = 0; s < ANS; s++) mbar_init(&full[s], 1);
     fence_barrier_init();
   }
   for (int i = tid; i < 2 * AINJ_BYTES / 16; i += NCOMPUTE) reinterpret_cast<float4 *>(s_inj_base)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncthreads();
 
   auto produce = [&](int item, int stage, int ds) {
-    const int shot = item / ntiles, tile = item - shot * ntiles;
+    const int tile = item / a.batch, shot = item - tile * a.batch;   // shot fastest
     const int z0 = (tile % g.tiles_z) * TILE_Z, x0 = (tile / g.tiles_z) * TILE_X;
     const int sz = a.st.src_z[shot], sx = a.st.src_x[shot];
     TileDesc d;
@@ -321,8 +334,9 @@ __global__ void __launch_bounds__(NCOMPUTE, 1) adj_step_kernel(const __grid_cons
     tma_load_3d(sb + AS_PAD, &a.tm.vn, z0 - 4, x0 - 2 + XM, p0 + F_VZ, &full[stage]);
   };
   if (tid == PRODUCER_TID)
-    for (int s = 0; s < NS; s++)
+    for (int s = 0; s < ANS; s++)
       if (blockIdx.x + s * stride < nitems) produce(blockIdx.x + s * stride, s, s);
+  __syncthreads();   // the first descriptors are visible
 
   const float dt = g.dt;
   // adjoint-kernel spelling of the differences: (-c1 (..) + c2 (..)) / h  (el_stress_adj.cu:54-61)
@@ -336,8 +350,7 @@ __global__ void __launch_bounds__(NCOMPUTE, 1) adj_step_kernel(const __grid_cons
 
   int stage = 0, phase = 0, nb = 0, ds = 0;
   for (int item = blockIdx.x; item < nitems; item += stride) {
-    mbar_wait(&full[stage], phase);
-    const TileDesc d = sdesc[ds];
+    const TileDesc d = sdesc[ds];   // written by the producer >= 1 block barrier ago
     const int gz = d.z0 - 4 + 4 * q, gx = d.x0 - 2 + c;
     const bool inb = (unsigned)gx < (unsigned)g.nx && (unsigned)gz < (unsigned)g.nz;
     const bool owner = inner && inb;
@@ -348,6 +361,7 @@ __global__ void __launch_bounds__(NCOMPUTE, 1) adj_step_kernel(const __grid_cons
     const bool actq = gx >= 2 && gx <= g.ax_hi && gz + 3 >= 2 && gz <= g.az_hi;
     const F4 ldt = ld4(mq), l2mdt = ld4(mq + pl), amudt = ld4(mq + 2 * pl);
     const F4 byadt = ld4(mq + 3 * pl), bybdt = ld4(mq + 4 * pl);
+    mbar_wait(&full[stage], phase);
 
     const unsigned char *sb = base + stage * ASTAGE_BYTES;
     const float *sa = reinterpret_cast<const float *>(sb);              // [3][VCOLS][VPITCH]: adjoint szz sxx sxz
@@ -491,7 +505,7 @@ __global__ void __launch_bounds__(NCOMPUTE, 1) adj_step_kernel(const __grid_cons
       st4(ao + F_VX * pl, vx);
     }
     __syncthreads();  // s_v / s_phi / s_inj are complete; nobody reads ring slot `stage` any more
-    if (tid == PRODUCER_TID && item + NS * stride < nitems) produce(item + NS * stride, stage, ds == 0 ? NS : ds - 1);
+    if (tid == PRODUCER_TID && item + ANS * stride < nitems) produce(item + ANS * stride, stage, ds == 0 ? ANS : ds - 1);
 
     // ---- adjoint stress of the same quad, owner threads (el_stress_adj.cu:52-95) ----
     if (owner) {
@@ -589,8 +603,8 @@ __global__ void __launch_bounds__(NCOMPUTE, 1) adj_step_kernel(const __grid_cons
     }
     if (pml_tile) __syncthreads();  // s_phi is single-buffered: everyone is done reading it before the next item writes
     nb ^= 1;
-    if (++ds == NS + 1) ds = 0;
-    if (++stage == NS) { stage = 0; phase ^= 1; }
+    if (++ds == ANS + 1) ds = 0;
+    if (++stage == ANS) { stage = 0; phase ^= 1; }
   }
 }
 

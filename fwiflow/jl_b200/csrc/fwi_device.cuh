@@ -108,28 +108,26 @@ struct __align__(16) TileDesc {  // built by the producer lane, read (broadcast)
 };
 static_assert(sizeof(TileDesc) == 64, "descriptor size");
 
-// Boundary frames: per step and field [left 5 columns | right 5 columns | top 5 rows | bottom 5 rows] of the ring
-// that starts 2 cells outside the inner box (Boundary.cu:17-27, utilities.cu:361-424).  One instance per thread
-// and tile: the column part of the index is computed once, idx(z) is then 3-4 instructions per cell.
-struct FrameCol {
-  int colbase, midbase, zlo2, zhi2, zlo_in, zhi_in;
-  bool xin;
-  __device__ __forceinline__ FrameCol(const Grid &g, int gx) {
-    xin = gx >= g.xlo - 2 && gx <= g.xhi + 2;
-    colbase = -1;
-    if (gx <= g.xlo + 2) colbase = (gx - (g.xlo - 2)) * g.f_nzB;
-    else if (gx >= g.xhi - 2) colbase = (5 + gx - (g.xhi - 2)) * g.f_nzB;
-    midbase = 10 * g.f_nzB + (gx - (g.xlo + 3)) * 10;
-    zlo2 = g.zlo - 2; zhi2 = g.zhi + 2; zlo_in = g.zlo + 2; zhi_in = g.zhi - 2;
-  }
-  __device__ __forceinline__ int idx(int z) const {
-    if (!xin || z < zlo2 || z > zhi2) return -1;
-    if (colbase >= 0) return colbase + z - zlo2;
-    if (z <= zlo_in) return midbase + z - zlo2;
-    if (z >= zhi_in) return midbase + 5 + z - zhi_in;
-    return -1;
-  }
-};
+// Boundary frames (the reference's Bnd store, Boundary.cu:17-41, utilities.cu:361-424): per step and field the
+// float4 quads that intersect the 5-cell ring starting 2 cells outside the inner box, laid out as
+// [left 5 columns | right 5 columns | per middle column: 2 top quads, 2 bottom quads].  Returns the quad slot of
+// the quad starting at row gz (a multiple of 4) in column gx, or -1.  Restoring a whole quad also restores a few
+// cells next to the ring with their exact forward values, which is harmless.
+__device__ __forceinline__ int frame_quad(const Grid &g, int gz, int gx) {
+  if (gx < g.xlo - 2 || gx > g.xhi + 2 || gz < g.f_zq0 || gz > g.zhi + 2) return -1;
+  if (gx <= g.xlo + 2) return (gx - (g.xlo - 2)) * g.f_nqB + ((gz - g.f_zq0) >> 2);
+  if (gx >= g.xhi - 2) return (5 + gx - (g.xhi - 2)) * g.f_nqB + ((gz - g.f_zq0) >> 2);
+  const int t = gz >> 2, mid = 10 * g.f_nqB + (gx - (g.xlo + 3)) * 4;
+  if ((unsigned)(t - g.f_tq0) < 2u) return mid + (t - g.f_tq0);
+  if ((unsigned)(t - g.f_bq0) < 2u) return mid + 2 + (t - g.f_bq0);
+  return -1;
+}
+// 16-byte asynchronous copy global -> shared (LDGSTS): no register staging; complete after cp_async_wait_all()
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 __device__ __forceinline__ bool tile_touches_frame(const Grid &g, int z0, int x0) {
   return !(z0 > g.zhi + 2 || z0 + TILE_Z - 1 < g.zlo - 2 || x0 > g.xhi + 2 || x0 + TILE_X - 1 < g.xlo - 2) &&
          !(z0 > g.zlo + 2 && z0 + TILE_Z - 1 < g.zhi - 2 && x0 > g.xlo + 2 && x0 + TILE_X - 1 < g.xhi - 2);

@@ -7,9 +7,9 @@
 //
 // Structure (B200): one CTA of 16 warps per SM, looping over (shot, tile) work items.
 //   * producer: one lane of the warp that owns the two right-hand halo columns (it has no velocity work) builds, for
-//     the item three iterations ahead, a small tile descriptor in shared memory and asks the TMA unit for the item's
+//     the item two iterations ahead, a small tile descriptor in shared memory and asks the TMA unit for the item's
 //     halo tiles -- velocity pair (72 x 34) and stress triple (64 x 32), two cp.async.bulk.tensor boxes, 44 KB --
-//     into a 3-stage shared-memory ring; completion is counted in bytes on an mbarrier.  The slot it refills is
+//     into a 2-stage shared-memory ring; completion is counted in bytes on an mbarrier.  The slot it refills is
 //     the one every warp finished reading before the block barrier of the current item.
 //   * compute: every thread owns ONE float4 quad (4 consecutive z cells) of the 64 x 32 stress region for
 //     both half-steps.  Stress: derivatives of the velocity tile, CPML, update, source; the new stresses go to a
@@ -31,7 +31,10 @@ using namespace dev;
 
 namespace {
 
-constexpr int NS = 3;                    // ring stages
+#ifndef FWD_NS
+#define FWD_NS 2
+#endif
+constexpr int NS = FWD_NS;               // ring stages
 constexpr int NTHREADS_FWD = NCOMPUTE;
 constexpr int V_BYTES = 2 * VCOLS * VPITCH * 4;
 constexpr int S_BYTES = 3 * SCOLS * SPITCH * 4;
@@ -68,7 +71,7 @@ __global__ void __launch_bounds__(NTHREADS_FWD, 1) fwd_step_kernel(const __grid_
   // producer step: descriptor (slot `ds` of NS + 1, so that it never overwrites the one in use) + TMA requests of
   // one item into ring slot `stage`
   auto produce = [&](int item, int stage, int ds) {
-    const int shot = item / ntiles, tile = item - shot * ntiles;
+    const int tile = item / a.batch, shot = item - tile * a.batch;   // shot fastest: the shots of a tile share its coefficients in L2
     const int tz = tile % g.tiles_z, tx = tile / g.tiles_z;
     const int z0 = tz * TILE_Z, x0 = tx * TILE_X;
     const int sz = a.st.src_z[shot], sx = a.st.src_x[shot];
@@ -158,18 +161,14 @@ __global__ void __launch_bounds__(NTHREADS_FWD, 1) fwd_step_kernel(const __grid_
     F4 szz = ld4(so + sj), sxx = ld4(so + SCOLS * SPITCH + sj), sxz = ld4(so + 2 * SCOLS * SPITCH + sj);
 
     if (SAVE && (d.flags & TF_FRAME) && owner) {  // from_bnd x5: state at time `it`, before the update (libCUFD.cu:206)
-      float *frm = a.frames + ((long long)d.shot * g.nSteps + a.it) * 5 * g.f_len;
-      const FrameCol fc(g, gx);
-#pragma unroll
-      for (int kk = 0; kk < 4; kk++) {
-        const int fidx = fc.idx(gz + kk);
-        if (fidx >= 0) {
-          frm[F_SZZ * g.f_len + fidx] = szz.v[kk];
-          frm[F_SXX * g.f_len + fidx] = sxx.v[kk];
-          frm[F_SXZ * g.f_len + fidx] = sxz.v[kk];
-          frm[F_VZ * g.f_len + fidx] = zB.v[kk];
-          frm[F_VX * g.f_len + fidx] = xB.v[kk];
-        }
+      const int fq = frame_quad(g, gz, gx);
+      if (fq >= 0) {
+        float *frm = a.frames + ((long long)d.shot * g.nSteps + a.it) * 5 * g.f_len + 4 * fq;
+        st4(frm + F_SZZ * g.f_len, szz);
+        st4(frm + F_SXX * g.f_len, sxx);
+        st4(frm + F_SXZ * g.f_len, sxz);
+        st4(frm + F_VZ * g.f_len, zB);
+        st4(frm + F_VX * g.f_len, xB);
       }
     }
     if (zq) {  // z-CPML on the whole quad: a = 0, b = 1, 1/K = 1 outside the layer (el_stress.cu:57-60,74-77)

@@ -69,16 +69,6 @@ __device__ __forceinline__ float stress_inc(float s, float lam, float mu, float 
 #endif
 }
 
-__device__ __forceinline__ int frame_index(const Grid &g, int z, int x) {
-  if (z < g.zlo - 2 || z > g.zhi + 2 || x < g.xlo - 2 || x > g.xhi + 2) return -1;
-  const int zr = z - (g.zlo - 2);
-  if (x <= g.xlo + 2) return (x - (g.xlo - 2)) * g.f_nzB + zr;
-  if (x >= g.xhi - 2) return (5 + x - (g.xhi - 2)) * g.f_nzB + zr;
-  if (z <= g.zlo + 2) return 10 * g.f_nzB + (x - (g.xlo + 3)) * 10 + zr;
-  if (z >= g.zhi - 2) return 10 * g.f_nzB + (x - (g.xlo + 3)) * 10 + 5 + (z - (g.zhi - 2));
-  return -1;
-}
-
 __device__ __forceinline__ bool z_in_pml(const Grid &g, int z) { return z < g.nPml || z > g.nz - g.nPml - g.nPad - 1; }
 __device__ __forceinline__ bool x_in_pml_s(const Grid &g, int x) { return x < g.nPml || x > g.nx - g.nPml - 1; }
 __device__ __forceinline__ bool x_in_pml_v(const Grid &g, int x) { return x < g.nPml || x > g.nx - g.nPml; }

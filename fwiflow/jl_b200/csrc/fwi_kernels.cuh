@@ -6,7 +6,7 @@
 //            allocation.  A "plane pointer" always points at (z=0, x=0).
 //   state  = [shot][slot][plane]: 36 planes per concurrent shot (slots below)
 //   model  = lambda, mu, mu_bar, byc_a, byc_b planes shared by all shots
-//   frames = [shot][step][field 0..4][flen]  saved boundary frames (5 layers)
+//   frames = [shot][step][field 0..4][flen]  saved boundary frames (the quads covering the 5-cell ring)
 //   traces = [shot][step][nrp]  (receiver fastest -> coalesced record / inject)
 #pragma once
 #include <cuda.h>
@@ -53,7 +53,10 @@ struct Grid {
   int tiles_z, tiles_x;    // tile grid covering [0,nz) x [0,nx)
   float dt, rdz, rdx;      // 1/dz, 1/dx
   // boundary frames
-  int f_nzB;           // zhi-zlo+5
+  // boundary frames, stored at float4-quad granularity (every quad that intersects the 5-cell ring)
+  int f_zq0;           // first row of the first ring quad: (zlo-2) & ~3
+  int f_nqB;           // quads per column of the left / right bands
+  int f_tq0, f_bq0;    // z >> 2 of the first quad of the top / bottom bands (two quads each)
   int f_len;           // floats per field per step
 };
 

@@ -127,8 +127,13 @@ void build_grid(const Para &p, Grid &g) {
   g.dt = p.dt;
   g.rdz = (float)(1.0 / (double)p.dz);
   g.rdx = (float)(1.0 / (double)p.dx);
-  g.f_nzB = g.zhi - g.zlo + 5;
-  g.f_len = 10 * g.f_nzB + 10 * std::max(0, g.xhi - g.xlo + 1 - 6);
+  // frames: left/right bands = 10 columns x the quads covering rows zlo-2 .. zhi+2; top/bottom bands = 2 quads each
+  // for the columns in between (5 consecutive rows always span exactly two aligned quads)
+  g.f_zq0 = (g.zlo - 2) & ~3;
+  g.f_nqB = ((g.zhi + 2) >> 2) - (g.f_zq0 >> 2) + 1;
+  g.f_tq0 = (g.zlo - 2) >> 2;
+  g.f_bq0 = (g.zhi - 2) >> 2;
+  g.f_len = 4 * (10 * g.f_nqB + 4 * std::max(0, g.xhi - g.xlo + 1 - 6));
   if (g.zhi - g.zlo + 1 < 8 || g.xhi - g.xlo + 1 < 8)
     throw Error(FWI_B200_ERR_GEOM, "grid too small: fewer than 8 cells between the PML layers");
 }
