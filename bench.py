@@ -12,8 +12,9 @@ computes it (calc_id 1).  One "step" = one gradient evaluation of the rank's 30 
            for N > 1 every step ends with the NCCL all-reduce of [grad_lambda|grad_mu|grad_den|misfit].
   e2e    : same metric through the reference-facing C-ABI call with HOST buffers (fwi_b200_backward: model and stf
            H2D, Shot<id>.bin read + H2D, gradients D2H inside the timed region).
-  roofline: dominant kernel, algorithmic bytes per launch / CUDA-event time per launch
-           / measured HBM peak (MEASURED_PEAKS.json).
+  roofline: dominant kernel (largest share of the step), algorithmic bytes per launch (DESIGN.md section 3:
+           60 B/cell forward, 64 B/box-cell reverse+imaging, 60 B/cell adjoint, + CPML strips) / CUDA-event time per
+           launch / measured HBM peak (MEASURED_PEAKS.json); traffic = ncu dram bytes per launch (profiles/traffic.json).
   cpu_baseline: the CPU oracle port (oracle/) on the host cores, bounded sample of the same workload.
 """
 from __future__ import annotations
@@ -268,6 +269,8 @@ def run_ours(args):
     traffic = ncu_traffic()
     kernels = []
     names = {1: "fwd_step_kernel<save_frames>", 2: "rev_image_kernel", 3: "adj_step_kernel"}
+    per_cell = {1: "60 + 32 (fz + fx) B per cell + frame quads", 2: "64 B per inner-box cell",
+                3: "60 + 64 (fz + fx) B per cell"}
     per_step_launch = {1: NSTEPS - 1, 2: NSTEPS - 1, 3: NSTEPS}
     nb = max(1, -(-len(my_ids) // plan.batch))
     if rank == 0:
@@ -275,6 +278,7 @@ def run_ours(args):
             k_ms, k_bytes = plan.time_kernel(which, iters=200, stream=stream.cuda_stream)
             ach = k_bytes / (k_ms * 1e-3) / 1e9
             kernels.append({"kernel": names[which], "ms_per_launch": k_ms, "alg_bytes_per_launch": k_bytes,
+                            "alg_bytes_rule": per_cell[which],
                             "achieved_gbs": ach, "frac": ach / peak, "launches_per_step": per_step_launch[which] * nb,
                             "share_of_step": per_step_launch[which] * nb * k_ms / (ms / args.steps),
                             "traffic": traffic.get(names[which])})

@@ -32,7 +32,7 @@ constexpr int RV_BYTES = 2 * SCOLS * SPITCH * 4;   // velocity pair, rows z0-4..
 constexpr int RSTAGE_BYTES = RW_BYTES + RV_BYTES;
 constexpr int SV_BYTES = 2 * SCOLS * SPITCH * 4;   // rewound velocities
 constexpr int NS = REV_NS;   // ring stages of the reverse kernel
-constexpr int FRM_BYTES = NCOMPUTE * 5 * 16;       // per-thread landing zone of the quad's saved frame values (5 fields)
+constexpr int FRM_BYTES = NCOMPUTE * 3 * 16;       // per-thread landing zone of the quad's saved stress frame values
 constexpr size_t REV_SMEM = (size_t)NS * RSTAGE_BYTES + 2 * SV_BYTES + FRM_BYTES + (NS + 1) * sizeof(TileDesc) + NS * 8 + 128;
 static_assert(RW_BYTES % 128 == 0 && RV_BYTES % 128 == 0, "TMA destination alignment");
 
@@ -41,7 +41,7 @@ rev_image_kernel(const __grid_constant__ BwdArgs a, int tz_first, int tx_first, 
   extern __shared__ unsigned char smem_raw[];
   unsigned char *base = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
   float *s_v_base = reinterpret_cast<float *>(base + NS * RSTAGE_BYTES);                            // [2][2][SCOLS][SPITCH]
-  float *s_frm = reinterpret_cast<float *>(base + NS * RSTAGE_BYTES + 2 * SV_BYTES);                // [5][NCOMPUTE] quads
+  float *s_frm = reinterpret_cast<float *>(base + NS * RSTAGE_BYTES + 2 * SV_BYTES);                // [3][NCOMPUTE] quads: szz sxx sxz
   TileDesc *sdesc = reinterpret_cast<TileDesc *>(base + NS * RSTAGE_BYTES + 2 * SV_BYTES + FRM_BYTES);   // [NS + 1]
   uint64_t *full = reinterpret_cast<uint64_t *>(base + NS * RSTAGE_BYTES + 2 * SV_BYTES + FRM_BYTES + (NS + 1) * sizeof(TileDesc));
 
@@ -115,15 +115,19 @@ rev_image_kernel(const __grid_constant__ BwdArgs a, int tz_first, int tx_first, 
 #pragma unroll
     for (int kk = 0; kk < 4; kk++) bx[kk] = colbox && (unsigned)(gz + kk - g.zlo) <= (unsigned)(g.zhi - g.zlo);
     const bool in_rect = gx >= g.xlo - 2 && gx <= g.xhi + 2 && gz + 3 >= g.zlo - 2 && gz <= g.zhi + 2;
-    // saved frame values of the quad (to_bnd, libCUFD.cu:388,403): copied asynchronously into this thread's
-    // landing zone, 5 x 16 bytes, no registers involved until they are needed
+    // saved frame values of the quad (to_bnd, libCUFD.cu:388,403), copied asynchronously (LDGSTS, no registers):
+    // the velocities straight into the quad's place in the rewound-velocity tile, the stresses into this thread's
+    // landing zone.  State slots hold F_VZ F_VX F_SZZ F_SXX F_SXZ in that order.
     int fq = -1;
     if ((d.flags & TF_FRAME) && in_rect) fq = frame_quad(g, gz, gx);
+    float *s_v = s_v_base + nb * (SV_BYTES / 4);
     float *my_frm = s_frm + 4 * tid;
     if (fq >= 0) {
       const float *frm = a.frames + ((long long)d.shot * g.nSteps + a.it) * 5 * g.f_len + 4 * fq;
+      cp_async16(s_v + sj, frm + F_VZ * g.f_len);
+      cp_async16(s_v + SCOLS * SPITCH + sj, frm + F_VX * g.f_len);
 #pragma unroll
-      for (int f = 0; f < 5; f++) cp_async16(my_frm + f * 4 * NCOMPUTE, frm + f * g.f_len);
+      for (int f = 0; f < 3; f++) cp_async16(my_frm + f * 4 * NCOMPUTE, frm + (F_SZZ + f) * g.f_len);
     }
 
     // global operands of the velocity half, requested before waiting for the ring: buoyancies, adjoint velocities
@@ -138,7 +142,6 @@ rev_image_kernel(const __grid_constant__ BwdArgs a, int tz_first, int tx_first, 
     const unsigned char *sb = base + stage * RSTAGE_BYTES;
     const float *sw = reinterpret_cast<const float *>(sb);              // [3][WCOLS][VPITCH]: szz sxx sxz of time it+1
     const float *sv = reinterpret_cast<const float *>(sb + RW_BYTES);   // [2][SCOLS][SPITCH]: vz vx of time it+1
-    float *s_v = s_v_base + nb * (SV_BYTES / 4);
 
     // ---- v^{it} = v^{it+1} - velocity(sigma^{it+1}) on 16 quads x 32 columns; rho imaging terms (el_velocity.cu:84-110) ----
     const float *zz = sw + (c + 2) * VPITCH + 4 * (q + 1);
@@ -169,13 +172,14 @@ rev_image_kernel(const __grid_constant__ BwdArgs a, int tz_first, int tx_first, 
         gb.v[kk] = (vxa.v[kk] * eb[kk]) * (half_rdt * bybdt.v[kk] * bybdt.v[kk]);
       }
     }
-    if (fq >= 0) {  // exact values of time `it` on the ring
+    if (fq >= 0) {  // exact values of time `it` on the ring: already in the shared tile
       cp_async_wait_all();
-      vz = ld4(my_frm + F_VZ * 4 * NCOMPUTE);
-      vx = ld4(my_frm + F_VX * 4 * NCOMPUTE);
+      vz = ld4(s_v + sj);
+      vx = ld4(s_v + SCOLS * SPITCH + sj);
+    } else {
+      st4(s_v + sj, vz);
+      st4(s_v + SCOLS * SPITCH + sj, vx);
     }
-    st4(s_v + sj, vz);
-    st4(s_v + SCOLS * SPITCH + sj, vx);
     float *fo = sq + fout * pl;
     const bool wr = owner && in_rect;
     if (wr) {
@@ -241,9 +245,9 @@ rev_image_kernel(const __grid_constant__ BwdArgs a, int tz_first, int tx_first, 
         st4(acc + G_RHO_B * pl, accB);
       }
       if (fq >= 0) {  // to_bnd(sigma) (libCUFD.cu:403)
-        szz = ld4(my_frm + F_SZZ * 4 * NCOMPUTE);
-        sxx = ld4(my_frm + F_SXX * 4 * NCOMPUTE);
-        sxz = ld4(my_frm + F_SXZ * 4 * NCOMPUTE);
+        szz = ld4(my_frm);
+        sxx = ld4(my_frm + 4 * NCOMPUTE);
+        sxz = ld4(my_frm + 8 * NCOMPUTE);
       }
       st4(fo + F_SZZ * pl, szz);
       st4(fo + F_SXX * pl, sxx);
@@ -275,7 +279,7 @@ constexpr int ASTAGE_BYTES = AS_PAD + AV_BYTES;
 constexpr int APHI_BYTES = 4 * SCOLS * SPITCH * 4;               // new phi of the region (tiles touching the CPML)
 constexpr int AINJ_BYTES = SCOLS * SPITCH * 4;                   // residual injection table
 constexpr size_t ADJ_SMEM =
-    (size_t)ANS * ASTAGE_BYTES + 2 * AV_BYTES + APHI_BYTES + 2 * AINJ_BYTES + (ANS + 1) * sizeof(TileDesc) + ANS * 8 + 128;
+    (size_t)ANS * ASTAGE_BYTES + 2 * AV_BYTES + APHI_BYTES + AINJ_BYTES + (ANS + 1) * sizeof(TileDesc) + ANS * 8 + 128;
 static_assert(AV_BYTES % 128 == 0, "TMA destination alignment");
 
 __global__ void __launch_bounds__(NCOMPUTE, 1) adj_step_kernel(const __grid_constant__ BwdArgs a) {
@@ -283,8 +287,8 @@ __global__ void __launch_bounds__(NCOMPUTE, 1) adj_step_kernel(const __grid_cons
   unsigned char *base = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
   float *s_v_base = reinterpret_cast<float *>(base + ANS * ASTAGE_BYTES);                         // [2][2][SCOLS][SPITCH]
   float *s_phi = reinterpret_cast<float *>(base + ANS * ASTAGE_BYTES + 2 * AV_BYTES);             // [4][SCOLS][SPITCH]
-  float *s_inj_base = reinterpret_cast<float *>(base + ANS * ASTAGE_BYTES + 2 * AV_BYTES + APHI_BYTES);   // [2][SCOLS][SPITCH]
-  unsigned char *tail = base + ANS * ASTAGE_BYTES + 2 * AV_BYTES + APHI_BYTES + 2 * AINJ_BYTES;
+  float *s_inj = reinterpret_cast<float *>(base + ANS * ASTAGE_BYTES + 2 * AV_BYTES + APHI_BYTES);        // [SCOLS][SPITCH]
+  unsigned char *tail = base + ANS * ASTAGE_BYTES + 2 * AV_BYTES + APHI_BYTES + AINJ_BYTES;
   TileDesc *sdesc = reinterpret_cast<TileDesc *>(tail);                                          // [ANS + 1]
   uint64_t *full = reinterpret_cast<uint64_t *>(tail + (ANS + 1) * sizeof(TileDesc));
 
@@ -308,7 +312,7 @@ __global__ void __launch_bounds__(NCOMPUTE, 1) adj_step_kernel(const __grid_cons
     for (int s = 0; s < ANS; s++) mbar_init(&full[s], 1);
     fence_barrier_init();
   }
-  for (int i = tid; i < 2 * AINJ_BYTES / 16; i += NCOMPUTE) reinterpret_cast<float4 *>(s_inj_base)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = tid; i < AINJ_BYTES / 16; i += NCOMPUTE) reinterpret_cast<float4 *>(s_inj)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncthreads();
 
   auto produce = [&](int item, int stage, int ds) {
@@ -367,7 +371,6 @@ __global__ void __launch_bounds__(NCOMPUTE, 1) adj_step_kernel(const __grid_cons
     const float *sa = reinterpret_cast<const float *>(sb);              // [3][VCOLS][VPITCH]: adjoint szz sxx sxz
     const float *sva = reinterpret_cast<const float *>(sb + AS_PAD);    // [2][SCOLS][SPITCH]: adjoint vz vx
     float *s_v = s_v_base + nb * (AV_BYTES / 4);
-    float *s_inj = s_inj_base + nb * (AINJ_BYTES / 4);
 
     // ---- adjoint velocity on 16 quads x 32 columns (el_velocity_adj.cu:56-100) ----
     const float *zz = sa + (c + 1) * VPITCH + 4 * (q + 1);
@@ -601,7 +604,8 @@ __global__ void __launch_bounds__(NCOMPUTE, 1) adj_step_kernel(const __grid_cons
       st4(ao + F_SXX * pl, sxx);
       st4(ao + F_SXZ * pl, sxz);
     }
-    if (pml_tile) __syncthreads();  // s_phi is single-buffered: everyone is done reading it before the next item writes
+    // s_phi and the injection table are single-buffered: everyone is done with them before the next item writes
+    if (pml_tile || d.r1 > d.r0) __syncthreads();
     nb ^= 1;
     if (++ds == ANS + 1) ds = 0;
     if (++stage == ANS) { stage = 0; phase ^= 1; }

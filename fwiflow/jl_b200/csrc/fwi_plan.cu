@@ -689,9 +689,10 @@ extern "C" int fwi_b200_plan_time_kernel(fwi_b200_plan *pl, int which, int iters
       const double box = (double)(g.zhi - g.zlo + 1) * (g.xhi - g.xlo + 1) * nb;
       const double fz = 2.0 * g.nPml / g.nz, fx = 2.0 * g.nPml / g.nx;
       double b = 0;
+      // 60 B forward, 124 B backward = 64 (reverse + imaging) + 60 (adjoint)
       if (which <= 1) b = cells * (60.0 + 32.0 * (fz + fx));
-      else if (which == 2) b = box * 140.0;        // 10 R + 5 W state, 5 coeff, 5 R+W imaging accumulators
-      else b = cells * (60.0 + 64.0 * (fz + fx));  // 5 R + 5 W adjoint state, 5 coeff, psi/phi in the strips
+      else if (which == 2) b = box * 64.0;         // forward state R+W (40) + three gradient accumulators R+W (24)
+      else b = cells * (60.0 + 64.0 * (fz + fx));  // adjoint state R+W, 5 coefficients, psi/phi in the strips
       if (which == 1) b += (double)nb * 5 * g.f_len * 4.0;
       *alg_bytes = b;
     }
