@@ -27,9 +27,11 @@ def page(rep, name, extra=()):
 
 
 def short(n):
-    for k in ("fwd_step_kernel<(bool)1>", "fwd_step_kernel<(bool)0>", "rev_image_kernel", "adj_step_kernel"):
-        if k.split("<")[0] in n and (("<" not in k) or k.split("<")[1][:7] in n.replace(" ", "")):
-            return k.replace("(bool)1", "save_frames").replace("(bool)0", "no_frames")
+    if "fwd_step_kernel" in n:
+        return "fwd_step_kernel<save_frames>" if ("<1>" in n or "(bool)1" in n) else "fwd_step_kernel<no_frames>"
+    for k in ("rev_image_kernel", "adj_step_kernel"):
+        if k in n:
+            return k
     return n.split("(")[0][-40:]
 
 
