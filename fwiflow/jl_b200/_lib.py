@@ -11,7 +11,8 @@ import os
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libfwi_b200.so")
+# FWI_B200_LIB: developer override used to time kernel variants built under variants/ (always a CUDA build of csrc/)
+LIB_PATH = os.environ.get("FWI_B200_LIB") or os.path.join(HERE, "libfwi_b200.so")
 
 c_dp = ctypes.POINTER(ctypes.c_double)
 c_fp = ctypes.POINTER(ctypes.c_float)

@@ -27,6 +27,21 @@ namespace {
 #ifndef ADJ_NS
 #define ADJ_NS 2
 #endif
+#ifndef FWI_L2PF
+#define FWI_L2PF 1
+#endif
+// coefficient tile -> L2 two items ahead: 0 off, 1 every item, 2 only the item of shot 0.  Off in the reverse kernel:
+// its TMA queue already carries the adjoint / accumulator prefetches, and a third box per item delayed the ring loads
+// (C3, 8 shots: 448 -> 628 us).
+#ifndef REV_PF_MODEL
+#define REV_PF_MODEL 0
+#endif
+#ifndef ADJ_PF_MODEL
+#define ADJ_PF_MODEL 1
+#endif
+#ifndef ADJ_DB
+#define ADJ_DB 0   // 1: double-buffer the phi / injection tiles instead of a second block barrier per item
+#endif
 constexpr int RW_BYTES = 3 * WCOLS * VPITCH * 4;   // stress triple, rows z0-8.., columns x0-4..
 constexpr int RV_BYTES = 2 * SCOLS * SPITCH * 4;   // velocity pair, rows z0-4.., columns x0-2..
 constexpr int RSTAGE_BYTES = RW_BYTES + RV_BYTES;
@@ -48,7 +63,7 @@ rev_image_kernel(const __grid_constant__ BwdArgs a, int tz_first, int tx_first, 
   const Grid &g = a.g;
   const int tid = threadIdx.x;
   const int nitems = a.batch * ntiles;
-  const int stride = gridDim.x;
+  const int stride = gridDim.x;   // round-robin item order (see fwd_step_kernel)
   const int fin = a.cur_f ? S_FB : S_FA, fout = a.cur_f ? S_FA : S_FB;
   const int ain = a.cur_a ? S_AB : S_AA;
   const int P = g.P;
@@ -61,11 +76,7 @@ rev_image_kernel(const __grid_constant__ BwdArgs a, int tz_first, int tx_first, 
   __syncthreads();
 
   auto produce = [&](int item, int stage, int ds) {
-#ifdef REV_SHOT_SLOW
-    const int shot = item / ntiles, t = item - shot * ntiles;
-#else
-    const int t = item / a.batch, shot = item - t * a.batch;   // shot fastest: the shots of a tile share its coefficients in L2
-#endif
+    const int t = item / a.batch, shot = item - t * a.batch;   // shot fastest: the shots of a tile share its coefficients
     const int z0 = (tz_first + t % ntz) * TILE_Z, x0 = (tx_first + t / ntz) * TILE_X;
     const int sz = a.st.src_z[shot], sx = a.st.src_x[shot];
     TileDesc d;
@@ -84,6 +95,14 @@ rev_image_kernel(const __grid_constant__ BwdArgs a, int tz_first, int tx_first, 
     mbar_arrive_expect_tx(&full[stage], RSTAGE_BYTES);
     tma_load_3d(sb, &a.tm.sw, z0 - 8, x0 - 4 + XM, p0 + F_SZZ, &full[stage]);
     tma_load_3d(sb + RW_BYTES, &a.tm.vn, z0 - 4, x0 - 2 + XM, p0 + F_VZ, &full[stage]);
+#if REV_PF_MODEL
+    if (REV_PF_MODEL == 1 || shot == 0) tma_prefetch_3d(&a.tm.m5, z0 - 4, x0 - 2 + XM, M_LDT);
+#endif
+#if FWI_L2PF
+    // operands of the owner quads that are fetched with direct loads: adjoint fields and imaging accumulators -> L2
+    tma_prefetch_3d(&a.tm.o5, z0, x0 + XM, shot * S_COUNT + ain);
+    tma_prefetch_3d(&a.tm.g5, z0, x0 + XM, shot * G_COUNT);
+#endif
   };
   if (tid == PRODUCER_TID)
     for (int s = 0; s < NS; s++)
@@ -278,17 +297,18 @@ constexpr int AV_BYTES = 2 * SCOLS * SPITCH * 4;                 // adjoint velo
 constexpr int ASTAGE_BYTES = AS_PAD + AV_BYTES;
 constexpr int APHI_BYTES = 4 * SCOLS * SPITCH * 4;               // new phi of the region (tiles touching the CPML)
 constexpr int AINJ_BYTES = SCOLS * SPITCH * 4;                   // residual injection table
+constexpr int ANB = ADJ_DB ? 2 : 1;                               // buffers of the phi / injection tiles
 constexpr size_t ADJ_SMEM =
-    (size_t)ANS * ASTAGE_BYTES + 2 * AV_BYTES + APHI_BYTES + AINJ_BYTES + (ANS + 1) * sizeof(TileDesc) + ANS * 8 + 128;
+    (size_t)ANS * ASTAGE_BYTES + 2 * AV_BYTES + ANB * (APHI_BYTES + AINJ_BYTES) + (ANS + 1) * sizeof(TileDesc) + ANS * 8 + 128;
 static_assert(AV_BYTES % 128 == 0, "TMA destination alignment");
 
 __global__ void __launch_bounds__(NCOMPUTE, 1) adj_step_kernel(const __grid_constant__ BwdArgs a) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char *base = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
   float *s_v_base = reinterpret_cast<float *>(base + ANS * ASTAGE_BYTES);                         // [2][2][SCOLS][SPITCH]
-  float *s_phi = reinterpret_cast<float *>(base + ANS * ASTAGE_BYTES + 2 * AV_BYTES);             // [4][SCOLS][SPITCH]
-  float *s_inj = reinterpret_cast<float *>(base + ANS * ASTAGE_BYTES + 2 * AV_BYTES + APHI_BYTES);        // [SCOLS][SPITCH]
-  unsigned char *tail = base + ANS * ASTAGE_BYTES + 2 * AV_BYTES + APHI_BYTES + AINJ_BYTES;
+  float *s_phi_base = reinterpret_cast<float *>(base + ANS * ASTAGE_BYTES + 2 * AV_BYTES);                      // [ANB][4][SCOLS][SPITCH]
+  float *s_inj_base = reinterpret_cast<float *>(base + ANS * ASTAGE_BYTES + 2 * AV_BYTES + ANB * APHI_BYTES);   // [ANB][SCOLS][SPITCH]
+  unsigned char *tail = base + ANS * ASTAGE_BYTES + 2 * AV_BYTES + ANB * (APHI_BYTES + AINJ_BYTES);
   TileDesc *sdesc = reinterpret_cast<TileDesc *>(tail);                                          // [ANS + 1]
   uint64_t *full = reinterpret_cast<uint64_t *>(tail + (ANS + 1) * sizeof(TileDesc));
 
@@ -296,7 +316,7 @@ __global__ void __launch_bounds__(NCOMPUTE, 1) adj_step_kernel(const __grid_cons
   const int tid = threadIdx.x;
   const int ntiles = g.tiles_z * g.tiles_x;
   const int nitems = a.batch * ntiles;
-  const int stride = gridDim.x;
+  const int stride = gridDim.x;   // round-robin item order (see fwd_step_kernel)
   const int ain = a.cur_a ? S_AB : S_AA, aout = a.cur_a ? S_AA : S_AB;
   const int psi_i = a.cur_a ? S_PSI_B : S_PSI_A, psi_o = a.cur_a ? S_PSI_A : S_PSI_B;
   const int phi_i = a.cur_a ? S_PHI_B : S_PHI_A, phi_o = a.cur_a ? S_PHI_A : S_PHI_B;
@@ -312,7 +332,7 @@ __global__ void __launch_bounds__(NCOMPUTE, 1) adj_step_kernel(const __grid_cons
     for (int s = 0; s < ANS; s++) mbar_init(&full[s], 1);
     fence_barrier_init();
   }
-  for (int i = tid; i < AINJ_BYTES / 16; i += NCOMPUTE) reinterpret_cast<float4 *>(s_inj)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = tid; i < ANB * AINJ_BYTES / 16; i += NCOMPUTE) reinterpret_cast<float4 *>(s_inj_base)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncthreads();
 
   auto produce = [&](int item, int stage, int ds) {
@@ -336,6 +356,26 @@ __global__ void __launch_bounds__(NCOMPUTE, 1) adj_step_kernel(const __grid_cons
     mbar_arrive_expect_tx(&full[stage], AS_BYTES + AV_BYTES);
     tma_load_3d(sb, &a.tm.s3, z0 - 8, x0 - 3 + XM, p0 + F_SZZ, &full[stage]);
     tma_load_3d(sb + AS_PAD, &a.tm.vn, z0 - 4, x0 - 2 + XM, p0 + F_VZ, &full[stage]);
+#if ADJ_PF_MODEL
+    if (ADJ_PF_MODEL == 1 || shot == 0) tma_prefetch_3d(&a.tm.m5, z0 - 4, x0 - 2 + XM, M_LDT);
+#endif
+#if FWI_L2PF
+    if (fl & TF_PML) {  // CPML memory of the layers this tile touches -> L2
+      const int ps = shot * S_COUNT;
+      if ((z0 - 4 < zq_lo) || (z0 + TILE_Z + 3 > zq_hi)) {
+        tma_prefetch_3d(&a.tm.r1, z0 - 4, x0 - 2 + XM, ps + psi_i + PSI_VX_Z);
+        tma_prefetch_3d(&a.tm.r1, z0 - 4, x0 - 2 + XM, ps + psi_i + PSI_VZ_Z);
+        tma_prefetch_3d(&a.tm.r1, z0 - 4, x0 - 2 + XM, ps + phi_i + PHI_SXZ_Z);
+        tma_prefetch_3d(&a.tm.r1, z0 - 4, x0 - 2 + XM, ps + phi_i + PHI_SZZ_Z);
+      }
+      if ((x0 - 2 < xq_lo) || (x0 + TILE_X + 1 > xq_hi)) {
+        tma_prefetch_3d(&a.tm.r1, z0 - 4, x0 - 2 + XM, ps + psi_i + PSI_VX_X);
+        tma_prefetch_3d(&a.tm.r1, z0 - 4, x0 - 2 + XM, ps + psi_i + PSI_VZ_X);
+        tma_prefetch_3d(&a.tm.r1, z0 - 4, x0 - 2 + XM, ps + phi_i + PHI_SXX_X);
+        tma_prefetch_3d(&a.tm.r1, z0 - 4, x0 - 2 + XM, ps + phi_i + PHI_SXZ_X);
+      }
+    }
+#endif
   };
   if (tid == PRODUCER_TID)
     for (int s = 0; s < ANS; s++)
@@ -371,6 +411,8 @@ __global__ void __launch_bounds__(NCOMPUTE, 1) adj_step_kernel(const __grid_cons
     const float *sa = reinterpret_cast<const float *>(sb);              // [3][VCOLS][VPITCH]: adjoint szz sxx sxz
     const float *sva = reinterpret_cast<const float *>(sb + AS_PAD);    // [2][SCOLS][SPITCH]: adjoint vz vx
     float *s_v = s_v_base + nb * (AV_BYTES / 4);
+    float *s_phi = s_phi_base + (ADJ_DB ? nb : 0) * (APHI_BYTES / 4);
+    float *s_inj = s_inj_base + (ADJ_DB ? nb : 0) * (AINJ_BYTES / 4);
 
     // ---- adjoint velocity on 16 quads x 32 columns (el_velocity_adj.cu:56-100) ----
     const float *zz = sa + (c + 1) * VPITCH + 4 * (q + 1);
@@ -605,7 +647,7 @@ __global__ void __launch_bounds__(NCOMPUTE, 1) adj_step_kernel(const __grid_cons
       st4(ao + F_SXZ * pl, sxz);
     }
     // s_phi and the injection table are single-buffered: everyone is done with them before the next item writes
-    if (pml_tile || d.r1 > d.r0) __syncthreads();
+    if (!ADJ_DB && (pml_tile || d.r1 > d.r0)) __syncthreads();
     nb ^= 1;
     if (++ds == ANS + 1) ds = 0;
     if (++stage == ANS) { stage = 0; phase ^= 1; }

@@ -84,6 +84,13 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, i
       : "memory");
 }
 
+// one 3-D box HBM -> L2 only (no shared-memory destination, no completion to wait for): used two items ahead for the
+// per-shot operands that the compute threads fetch with direct 16-byte loads (CPML memory, adjoint fields, imaging
+// accumulators), so that those loads find their sectors in L2 instead of paying the HBM latency inside the item.
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap *map, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
 // ---- tile geometry shared by the persistent step kernels ----------------------------------------
 constexpr int SQ = (TILE_Z + 8) / 4;     // 16 quads per column of the "stress region": rows z0-4 .. z0+TILE_Z+3
 constexpr int SCOLS = TILE_X + 4;        // 32 columns of the stress region: x0-2 .. x0+TILE_X+1

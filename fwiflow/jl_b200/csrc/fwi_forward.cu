@@ -34,6 +34,12 @@ namespace {
 #ifndef FWD_NS
 #define FWD_NS 2
 #endif
+#ifndef FWI_L2PF
+#define FWI_L2PF 1
+#endif
+#ifndef FWD_PF_MODEL
+#define FWD_PF_MODEL 1   // coefficient tile -> L2 two items ahead: 0 off, 1 every item, 2 only the item of shot 0
+#endif
 constexpr int NS = FWD_NS;               // ring stages
 constexpr int NTHREADS_FWD = NCOMPUTE;
 constexpr int V_BYTES = 2 * VCOLS * VPITCH * 4;
@@ -56,11 +62,15 @@ __global__ void __launch_bounds__(NTHREADS_FWD, 1) fwd_step_kernel(const __grid_
   const int tid = threadIdx.x;
   const int ntiles = g.tiles_z * g.tiles_x;
   const int nitems = a.batch * ntiles;
+  // Items are dealt round-robin: at any instant the CTAs work on ~148 consecutive items = a few z-adjacent tiles of
+  // every shot, i.e. whole grid columns -- contiguous HBM pages.  (A contiguous chunk of items per CTA, which would keep
+  // a tile's coefficients in registers across shots, was measured 15-45 % SLOWER: the accesses scatter over HBM pages.)
   const int stride = gridDim.x;
   const int fin = a.cur ? S_FB : S_FA, fout = a.cur ? S_FA : S_FB;
   const int P = g.P;
   const long long pl = g.plane;
   const int zp_hi = g.nz - g.nPml - g.nPad - 1;  // z > zp_hi is bottom PML
+  const int pin_ = a.cur ? S_PSI_B : S_PSI_A;
 
   if (tid == 0) {
     for (int s = 0; s < NS; s++) mbar_init(&full[s], 1);
@@ -93,6 +103,26 @@ __global__ void __launch_bounds__(NTHREADS_FWD, 1) fwd_step_kernel(const __grid_
     mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);   // release: the descriptor is visible to whoever sees the phase flip
     tma_load_3d(sb, &a.tm.v, z0 - 8, x0 - 3 + XM, p0 + F_VZ, &full[stage]);
     tma_load_3d(sb + V_BYTES, &a.tm.s, z0 - 4, x0 - 2 + XM, p0 + F_SZZ, &full[stage]);
+#if FWD_PF_MODEL
+    if (FWD_PF_MODEL == 1 || shot == 0) tma_prefetch_3d(&a.tm.m5, z0 - 4, x0 - 2 + XM, M_LDT);
+#endif
+#if FWI_L2PF
+    if (fl & TF_PML) {  // CPML memory of the layers this tile touches: HBM -> L2 now, direct loads two items later
+      const int ps = shot * S_COUNT;
+      if ((z0 - 4 < g.nPml) || (z0 + TILE_Z + 3 > zp_hi)) {
+        tma_prefetch_3d(&a.tm.r1, z0 - 4, x0 - 2 + XM, ps + pin_ + PSI_VZ_Z);
+        tma_prefetch_3d(&a.tm.r1, z0 - 4, x0 - 2 + XM, ps + pin_ + PSI_VX_Z);
+        tma_prefetch_3d(&a.tm.r1, z0 - 4, x0 - 2 + XM, ps + S_PHI_A + PHI_SZZ_Z);
+        tma_prefetch_3d(&a.tm.r1, z0 - 4, x0 - 2 + XM, ps + S_PHI_A + PHI_SXZ_Z);
+      }
+      if ((x0 - 2 < g.nPml) || (x0 + TILE_X + 1 > g.nx - g.nPml - 1)) {
+        tma_prefetch_3d(&a.tm.r1, z0 - 4, x0 - 2 + XM, ps + pin_ + PSI_VX_X);
+        tma_prefetch_3d(&a.tm.r1, z0 - 4, x0 - 2 + XM, ps + pin_ + PSI_VZ_X);
+        tma_prefetch_3d(&a.tm.r1, z0 - 4, x0 - 2 + XM, ps + S_PHI_A + PHI_SXZ_X);
+        tma_prefetch_3d(&a.tm.r1, z0 - 4, x0 - 2 + XM, ps + S_PHI_A + PHI_SXX_X);
+      }
+    }
+#endif
   };
   if (tid == PRODUCER_TID)
     for (int s = 0; s < NS; s++)
@@ -239,10 +269,15 @@ __global__ void __launch_bounds__(NTHREADS_FWD, 1) fwd_step_kernel(const __grid_
       fx1 = ld4(sq + (S_PHI_A + PHI_SXZ_X) * pl);
       fx2 = ld4(sq + (S_PHI_A + PHI_SXX_X) * pl);
     }
+    // the next item's stress coefficients: requested now, used after the barrier.  Its tile origin is recomputed here
+    // rather than read from the producer's descriptor, which is written after the previous block barrier and is
+    // therefore only safe to read on the far side of this one.
     const bool more = item + stride < nitems;
     const float *mq_next = a.m.ldt;
     if (more) {
-      mq_next = coef_ptr(sdesc[ds == NS ? 0 : ds + 1]);
+      const int tn = (item + stride) / a.batch;
+      const int gzn = (tn % g.tiles_z) * TILE_Z - 4 + 4 * q, gxn = min((tn / g.tiles_z) * TILE_X - 2 + c, gx_max);
+      mq_next = a.m.ldt + ((long long)gxn * P + gzn);
       ldt = ld4(mq_next); l2mdt = ld4(mq_next + pl); amudt = ld4(mq_next + 2 * pl);
     }
     __syncthreads();  // s_new is complete; nobody reads ring slot `stage` any more
@@ -360,13 +395,17 @@ void encode_one(CUtensorMap *m, const Grid &g, float *plane0, long long nplanes,
 
 }  // namespace
 
-void encode_tma_maps(const Grid &g, float *state, long long nplanes, float *model, TmaMaps *out) {
+void encode_tma_maps(const Grid &g, float *state, long long nplanes, float *gacc, long long gacc_planes, float *model,
+                     TmaMaps *out) {
   encode_one(&out->v, g, state, nplanes, VPITCH, VCOLS, 2);
   encode_one(&out->s, g, state, nplanes, SPITCH, SCOLS, 3);
   encode_one(&out->sw, g, state, nplanes, TILE_Z + 16, TILE_X + 8, 3);
   encode_one(&out->vn, g, state, nplanes, TILE_Z + 8, TILE_X + 4, 2);
   encode_one(&out->s3, g, state, nplanes, TILE_Z + 16, TILE_X + 6, 3);
-  (void)model;
+  encode_one(&out->o5, g, state, nplanes, TILE_Z, TILE_X, 5);
+  encode_one(&out->r1, g, state, nplanes, SPITCH, SCOLS, 1);
+  if (gacc) encode_one(&out->g5, g, gacc, gacc_planes, TILE_Z, TILE_X, 5);
+  encode_one(&out->m5, g, model, M_COUNT, SPITCH, SCOLS, 5);
 }
 
 size_t forward_smem_bytes() { return FWD_SMEM; }

@@ -78,6 +78,11 @@ struct alignas(64) TmaMaps {
   CUtensorMap sw;   // state planes, box (TILE_Z+16, TILE_X+8, 3): stress triple with halo 8 / 4 (reverse step)
   CUtensorMap vn;   // state planes, box (TILE_Z+8,  TILE_X+4, 2): velocity pair with halo 4 / 2 (reverse / adjoint step)
   CUtensorMap s3;   // state planes, box (TILE_Z+16, TILE_X+6, 3): stress triple with halo 8 / 3 (adjoint step)
+  // L2 prefetch boxes (cp.async.bulk.prefetch.tensor): operands the threads read with direct loads
+  CUtensorMap o5;   // state planes, box (TILE_Z, TILE_X, 5): the five adjoint fields of the owner tile (reverse step)
+  CUtensorMap r1;   // state planes, box (TILE_Z+8, TILE_X+4, 1): one CPML memory plane of the tile region
+  CUtensorMap g5;   // imaging accumulators [batch][G_COUNT][plane], box (TILE_Z, TILE_X, 5)
+  CUtensorMap m5;   // model planes, box (TILE_Z+8, TILE_X+4, 5): the five dt-scaled coefficient planes of the tile region
 };
 
 struct Profiles {
@@ -161,7 +166,9 @@ void launch_finalize(const Grid &g, const float *gacc, int nslots, const float *
                      float *result, cudaStream_t s);
 
 // host: encode the TMA descriptors for a state buffer of `nplanes` planes and the model buffer
-void encode_tma_maps(const Grid &g, float *state, long long nplanes, float *model, TmaMaps *out);
+// `gacc` may be null (no gradient): its descriptor is then left untouched
+void encode_tma_maps(const Grid &g, float *state, long long nplanes, float *gacc, long long gacc_planes, float *model,
+                     TmaMaps *out);
 size_t forward_smem_bytes();
 size_t reverse_smem_bytes();
 size_t adjoint_smem_bytes();

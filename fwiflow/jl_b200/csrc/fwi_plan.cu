@@ -80,7 +80,7 @@ struct fwi_b200_plan {
   int partial_per_shot = 0;
   size_t trace_stride = 0;  // max_nrec * nSteps
   TmaMaps tm{};             // TMA descriptors of the state / model buffers (re-encoded when `state` moves)
-  float *tm_state = nullptr;
+  float *tm_state = nullptr, *tm_gacc = nullptr;
   size_t tm_state_n = 0;
 
   float *mplane(int k) { return model.p + (long long)k * g.plane; }
@@ -239,10 +239,13 @@ void choose_batch(fwi_b200_plan &pl, int max_batch) {
 void alloc_run_buffers(fwi_b200_plan &pl, int calc_id) {
   const Grid &g = pl.g;
   pl.state.alloc((size_t)pl.batch * S_COUNT * g.plane);
-  if (pl.tm_state != pl.state.p || pl.tm_state_n != pl.state.n) {
-    encode_tma_maps(g, pl.state.p, (long long)pl.batch * S_COUNT, pl.model.p, &pl.tm);
+  if (calc_id == 1) pl.gacc.alloc((size_t)pl.batch * G_COUNT * g.plane);
+  if (pl.tm_state != pl.state.p || pl.tm_state_n != pl.state.n || (calc_id == 1 && pl.tm_gacc != pl.gacc.p)) {
+    encode_tma_maps(g, pl.state.p, (long long)pl.batch * S_COUNT, calc_id == 1 ? pl.gacc.p : nullptr,
+                    (long long)pl.batch * G_COUNT, pl.model.p, &pl.tm);
     pl.tm_state = pl.state.p;
     pl.tm_state_n = pl.state.n;
+    if (calc_id == 1) pl.tm_gacc = pl.gacc.p;
   }
   pl.syn_tr.alloc((size_t)pl.batch * g.nSteps * pl.nrp);
   if (calc_id != 2) {
@@ -252,7 +255,6 @@ void alloc_run_buffers(fwi_b200_plan &pl, int calc_id) {
     pl.partial.alloc((size_t)pl.batch * nb);
   }
   if (calc_id == 1) {
-    pl.gacc.alloc((size_t)pl.batch * G_COUNT * g.plane);
     pl.frames.alloc((size_t)pl.batch * g.nSteps * 5 * g.f_len);
   }
   if (calc_id == 2 || pl.para.save_scratch) pl.syn_rt.alloc((size_t)pl.group * pl.trace_stride);

@@ -12,8 +12,8 @@ c = synthetic.case_c2(nshots=nshots, nSteps=64) if case == "c2" else synthetic.c
 para = c.write_files(tempfile.mkdtemp(prefix="kt_"))
 ids = np.arange(nshots, dtype=np.int32)
 p = ops.Plan(para, ids)
-p.set_stf(c.stf); p.set_model(*c.moduli("true")); p.run(2); p.write_obs_files()
-p.set_model(*c.moduli("init")); p.load_obs_files(); p.run(1)
+p.set_stf(c.stf); p.set_model(*c.moduli("true")); p.run(2); print('obs ok', flush=True); p.write_obs_files()
+p.set_model(*c.moduli("init")); p.load_obs_files(); p.run(1); print('grad ok', flush=True)
 peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
 names = {0: "fwd", 1: "fwd+save", 2: "rev_image", 3: "adj"}
 for w in names:
