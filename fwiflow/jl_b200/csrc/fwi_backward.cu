@@ -69,13 +69,14 @@ rev_image_kernel(const __grid_constant__ BwdArgs a, int tz_first, int tx_first, 
   const int P = g.P;
   const long long pl = g.plane;
 
+  pdl_launch_dependents();
   if (tid == 0) {
     for (int s = 0; s < NS; s++) mbar_init(&full[s], 1);
     fence_barrier_init();
   }
   __syncthreads();
 
-  auto produce = [&](int item, int stage, int ds) {
+  auto produce = [&](int item, int stage, int ds, bool first = false) {
     const int t = item / a.batch, shot = item - t * a.batch;   // shot fastest: the shots of a tile share its coefficients
     const int z0 = (tz_first + t % ntz) * TILE_Z, x0 = (tx_first + t / ntz) * TILE_X;
     const int sz = a.st.src_z[shot], sx = a.st.src_x[shot];
@@ -92,6 +93,7 @@ rev_image_kernel(const __grid_constant__ BwdArgs a, int tz_first, int tx_first, 
     sdesc[ds] = d;
     unsigned char *sb = base + stage * RSTAGE_BYTES;
     const int p0 = shot * S_COUNT + fin;
+    if (first) pdl_wait();   // everything above reads static tables only
     mbar_arrive_expect_tx(&full[stage], RSTAGE_BYTES);
     tma_load_3d(sb, &a.tm.sw, z0 - 8, x0 - 4 + XM, p0 + F_SZZ, &full[stage]);
     tma_load_3d(sb + RW_BYTES, &a.tm.vn, z0 - 4, x0 - 2 + XM, p0 + F_VZ, &full[stage]);
@@ -106,8 +108,9 @@ rev_image_kernel(const __grid_constant__ BwdArgs a, int tz_first, int tx_first, 
   };
   if (tid == PRODUCER_TID)
     for (int s = 0; s < NS; s++)
-      if (blockIdx.x + s * stride < nitems) produce(blockIdx.x + s * stride, s, s);
+      if (blockIdx.x + s * stride < nitems) produce(blockIdx.x + s * stride, s, s, s == 0);
   __syncthreads();   // the first descriptors are visible: per-item global loads may start before the TMA data lands
+  pdl_wait();
 
   const float dt = g.dt;
   const float kz1 = C1 * g.rdz, kz2 = C2 * g.rdz, kx1 = C1 * g.rdx, kx2 = C2 * g.rdx;
@@ -153,8 +156,8 @@ rev_image_kernel(const __grid_constant__ BwdArgs a, int tz_first, int tx_first, 
     const F4 byadt = ld4(mq + 3 * pl), bybdt = ld4(mq + 4 * pl);
     F4 vza = zero4(), vxa = zero4();
     if (owner) {
-      vza = ld4(sq + (ain + F_VZ) * pl);
-      vxa = ld4(sq + (ain + F_VX) * pl);
+      vza = ld4s(sq + (ain + F_VZ) * pl);
+      vxa = ld4s(sq + (ain + F_VX) * pl);
     }
     mbar_wait(&full[stage], phase);
 
@@ -209,9 +212,9 @@ rev_image_kernel(const __grid_constant__ BwdArgs a, int tz_first, int tx_first, 
     F4 ldt, l2mdt, amudt, za, xa, xza, gl, gm, gs, accA, accB;
     if (wr) {
       ldt = ld4(mq); l2mdt = ld4(mq + pl); amudt = ld4(mq + 2 * pl);
-      za = ld4(sq + (ain + F_SZZ) * pl); xa = ld4(sq + (ain + F_SXX) * pl); xza = ld4(sq + (ain + F_SXZ) * pl);
-      gl = ld4(acc + G_LAM * pl); gm = ld4(acc + G_MU * pl); gs = ld4(acc + G_MUS * pl);
-      accA = ld4(acc + G_RHO_A * pl); accB = ld4(acc + G_RHO_B * pl);
+      za = ld4s(sq + (ain + F_SZZ) * pl); xa = ld4s(sq + (ain + F_SXX) * pl); xza = ld4s(sq + (ain + F_SXZ) * pl);
+      gl = ld4s(acc + G_LAM * pl); gm = ld4s(acc + G_MU * pl); gs = ld4s(acc + G_MUS * pl);
+      accA = ld4s(acc + G_RHO_A * pl); accB = ld4s(acc + G_RHO_B * pl);
     }
     __syncthreads();  // s_v is complete; nobody reads ring slot `stage` any more
     if (tid == PRODUCER_TID && item + NS * stride < nitems) produce(item + NS * stride, stage, ds == 0 ? NS : ds - 1);
@@ -328,6 +331,7 @@ __global__ void __launch_bounds__(NCOMPUTE, 1) adj_step_kernel(const __grid_cons
   const int zq_lo = g.nPml + 2, zq_hi = g.nz - g.nPad - g.nPml - 3;
   const int xq_lo = g.nPml + 2, xq_hi = g.nx - g.nPml - 3;
 
+  pdl_launch_dependents();
   if (tid == 0) {
     for (int s = 0; s < ANS; s++) mbar_init(&full[s], 1);
     fence_barrier_init();
@@ -335,7 +339,7 @@ __global__ void __launch_bounds__(NCOMPUTE, 1) adj_step_kernel(const __grid_cons
   for (int i = tid; i < ANB * AINJ_BYTES / 16; i += NCOMPUTE) reinterpret_cast<float4 *>(s_inj_base)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncthreads();
 
-  auto produce = [&](int item, int stage, int ds) {
+  auto produce = [&](int item, int stage, int ds, bool first = false) {
     const int tile = item / a.batch, shot = item - tile * a.batch;   // shot fastest
     const int z0 = (tile % g.tiles_z) * TILE_Z, x0 = (tile / g.tiles_z) * TILE_X;
     const int sz = a.st.src_z[shot], sx = a.st.src_x[shot];
@@ -353,6 +357,7 @@ __global__ void __launch_bounds__(NCOMPUTE, 1) adj_step_kernel(const __grid_cons
     sdesc[ds] = d;
     unsigned char *sb = base + stage * ASTAGE_BYTES;
     const int p0 = shot * S_COUNT + ain;
+    if (first) pdl_wait();   // everything above reads static tables only
     mbar_arrive_expect_tx(&full[stage], AS_BYTES + AV_BYTES);
     tma_load_3d(sb, &a.tm.s3, z0 - 8, x0 - 3 + XM, p0 + F_SZZ, &full[stage]);
     tma_load_3d(sb + AS_PAD, &a.tm.vn, z0 - 4, x0 - 2 + XM, p0 + F_VZ, &full[stage]);
@@ -379,8 +384,9 @@ __global__ void __launch_bounds__(NCOMPUTE, 1) adj_step_kernel(const __grid_cons
   };
   if (tid == PRODUCER_TID)
     for (int s = 0; s < ANS; s++)
-      if (blockIdx.x + s * stride < nitems) produce(blockIdx.x + s * stride, s, s);
+      if (blockIdx.x + s * stride < nitems) produce(blockIdx.x + s * stride, s, s, s == 0);
   __syncthreads();   // the first descriptors are visible
+  pdl_wait();
 
   const float dt = g.dt;
   // adjoint-kernel spelling of the differences: (-c1 (..) + c2 (..)) / h  (el_stress_adj.cu:54-61)
@@ -507,8 +513,8 @@ __global__ void __launch_bounds__(NCOMPUTE, 1) adj_step_kernel(const __grid_cons
         // phi memory of the quad, CPML cells only (el_velocity_adj.cu:74-79,95-100); buoyancies are 0 on inactive cells
         if (xp) {
           const float bx = xpf[PR_B * nxp], bxh = xpf[PR_BH * nxp];
-          f_sxx_x = ld4(sq + (phi_i + PHI_SXX_X) * pl);
-          f_sxz_x = ld4(sq + (phi_i + PHI_SXZ_X) * pl);
+          f_sxx_x = ld4s(sq + (phi_i + PHI_SXX_X) * pl);
+          f_sxz_x = ld4s(sq + (phi_i + PHI_SXZ_X) * pl);
 #pragma unroll
           for (int kk = 0; kk < 4; kk++) {
             f_sxx_x.v[kk] = fmaf(bxh, f_sxx_x.v[kk], bybdt.v[kk] * vx.v[kk]);
@@ -521,8 +527,8 @@ __global__ void __launch_bounds__(NCOMPUTE, 1) adj_step_kernel(const __grid_cons
         }
         if (zq_pml) {
           const F4 bz = ld4(zprof + PR_B * P + gz), bzh = ld4(zprof + PR_BH * P + gz);
-          f_sxz_z = ld4(sq + (phi_i + PHI_SXZ_Z) * pl);
-          f_szz_z = ld4(sq + (phi_i + PHI_SZZ_Z) * pl);
+          f_sxz_z = ld4s(sq + (phi_i + PHI_SXZ_Z) * pl);
+          f_szz_z = ld4s(sq + (phi_i + PHI_SZZ_Z) * pl);
 #pragma unroll
           for (int kk = 0; kk < 4; kk++) {
             const int z = gz + kk;
@@ -668,7 +674,7 @@ void configure_backward_kernels() {
 void launch_adjoint_step(const BwdArgs &a, cudaStream_t s) {
   const int nitems = a.batch * a.g.tiles_z * a.g.tiles_x;
   const int blocks = nitems < sm_count() ? nitems : sm_count();
-  adj_step_kernel<<<blocks, NCOMPUTE, ADJ_SMEM, s>>>(a);
+  launch_step(adj_step_kernel, blocks, NCOMPUTE, ADJ_SMEM, s, a);
 }
 
 void launch_reverse_imaging(const BwdArgs &a, cudaStream_t s) {
@@ -678,7 +684,7 @@ void launch_reverse_imaging(const BwdArgs &a, cudaStream_t s) {
   const int ntz = tz1 - tz0 + 1, ntx = tx1 - tx0 + 1;
   const int nitems = a.batch * ntz * ntx;
   const int blocks = nitems < sm_count() ? nitems : sm_count();
-  rev_image_kernel<<<blocks, NCOMPUTE, REV_SMEM, s>>>(a, tz0, tx0, ntz, ntz * ntx);
+  launch_step(rev_image_kernel, blocks, NCOMPUTE, REV_SMEM, s, a, tz0, tx0, ntz, ntz * ntx);
 }
 
 }  // namespace fwi

@@ -5,8 +5,16 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <utility>
 
 #include "fwi_kernels.cuh"
+
+#ifndef FWI_PDL
+#define FWI_PDL 1   // programmatic dependent launch: a step kernel's prologue overlaps the tail of the previous launch
+#endif
+#ifndef FWI_STREAM_LD
+#define FWI_STREAM_LD 0   // measured: L1::no_allocate loads are slower here (rev C3 447 -> 590 us)
+#endif
 
 namespace fwi {
 namespace dev {
@@ -21,6 +29,18 @@ struct F4 {
 __device__ __forceinline__ F4 ld4(const float *p) {
   const float4 t = *reinterpret_cast<const float4 *>(p);
   return F4{{t.x, t.y, t.z, t.w}};
+}
+// streaming 16-byte load: the line is not kept in L1 (per-shot operands that are read once per launch), which leaves the
+// L1 data array to the loads that do have reuse (coefficients, CPML memory read with x-neighbours)
+__device__ __forceinline__ F4 ld4s(const float *p) {
+#if FWI_STREAM_LD
+  F4 r;
+  asm volatile("ld.global.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]) : "l"(p));
+  return r;
+#else
+  return ld4(p);
+#endif
 }
 __device__ __forceinline__ void st4(float *p, const F4 &a) {
   *reinterpret_cast<float4 *>(p) = make_float4(a.v[0], a.v[1], a.v[2], a.v[3]);
@@ -91,6 +111,21 @@ __device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap *map, int c0, 
   asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 
+// Programmatic dependent launch (the step kernels are launched with cudaLaunchAttributeProgrammaticStreamSerialization):
+// a CTA of the next launch becomes resident as soon as an SM is free and runs its prologue -- barrier init, tile
+// descriptors, static coefficient loads -- while the previous launch drains; nothing written by the previous launch
+// may be touched before pdl_wait().
+__device__ __forceinline__ void pdl_launch_dependents() {
+#if FWI_PDL
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdl_wait() {
+#if FWI_PDL
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+
 // ---- tile geometry shared by the persistent step kernels ----------------------------------------
 constexpr int SQ = (TILE_Z + 8) / 4;     // 16 quads per column of the "stress region": rows z0-4 .. z0+TILE_Z+3
 constexpr int SCOLS = TILE_X + 4;        // 32 columns of the stress region: x0-2 .. x0+TILE_X+1
@@ -143,5 +178,21 @@ __device__ __forceinline__ bool tile_touches_frame(const Grid &g, int z0, int x0
 }  // namespace dev
 
 int sm_count();  // fwi_forward.cu
+
+// <<<blocks, threads, smem, stream>>> with the programmatic-stream-serialization attribute (see pdl_wait())
+template <typename... KArgs, typename... Args>
+inline void launch_step(void (*kernel)(KArgs...), int blocks, int threads, size_t smem, cudaStream_t s, Args &&...args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)blocks);
+  cfg.blockDim = dim3((unsigned)threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = FWI_PDL;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 }  // namespace fwi

@@ -72,6 +72,7 @@ __global__ void __launch_bounds__(NTHREADS_FWD, 1) fwd_step_kernel(const __grid_
   const int zp_hi = g.nz - g.nPml - g.nPad - 1;  // z > zp_hi is bottom PML
   const int pin_ = a.cur ? S_PSI_B : S_PSI_A;
 
+  pdl_launch_dependents();
   if (tid == 0) {
     for (int s = 0; s < NS; s++) mbar_init(&full[s], 1);
     fence_barrier_init();
@@ -80,7 +81,7 @@ __global__ void __launch_bounds__(NTHREADS_FWD, 1) fwd_step_kernel(const __grid_
 
   // producer step: descriptor (slot `ds` of NS + 1, so that it never overwrites the one in use) + TMA requests of
   // one item into ring slot `stage`
-  auto produce = [&](int item, int stage, int ds) {
+  auto produce = [&](int item, int stage, int ds, bool first = false) {
     const int tile = item / a.batch, shot = item - tile * a.batch;   // shot fastest: the shots of a tile share its coefficients in L2
     const int tz = tile % g.tiles_z, tx = tile / g.tiles_z;
     const int z0 = tz * TILE_Z, x0 = tx * TILE_X;
@@ -100,6 +101,7 @@ __global__ void __launch_bounds__(NTHREADS_FWD, 1) fwd_step_kernel(const __grid_
     sdesc[ds] = d;
     unsigned char *sb = base + stage * STAGE_BYTES;
     const int p0 = shot * S_COUNT + fin;
+    if (first) pdl_wait();   // everything above reads static tables only; the wavefields belong to the previous launch
     mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);   // release: the descriptor is visible to whoever sees the phase flip
     tma_load_3d(sb, &a.tm.v, z0 - 8, x0 - 3 + XM, p0 + F_VZ, &full[stage]);
     tma_load_3d(sb + V_BYTES, &a.tm.s, z0 - 4, x0 - 2 + XM, p0 + F_SZZ, &full[stage]);
@@ -126,7 +128,7 @@ __global__ void __launch_bounds__(NTHREADS_FWD, 1) fwd_step_kernel(const __grid_
   };
   if (tid == PRODUCER_TID)
     for (int s = 0; s < NS; s++)
-      if (blockIdx.x + s * stride < nitems) produce(blockIdx.x + s * stride, s, s);
+      if (blockIdx.x + s * stride < nitems) produce(blockIdx.x + s * stride, s, s, s == 0);
 
   const float dt = g.dt;
   const float kz1 = C1 * g.rdz, kz2 = C2 * g.rdz, kx1 = C1 * g.rdx, kx2 = C2 * g.rdx;
@@ -151,6 +153,7 @@ __global__ void __launch_bounds__(NTHREADS_FWD, 1) fwd_step_kernel(const __grid_
     ldt = ld4(mq); l2mdt = ld4(mq + pl); amudt = ld4(mq + 2 * pl); byadt = ld4(mq + 3 * pl); bybdt = ld4(mq + 4 * pl);
   }
 
+  pdl_wait();
   int stage = 0, phase = 0, nb = 0, ds = 0;
   for (int item = blockIdx.x; item < nitems; item += stride) {
     mbar_wait(&full[stage], phase);
@@ -165,12 +168,12 @@ __global__ void __launch_bounds__(NTHREADS_FWD, 1) fwd_step_kernel(const __grid_
     const bool xq_v = pml && (gx < g.nPml || gx > g.nx - g.nPml);       // velocity flavour  (el_velocity.cu:56)
     F4 pz1, pz2, px1, px2;
     if (zq) {
-      pz1 = ld4(sq + (pin + PSI_VZ_Z) * pl);
-      pz2 = ld4(sq + (pin + PSI_VX_Z) * pl);
+      pz1 = ld4s(sq + (pin + PSI_VZ_Z) * pl);
+      pz2 = ld4s(sq + (pin + PSI_VX_Z) * pl);
     }
     if (xq_s) {
-      px1 = ld4(sq + (pin + PSI_VX_X) * pl);
-      px2 = ld4(sq + (pin + PSI_VZ_X) * pl);
+      px1 = ld4s(sq + (pin + PSI_VX_X) * pl);
+      px2 = ld4s(sq + (pin + PSI_VZ_X) * pl);
     }
 
     const unsigned char *sb = base + stage * STAGE_BYTES;
@@ -262,12 +265,12 @@ __global__ void __launch_bounds__(NTHREADS_FWD, 1) fwd_step_kernel(const __grid_
     // CPML memory of the velocity half-step and the NEXT item's stress coefficients: requested now, used after the barrier
     F4 fz1, fz2, fx1, fx2;
     if (zq && owner) {
-      fz1 = ld4(sq + (S_PHI_A + PHI_SZZ_Z) * pl);
-      fz2 = ld4(sq + (S_PHI_A + PHI_SXZ_Z) * pl);
+      fz1 = ld4s(sq + (S_PHI_A + PHI_SZZ_Z) * pl);
+      fz2 = ld4s(sq + (S_PHI_A + PHI_SXZ_Z) * pl);
     }
     if (xq_v && owner) {
-      fx1 = ld4(sq + (S_PHI_A + PHI_SXZ_X) * pl);
-      fx2 = ld4(sq + (S_PHI_A + PHI_SXX_X) * pl);
+      fx1 = ld4s(sq + (S_PHI_A + PHI_SXZ_X) * pl);
+      fx2 = ld4s(sq + (S_PHI_A + PHI_SXX_X) * pl);
     }
     // the next item's stress coefficients: requested now, used after the barrier.  Its tile origin is recomputed here
     // rather than read from the producer's descriptor, which is written after the previous block barrier and is
@@ -419,9 +422,9 @@ void launch_forward_step(const FwdArgs &a, bool save_frames, cudaStream_t s) {
   const int nitems = a.batch * a.g.tiles_z * a.g.tiles_x;
   const int blocks = nitems < sm_count() ? nitems : sm_count();
   if (save_frames)
-    fwd_step_kernel<true><<<blocks, NTHREADS_FWD, FWD_SMEM, s>>>(a);
+    launch_step(fwd_step_kernel<true>, blocks, NTHREADS_FWD, FWD_SMEM, s, a);
   else
-    fwd_step_kernel<false><<<blocks, NTHREADS_FWD, FWD_SMEM, s>>>(a);
+    launch_step(fwd_step_kernel<false>, blocks, NTHREADS_FWD, FWD_SMEM, s, a);
 }
 
 }  // namespace fwi
