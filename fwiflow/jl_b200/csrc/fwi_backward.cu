@@ -39,6 +39,9 @@ namespace {
 #ifndef ADJ_PF_MODEL
 #define ADJ_PF_MODEL 1
 #endif
+#ifndef ADJ_SPLIT
+#define ADJ_SPLIT 1   // single-buffered phi / injection tiles are handed over with an arrive / wait pair instead of a block barrier
+#endif
 #ifndef ADJ_DB
 #define ADJ_DB 0   // 1: double-buffer the phi / injection tiles instead of a second block barrier per item
 #endif
@@ -302,7 +305,7 @@ constexpr int APHI_BYTES = 4 * SCOLS * SPITCH * 4;               // new phi of t
 constexpr int AINJ_BYTES = SCOLS * SPITCH * 4;                   // residual injection table
 constexpr int ANB = ADJ_DB ? 2 : 1;                               // buffers of the phi / injection tiles
 constexpr size_t ADJ_SMEM =
-    (size_t)ANS * ASTAGE_BYTES + 2 * AV_BYTES + ANB * (APHI_BYTES + AINJ_BYTES) + (ANS + 1) * sizeof(TileDesc) + ANS * 8 + 128;
+    (size_t)ANS * ASTAGE_BYTES + 2 * AV_BYTES + ANB * (APHI_BYTES + AINJ_BYTES) + (ANS + 1) * sizeof(TileDesc) + (ANS + 1) * 8 + 128;
 static_assert(AV_BYTES % 128 == 0, "TMA destination alignment");
 
 __global__ void __launch_bounds__(NCOMPUTE, 1) adj_step_kernel(const __grid_constant__ BwdArgs a) {
@@ -334,6 +337,7 @@ __global__ void __launch_bounds__(NCOMPUTE, 1) adj_step_kernel(const __grid_cons
   pdl_launch_dependents();
   if (tid == 0) {
     for (int s = 0; s < ANS; s++) mbar_init(&full[s], 1);
+    mbar_init(&full[ANS], NCOMPUTE / 32);   // "done with the phi / injection tiles of the previous item": one arrival per warp
     fence_barrier_init();
   }
   for (int i = tid; i < ANB * AINJ_BYTES / 16; i += NCOMPUTE) reinterpret_cast<float4 *>(s_inj_base)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -398,7 +402,7 @@ __global__ void __launch_bounds__(NCOMPUTE, 1) adj_step_kernel(const __grid_cons
   const int cm2 = (c > 0 ? 2 : 1) * VPITCH, cp2 = (c < SCOLS - 1 ? 2 : 1) * VPITCH;   // keep halo-column reads in the tile
   const float *zprof = a.pr.z;
 
-  int stage = 0, phase = 0, nb = 0, ds = 0;
+  int stage = 0, phase = 0, nb = 0, ds = 0, kdone = 0;
   for (int item = blockIdx.x; item < nitems; item += stride) {
     const TileDesc d = sdesc[ds];   // written by the producer >= 1 block barrier ago
     const int gz = d.z0 - 4 + 4 * q, gx = d.x0 - 2 + c;
@@ -443,6 +447,9 @@ __global__ void __launch_bounds__(NCOMPUTE, 1) adj_step_kernel(const __grid_cons
         if (kk == ks) { s1 = zzB.v[kk]; s2 = xxB.v[kk]; }
       a.stf_grad[d.shot * g.nSteps + a.it] = (float)(-((double)s1 + 3.0 * (double)s2) * (double)dt);
     }
+    // the phi / injection tiles are single-buffered: every warp has finished the stress half of the previous item
+    // (arrive at the end of an item, wait here: the skew between warps is absorbed by the work above)
+    if (ADJ_SPLIT && !ADJ_DB && kdone > 0) mbar_wait(&full[ANS], (kdone - 1) & 1);
     // residual injection at time index `it` (utilities.cu:569-580): receivers of this tile add into the table
     for (int r = d.r0 + tid; r < d.r1; r += NCOMPUTE) {
       const int loc = a.st.rec_loc[d.shot * a.st.nrp + r];
@@ -653,7 +660,13 @@ __global__ void __launch_bounds__(NCOMPUTE, 1) adj_step_kernel(const __grid_cons
       st4(ao + F_SXZ * pl, sxz);
     }
     // s_phi and the injection table are single-buffered: everyone is done with them before the next item writes
-    if (!ADJ_DB && (pml_tile || d.r1 > d.r0)) __syncthreads();
+    if (ADJ_SPLIT && !ADJ_DB) {
+      __syncwarp();
+      if ((tid & 31) == 0) mbar_arrive(&full[ANS]);
+      kdone++;
+    } else if (!ADJ_DB && (pml_tile || d.r1 > d.r0)) {
+      __syncthreads();
+    }
     nb ^= 1;
     if (++ds == ANS + 1) ds = 0;
     if (++stage == ANS) { stage = 0; phase ^= 1; }
