@@ -715,11 +715,11 @@ namespace {
 struct CacheEntry {
   int gpu;
   std::string key;
-  std::unique_ptr<fwi_b200_plan> plan;
+  std::shared_ptr<fwi_b200_plan> plan;   // shared: a call in flight keeps its plan alive if another thread evicts the entry
 };
 std::mutex g_cache_mu;
 std::list<CacheEntry> g_cache;
-constexpr size_t kCacheMax = 4;
+constexpr size_t kCacheMax = 8;   // baseline + 5 monitor surveys of a time-lapse inversion stay resident
 
 std::string cache_key(const char *para_fname, const Para &p, const std::string &survey_text, int group, const int *ids) {
   std::string k = std::string(para_fname) + "\n" + p.text + "\n" + survey_text + "\n";
@@ -727,7 +727,7 @@ std::string cache_key(const char *para_fname, const Para &p, const std::string &
   return k;
 }
 
-fwi_b200_plan *cached_plan(const char *para_fname, int gpu, int group, const int *ids) {
+std::shared_ptr<fwi_b200_plan> cached_plan(const char *para_fname, int gpu, int group, const int *ids) {
   Para p = read_para(para_fname);
   std::string survey_text;
   {
@@ -743,14 +743,14 @@ fwi_b200_plan *cached_plan(const char *para_fname, int gpu, int group, const int
   for (auto it = g_cache.begin(); it != g_cache.end(); ++it)
     if (it->gpu == gpu && it->key == key) {
       g_cache.splice(g_cache.begin(), g_cache, it);
-      return g_cache.front().plan.get();
+      return g_cache.front().plan;
     }
   while (g_cache.size() >= kCacheMax) g_cache.pop_back();
   fwi_b200_plan *raw = nullptr;
   int rc = fwi_b200_plan_create(&raw, para_fname, gpu, group, ids, 0);
   if (rc != FWI_B200_OK) throw Error(rc, last_error_cstr());
-  g_cache.push_front(CacheEntry{gpu, key, std::unique_ptr<fwi_b200_plan>(raw)});
-  return raw;
+  g_cache.push_front(CacheEntry{gpu, key, std::shared_ptr<fwi_b200_plan>(raw)});
+  return g_cache.front().plan;
 }
 
 void check(int rc) {
@@ -766,7 +766,8 @@ int host_call(double *misfit, double *gl, double *gm, double *gd, double *gs, co
       throw Error(FWI_B200_ERR_ARG, "cufd: null input");
     if (calc_id == 1 && !(gl && gm && gd && gs) && !also_misfit)
       throw Error(FWI_B200_ERR_ARG, "cufd: calc_id 1 needs the four gradient outputs");
-    fwi_b200_plan *pl = cached_plan(para_fname, gpu_id, group_size, shot_ids);
+    const std::shared_ptr<fwi_b200_plan> hold = cached_plan(para_fname, gpu_id, group_size, shot_ids);
+    fwi_b200_plan *pl = hold.get();
     check(fwi_b200_plan_set_model(pl, Lambda, Mu, Den));
     check(fwi_b200_plan_set_stf(pl, stf));
     if (calc_id != 2) check(fwi_b200_plan_load_obs_files(pl));

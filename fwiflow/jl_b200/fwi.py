@@ -21,7 +21,7 @@ from . import ops
 from .utils import (moduli_to_velocity_grads, paraGen, surveyGen, symmetric_pad, velocity_to_moduli)
 
 __all__ = ["FWI", "FWIExample", "compute_observation", "compute_misfit", "compute_misfit_and_gradient", "padding",
-           "try_pad"]
+           "try_pad", "timelapse_misfit_and_gradients"]
 
 
 @dataclass
@@ -166,3 +166,38 @@ def compute_misfit_and_gradient(fwi: FWI, cp, cs, rho, stf_array, shot_ids=None,
     if not is_masked:
         g_cp, g_cs, g_rho = g_cp * fwi.mask, g_cs * fwi.mask, g_rho * fwi.mask
     return misfit, g_cp, g_cs, g_rho
+
+
+def timelapse_misfit_and_gradients(surveys, stf_array, shot_ids=None, gpu_ids=(0,), **kw):
+    """Time-lapse (flow-coupled) FWI: one misfit + gradient per survey, baseline and monitors, as the reference's
+    coupled inversion evaluates them (docs/codes/src_fwi_coupled/main_two_phase_flow_inversion.jl:50-62,84-93: one
+    `fwi_op` per survey with its own para file / Data directory, survey i on GPU `i % nGpus`, misfits summed).
+
+    surveys : sequence of (fwi, cp, cs, rho) -- each `fwi` has its own WORKSPACE holding that survey's observations
+    gpu_ids : GPUs to spread the surveys over; surveys mapped to the same GPU run one after the other, different
+              GPUs run concurrently (the C ABI releases the GIL; one host thread per GPU like TF's inter-op threads)
+    returns : (sum of misfits, [(misfit, d/dcp, d/dcs, d/drho) per survey])
+    """
+    import threading
+
+    gpu_ids = list(gpu_ids)
+    out = [None] * len(surveys)
+    errs = []
+
+    def worker(g):
+        try:
+            for i in range(g, len(surveys), len(gpu_ids)):
+                fwi, cp, cs, rho = surveys[i]
+                out[i] = compute_misfit_and_gradient(fwi, cp, cs, rho, stf_array, shot_ids=shot_ids,
+                                                     gpu_id=gpu_ids[g], **kw)
+        except Exception as e:  # re-raised in the caller's thread
+            errs.append(e)
+
+    threads = [threading.Thread(target=worker, args=(g,)) for g in range(len(gpu_ids))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errs:
+        raise errs[0]
+    return float(sum(o[0] for o in out)), out
