@@ -13,6 +13,7 @@
 #include <cstring>
 #include <list>
 #include <memory>
+#include <thread>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -81,12 +82,30 @@ struct fwi_b200_plan {
   size_t trace_stride = 0;  // max_nrec * nSteps
   TmaMaps tm{};             // TMA descriptors of the state / model buffers (re-encoded when `state` moves)
   float *tm_state = nullptr, *tm_gacc = nullptr;
+
+  // Overlapped loading of Data/Shot<id>.bin for the host-buffer entry points: a host thread reads the files into two
+  // pinned staging buffers and copies them on `copy_stream` while the forward time loop is already being enqueued
+  // and executed; the observations are first needed by the residual kernels, which wait on `obs_ready`.
+  std::thread loader;
+  int loader_code = 0;
+  std::string loader_err;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t obs_ready = nullptr, pin_ev[2] = {nullptr, nullptr};
+  float *pin[2] = {nullptr, nullptr};
+  size_t pin_n = 0;
   size_t tm_state_n = 0;
 
   float *mplane(int k) { return model.p + (long long)k * g.plane; }
 
   ~fwi_b200_plan() {
     cudaSetDevice(gpu);
+    if (loader.joinable()) loader.join();
+    if (copy_stream) { cudaStreamSynchronize(copy_stream); cudaStreamDestroy(copy_stream); }
+    if (obs_ready) cudaEventDestroy(obs_ready);
+    for (int k = 0; k < 2; k++) {
+      if (pin_ev[k]) cudaEventDestroy(pin_ev[k]);
+      if (pin[k]) cudaFreeHost(pin[k]);
+    }
     if (stream) cudaStreamSynchronize(stream);
     model.release(); model_in.release(); cpmax.release(); zprof.release(); xprof.release(); w2.release();
     state.release(); gacc.release(); frames.release(); syn_tr.release(); res_tr.release();
@@ -287,6 +306,72 @@ Model model_of(fwi_b200_plan &pl) {
   return m;
 }
 
+// ---- overlapped observation loading (host-buffer entry points) ----
+void start_obs_load(fwi_b200_plan &pl) {
+  if (pl.loader.joinable()) pl.loader.join();
+  pl.obs_rt.alloc((size_t)pl.group * pl.trace_stride);
+  if (!pl.copy_stream) {
+    CUDA_OK(cudaStreamCreateWithFlags(&pl.copy_stream, cudaStreamNonBlocking));
+    CUDA_OK(cudaEventCreateWithFlags(&pl.obs_ready, cudaEventDisableTiming));
+    for (int k = 0; k < 2; k++) CUDA_OK(cudaEventCreateWithFlags(&pl.pin_ev[k], cudaEventDisableTiming));
+  }
+  if (pl.pin_n < pl.trace_stride) {
+    for (int k = 0; k < 2; k++) {
+      if (pl.pin[k]) cudaFreeHost(pl.pin[k]);
+      pl.pin[k] = nullptr;
+      CUDA_OK(cudaMallocHost(reinterpret_cast<void **>(&pl.pin[k]), std::max<size_t>(pl.trace_stride, 1) * sizeof(float)));
+    }
+    pl.pin_n = pl.trace_stride;
+  }
+  // the previous evaluation may still be reading obs_rt on the compute stream
+  CUDA_OK(cudaStreamSynchronize(pl.stream));
+  pl.loader_code = 0;
+  pl.loader_err.clear();
+  fwi_b200_plan *p = &pl;
+  pl.loader = std::thread([p] {
+    try {
+      if (cudaSetDevice(p->gpu) != cudaSuccess) throw Error(FWI_B200_ERR_CUDA, "loader: cudaSetDevice failed");
+      for (int i = 0; i < p->group; i++) {
+        const int b = i & 1;
+        const size_t n = p->survey.shots[i].z_rec.size() * (size_t)p->g.nSteps;
+        if (i >= 2) CUDA_OK(cudaEventSynchronize(p->pin_ev[b]));   // the copy out of this staging buffer is done
+        read_f32(p->para.data_dir_name + "/Shot" + std::to_string(p->shot_ids[i]) + ".bin", p->pin[b], n);
+        CUDA_OK(cudaMemcpyAsync(p->obs_rt.p + (size_t)i * p->trace_stride, p->pin[b], n * sizeof(float),
+                                cudaMemcpyHostToDevice, p->copy_stream));
+        CUDA_OK(cudaEventRecord(p->pin_ev[b], p->copy_stream));
+      }
+      CUDA_OK(cudaEventRecord(p->obs_ready, p->copy_stream));
+    } catch (const Error &e) {
+      p->loader_code = e.code;
+      p->loader_err = e.what();
+    } catch (const std::exception &e) {
+      p->loader_code = FWI_B200_ERR_IO;
+      p->loader_err = e.what();
+    }
+  });
+  for (int i = 0; i < pl.group; i++) pl.obs_set[i] = 2;   // 2 = on its way
+}
+
+// called before anything reads obs_rt: the loader has recorded obs_ready (or failed), then stream `s` waits for it
+void finish_obs_load(fwi_b200_plan &pl, cudaStream_t s) {
+  if (!pl.loader.joinable()) return;
+  pl.loader.join();
+  if (pl.loader_code != 0) {
+    for (int i = 0; i < pl.group; i++) pl.obs_set[i] = 0;
+    throw Error(pl.loader_code, pl.loader_err);
+  }
+  for (int i = 0; i < pl.group; i++) pl.obs_set[i] = 1;
+  CUDA_OK(cudaStreamWaitEvent(s, pl.obs_ready, 0));
+}
+
+// an asynchronous load that nobody consumed (failed or forward-only call): wait for it before obs_rt is touched again
+void settle_obs_load(fwi_b200_plan &pl) {
+  if (!pl.loader.joinable()) return;
+  pl.loader.join();
+  if (pl.copy_stream) cudaStreamSynchronize(pl.copy_stream);
+  for (int i = 0; i < pl.group; i++) pl.obs_set[i] = pl.loader_code == 0 ? 1 : 0;
+}
+
 void run_locked(fwi_b200_plan &pl, int calc_id, cudaStream_t s) {
   const Grid &g = pl.g;
   if (calc_id < 0 || calc_id > 2) throw Error(FWI_B200_ERR_ARG, "invalid calc_id " + std::to_string(calc_id));
@@ -333,6 +418,7 @@ void run_locked(fwi_b200_plan &pl, int calc_id, cudaStream_t s) {
       continue;
     }
     // residual + misfit: libCUFD.cu:254-330
+    finish_obs_load(pl, s);
     for (int k = 0; k < nb; k++) {
       const int nrec = (int)pl.survey.shots[first + k].z_rec.size();
       ResidualArgs ra{};
@@ -506,6 +592,7 @@ extern "C" int fwi_b200_plan_set_obs(fwi_b200_plan *pl, int ishot, const float *
     if (!pl || !obs || ishot < 0 || ishot >= pl->group) throw Error(FWI_B200_ERR_ARG, "set_obs: bad arguments");
     std::lock_guard<std::mutex> lk(pl->mu);
     use_device(pl->gpu);
+    settle_obs_load(*pl);
     pl->obs_rt.alloc((size_t)pl->group * pl->trace_stride);
     const size_t n = pl->survey.shots[ishot].z_rec.size() * (size_t)pl->g.nSteps;
     CUDA_OK(cudaMemcpyAsync(pl->obs_rt.p + (size_t)ishot * pl->trace_stride, obs, n * sizeof(float), cudaMemcpyHostToDevice, pl->stream));
@@ -519,6 +606,7 @@ extern "C" int fwi_b200_plan_load_obs_files(fwi_b200_plan *pl) {
     if (!pl) throw Error(FWI_B200_ERR_ARG, "load_obs_files: null plan");
     std::lock_guard<std::mutex> lk(pl->mu);
     use_device(pl->gpu);
+    settle_obs_load(*pl);
     pl->obs_rt.alloc((size_t)pl->group * pl->trace_stride);
     std::vector<float> h(pl->trace_stride);
     for (int i = 0; i < pl->group; i++) {
@@ -655,6 +743,7 @@ extern "C" int fwi_b200_plan_time_kernel(fwi_b200_plan *pl, int which, int iters
     use_device(pl->gpu);
     const Grid &g = pl->g;
     alloc_run_buffers(*pl, 1);
+    settle_obs_load(*pl);
     if (!pl->obs_rt.p) pl->obs_rt.alloc((size_t)pl->group * pl->trace_stride);
     cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : pl->stream;
     const int nb = std::min(pl->batch, pl->group);
@@ -770,7 +859,11 @@ int host_call(double *misfit, double *gl, double *gm, double *gd, double *gs, co
     fwi_b200_plan *pl = hold.get();
     check(fwi_b200_plan_set_model(pl, Lambda, Mu, Den));
     check(fwi_b200_plan_set_stf(pl, stf));
-    if (calc_id != 2) check(fwi_b200_plan_load_obs_files(pl));
+    if (calc_id != 2) {   // Data/Shot<id>.bin -> device, overlapped with the forward time loop
+      std::lock_guard<std::mutex> lk(pl->mu);
+      use_device(pl->gpu);
+      start_obs_load(*pl);
+    }
     check(fwi_b200_plan_run(pl, calc_id, nullptr, 1));
     if (calc_id == 2) {
       check(fwi_b200_plan_write_obs_files(pl));
