@@ -39,6 +39,9 @@ namespace {
 #ifndef ADJ_PF_MODEL
 #define ADJ_PF_MODEL 1
 #endif
+#ifndef FWI_ZIGZAG
+#define FWI_ZIGZAG 1
+#endif
 #ifndef ADJ_SPLIT
 #define ADJ_SPLIT 1   // single-buffered phi / injection tiles are handed over with an arrive / wait pair instead of a block barrier
 #endif
@@ -80,7 +83,8 @@ rev_image_kernel(const __grid_constant__ BwdArgs a, int tz_first, int tx_first, 
   __syncthreads();
 
   auto produce = [&](int item, int stage, int ds, bool first = false) {
-    const int t = item / a.batch, shot = item - t * a.batch;   // shot fastest: the shots of a tile share its coefficients
+    const int io = a.order ? nitems - 1 - item : item;       // reverse launches run descending, adjoint launches ascending
+    const int t = io / a.batch, shot = io - t * a.batch;      // shot fastest: the shots of a tile share its coefficients
     const int z0 = (tz_first + t % ntz) * TILE_Z, x0 = (tx_first + t / ntz) * TILE_X;
     const int sz = a.st.src_z[shot], sx = a.st.src_x[shot];
     TileDesc d;
@@ -344,7 +348,8 @@ __global__ void __launch_bounds__(NCOMPUTE, 1) adj_step_kernel(const __grid_cons
   __syncthreads();
 
   auto produce = [&](int item, int stage, int ds, bool first = false) {
-    const int tile = item / a.batch, shot = item - tile * a.batch;   // shot fastest
+    const int io = a.order ? nitems - 1 - item : item;
+    const int tile = io / a.batch, shot = io - tile * a.batch;   // shot fastest
     const int z0 = (tile % g.tiles_z) * TILE_Z, x0 = (tile / g.tiles_z) * TILE_X;
     const int sz = a.st.src_z[shot], sx = a.st.src_x[shot];
     TileDesc d;
@@ -684,13 +689,19 @@ void configure_backward_kernels() {
   cudaFuncSetAttribute(adj_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ADJ_SMEM);
 }
 
-void launch_adjoint_step(const BwdArgs &a, cudaStream_t s) {
+// Item order (FWI_ZIGZAG): the adjoint step runs ascending, the reverse step -- which reads the adjoint state the
+// adjoint step has just written, and whose output the next adjoint step's neighbourhood in L2 follows -- descending.
+void launch_adjoint_step(const BwdArgs &a_in, cudaStream_t s) {
+  BwdArgs a = a_in;
+  a.order = 0;
   const int nitems = a.batch * a.g.tiles_z * a.g.tiles_x;
   const int blocks = nitems < sm_count() ? nitems : sm_count();
   launch_step(adj_step_kernel, blocks, NCOMPUTE, ADJ_SMEM, s, a);
 }
 
-void launch_reverse_imaging(const BwdArgs &a, cudaStream_t s) {
+void launch_reverse_imaging(const BwdArgs &a_in, cudaStream_t s) {
+  BwdArgs a = a_in;
+  a.order = FWI_ZIGZAG ? 1 : 0;
   const Grid &g = a.g;
   const int tz0 = max(g.zlo - 2, 0) / TILE_Z, tz1 = min(g.zhi + 2, g.nz - 1) / TILE_Z;
   const int tx0 = max(g.xlo - 2, 0) / TILE_X, tx1 = min(g.xhi + 2, g.nx - 1) / TILE_X;

@@ -37,6 +37,9 @@ namespace {
 #ifndef FWI_L2PF
 #define FWI_L2PF 1
 #endif
+#ifndef FWI_ZIGZAG
+#define FWI_ZIGZAG 1
+#endif
 #ifndef FWD_PF_MODEL
 #define FWD_PF_MODEL 1   // coefficient tile -> L2 two items ahead: 0 off, 1 every item, 2 only the item of shot 0
 #endif
@@ -82,7 +85,8 @@ __global__ void __launch_bounds__(NTHREADS_FWD, 1) fwd_step_kernel(const __grid_
   // producer step: descriptor (slot `ds` of NS + 1, so that it never overwrites the one in use) + TMA requests of
   // one item into ring slot `stage`
   auto produce = [&](int item, int stage, int ds, bool first = false) {
-    const int tile = item / a.batch, shot = item - tile * a.batch;   // shot fastest: the shots of a tile share its coefficients in L2
+    const int io = a.order ? nitems - 1 - item : item;             // zig-zag over launches (launch_forward_step)
+    const int tile = io / a.batch, shot = io - tile * a.batch;      // shot fastest: the shots of a tile share its coefficients in L2
     const int tz = tile % g.tiles_z, tx = tile / g.tiles_z;
     const int z0 = tz * TILE_Z, x0 = tx * TILE_X;
     const int sz = a.st.src_z[shot], sx = a.st.src_x[shot];
@@ -278,7 +282,7 @@ __global__ void __launch_bounds__(NTHREADS_FWD, 1) fwd_step_kernel(const __grid_
     const bool more = item + stride < nitems;
     const float *mq_next = a.m.ldt;
     if (more) {
-      const int tn = (item + stride) / a.batch;
+      const int tn = (a.order ? nitems - 1 - (item + stride) : item + stride) / a.batch;
       const int gzn = (tn % g.tiles_z) * TILE_Z - 4 + 4 * q, gxn = min((tn / g.tiles_z) * TILE_X - 2 + c, gx_max);
       mq_next = a.m.ldt + ((long long)gxn * P + gzn);
       ldt = ld4(mq_next); l2mdt = ld4(mq_next + pl); amudt = ld4(mq_next + 2 * pl);
@@ -418,7 +422,11 @@ void configure_forward_kernels() {
   cudaFuncSetAttribute(fwd_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM);
 }
 
-void launch_forward_step(const FwdArgs &a, bool save_frames, cudaStream_t s) {
+// Item order alternates from one time step to the next (FWI_ZIGZAG): the wavefields a step reads are the ones the
+// previous step wrote, and what it wrote LAST is what is still in the 126 MB L2 -- so the next step starts there.
+void launch_forward_step(const FwdArgs &a_in, bool save_frames, cudaStream_t s) {
+  FwdArgs a = a_in;
+  a.order = FWI_ZIGZAG ? (a.it & 1) : 0;
   const int nitems = a.batch * a.g.tiles_z * a.g.tiles_x;
   const int blocks = nitems < sm_count() ? nitems : sm_count();
   if (save_frames)

@@ -111,6 +111,7 @@ struct FwdArgs {
   int batch;
   int it;              // time index of the state being advanced (it -> it+1)
   int cur;             // 0: read buffer A, write B; 1: the reverse
+  int order;           // 0: items in ascending order, 1: descending (see launch_forward_step)
   TmaMaps tm;
 };
 
@@ -128,6 +129,7 @@ struct BwdArgs {
   int it;
   int cur_f;           // forward-field buffer holding state it+1
   int cur_a;           // adjoint buffer holding the pre-update adjoint state
+  int order;           // item order of this launch (0 ascending, 1 descending)
   TmaMaps tm;
 };
 
