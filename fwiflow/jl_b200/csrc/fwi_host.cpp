@@ -61,10 +61,12 @@ Para read_para(const std::string &fname) {
     p.save_scratch = true;
     p.scratch_dir_name = s->str;
   }
-  // optional data-conditioning branch (Parameter.cpp:146-177): not built -> refuse, never ignore
-  if (const JsonValue *w = j.find("if_win"))
-    if (w->type == JsonValue::Bool && w->b)
-      throw Error(FWI_B200_ERR_UNSUPPORTED, "para file: if_win=true (per-trace windows) is not supported");
+  // optional data-conditioning branch (Parameter.cpp:146-177): per-trace windows / weights are built, the
+  // band-pass filter and the source-signature update are not -> refused, never ignored
+  if (const JsonValue *w = j.find("if_win")) {
+    if (w->type != JsonValue::Bool) throw Error(FWI_B200_ERR_JSON, "para file: if_win must be a boolean");
+    p.if_win = w->b;
+  }
   if (j.has("filter"))
     throw Error(FWI_B200_ERR_UNSUPPORTED, "para file: 'filter' (band-pass) is not supported");
   if (const JsonValue *u = j.find("if_src_update"))
@@ -77,7 +79,7 @@ Para read_para(const std::string &fname) {
   return p;
 }
 
-Survey read_survey(const std::string &fname, int nPml, int group_size, const int *shot_ids) {
+Survey read_survey(const std::string &fname, int nPml, int group_size, const int *shot_ids, bool if_win) {
   Survey s;
   s.text = slurp(fname, "survey file");
   JsonValue j;
@@ -111,6 +113,21 @@ Survey read_survey(const std::string &fname, int nPml, int group_size, const int
         throw Error(FWI_B200_ERR_JSON, "survey file: receiver coordinates must be numbers");
       o.z_rec[r] = static_cast<int>(zr.arr[r].num) + nPml;
       o.x_rec[r] = static_cast<int>(xr.arr[r].num) + nPml;
+    }
+    if (if_win) {  // Src_Rec.cu:157-200: seconds, one value per receiver; doubles narrowed to float
+      auto read_f = [&](const char *name, std::vector<float> &dst) {
+        const JsonValue &a = need(*sh, name, JsonValue::Array, F);
+        if (static_cast<int>(a.arr.size()) != nrec)
+          throw Error(FWI_B200_ERR_JSON, "survey file: '" + key + "' " + name + " must have nrec entries");
+        dst.resize(nrec);
+        for (int r = 0; r < nrec; r++) {
+          if (a.arr[r].type != JsonValue::Number) throw Error(FWI_B200_ERR_JSON, std::string("survey file: ") + name + " must be numbers");
+          dst[r] = static_cast<float>(a.arr[r].num);
+        }
+      };
+      read_f("win_start", o.win_start);
+      read_f("win_end", o.win_end);
+      read_f("weights", o.weights);
     }
   }
   return s;

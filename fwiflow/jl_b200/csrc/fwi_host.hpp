@@ -23,6 +23,7 @@ struct Para {
   float dz = 0, dx = 0, dt = 0, f0 = 0;
   std::string survey_fname, data_dir_name, scratch_dir_name;
   bool save_scratch = false;
+  bool if_win = false;  // per-trace time windows + trace weights from the survey file (Parameter.cpp:146-150)
   std::string text;  // raw file content (plan-cache key)
 };
 Para read_para(const std::string &fname);
@@ -32,13 +33,14 @@ struct Shot {
   int id = 0;            // global shot id ("shot<id>")
   int z_src = 0, x_src = 0;  // padded, 0-based (json value + nPml)
   std::vector<int> z_rec, x_rec;  // padded, 0-based
+  std::vector<float> win_start, win_end, weights;  // per receiver, only with if_win (Src_Rec.cu:157-200)
 };
 struct Survey {
   int nShots = 0;
   std::vector<Shot> shots;  // the shots of the group, in group order
   std::string text;
 };
-Survey read_survey(const std::string &fname, int nPml, int group_size, const int *shot_ids);
+Survey read_survey(const std::string &fname, int nPml, int group_size, const int *shot_ids, bool if_win = false);
 
 // ---- CPML profiles (reference: utilities.cu:242-358, Cpml.cu:46-52) ---------
 struct CpmlProfiles {

@@ -190,6 +190,32 @@ __global__ void model_derive_kernel(Grid g, float *model, unsigned int *cpmax_bi
 // =================================================================================================
 // residual / misfit
 // =================================================================================================
+// cuda_window with per-trace limits (utilities.cu:654-706), literally: float times, the ramps evaluated through
+// double sin / cos, amp^2 * weight as the multiplier.  The reference leaves a trace UNTOUCHED (no weight either) when
+// the window is empty ("Window error 1") -- reproduced.
+__device__ __forceinline__ float trace_window(int idt, int nt, float dt, float t0, float t3, float weight, float ratio) {
+  const double PI = 3.141592653589793238462643383279502884197169;
+  const float t = idt * dt;
+  const float t_max = nt * dt;
+  if (t0 < 0.0f) t0 = 0.0f;
+  if (t0 > t_max) t0 = t_max;
+  if (t3 < 0.0f) t3 = 0.0f;
+  if (t3 > t_max) t3 = t_max;
+  const float offset = (t3 - t0) * ratio;
+  if (offset <= 0.0f) return 1.0f;
+  const float t1 = t0 + offset, t2 = t3 - offset;
+  float amp;
+  if (t >= t0 && t < t1)
+    amp = (float)sin(PI / 2.0 * (double)(t - t0) / (double)(t1 - t0));
+  else if (t >= t1 && t < t2)
+    amp = 1.0f;
+  else if (t >= t2 && t < t3)
+    amp = (float)cos(PI / 2.0 * (double)(t - t2) / (double)(t3 - t2));
+  else
+    amp = 0.0f;
+  return amp * amp * weight;
+}
+
 __global__ void residual_kernel(ResidualArgs a) {
   __shared__ float t_obs[32][33];
   __shared__ float t_res[32][33];
@@ -207,12 +233,16 @@ __global__ void residual_kernel(ResidualArgs a) {
     const int t = tb + q, rec = rb + threadIdx.x;
     float res = 0.0f, sc = 0.0f, oc = 0.0f;
     if (t < a.nSteps && rec < a.nrec) {
-      const float w = a.w2[t];
-      oc = t_obs[threadIdx.x][q] * w;                   // cuda_window on obs  (libCUFD.cu:268)
-      sc = a.syn_tr[(long long)t * a.nrp + rec] * w;    // cuda_window on syn  (libCUFD.cu:270)
+      float w = a.w2[t], wr = w;
+      if (a.win_start) {   // if_win: per-trace window + weight, ramp ratio 0.005 on the data and 0.1 on the residual
+        w = trace_window(t, a.nSteps, a.dt, a.win_start[rec], a.win_end[rec], a.weights[rec], 0.005f);
+        wr = trace_window(t, a.nSteps, a.dt, a.win_start[rec], a.win_end[rec], a.weights[rec], 0.1f);
+      }
+      oc = t_obs[threadIdx.x][q] * w;                   // cuda_window on obs  (libCUFD.cu:259-268)
+      sc = a.syn_tr[(long long)t * a.nrp + rec] * w;    // cuda_window on syn  (libCUFD.cu:263-270)
       res = (t > 0) ? oc - sc : 0.0f;                   // gpuMinus            (utilities.cu:154-167)
       acc += (double)(res * res);                       // cuda_cal_objective  (utilities.cu:169-205)
-      res *= w;                                         // cuda_window on res  (libCUFD.cu:312)
+      res *= wr;                                        // cuda_window on res  (libCUFD.cu:305-312)
       a.res_tr[(long long)t * a.nrp + rec] = res;
     }
     t_res[q][threadIdx.x] = res;

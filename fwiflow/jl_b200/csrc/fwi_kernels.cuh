@@ -150,6 +150,9 @@ struct ResidualArgs {
   const float *syn_tr;   // [nSteps][nrp]  raw synthetic (receiver fastest)
   const float *obs_rt;   // [nrec][nSteps] observed (time fastest, file layout)
   const float *w2;       // [nSteps] taper multipliers
+  // per-trace windows (para "if_win", libCUFD.cu:257-266,304-309): seconds / trace weights, null without if_win
+  const float *win_start, *win_end, *weights;   // [nrec]
+  float dt;
   float *res_tr;         // [nSteps][nrp]  tapered residual for injection
   float *syn_rt;         // [nrec][nSteps] conditioned synthetic   (may be null)
   float *res_rt;         // [nrec][nSteps] tapered residual        (may be null)

@@ -76,6 +76,7 @@ struct fwi_b200_plan {
   DevBuf<float> state, gacc, frames, syn_tr, res_tr;
   DevBuf<float> obs_rt, syn_rt, res_rt, obs_cond_rt;  // [group][max_nrec*nSteps]
   DevBuf<int> src_z, src_x, rec_ptr, rec_loc, rec_id;
+  DevBuf<float> win;          // [group][3][max_nrec] win_start | win_end | weights (para if_win)
   DevBuf<float> stf, stf_grad, j_shot, misfit_half, result;
   DevBuf<double> partial;
   int partial_per_shot = 0;
@@ -110,7 +111,7 @@ struct fwi_b200_plan {
     model.release(); model_in.release(); cpmax.release(); zprof.release(); xprof.release(); w2.release();
     state.release(); gacc.release(); frames.release(); syn_tr.release(); res_tr.release();
     obs_rt.release(); syn_rt.release(); res_rt.release(); obs_cond_rt.release();
-    src_z.release(); src_x.release(); rec_ptr.release(); rec_loc.release(); rec_id.release();
+    src_z.release(); src_x.release(); rec_ptr.release(); rec_loc.release(); rec_id.release(); win.release();
     stf.release(); stf_grad.release(); j_shot.release(); misfit_half.release(); result.release();
     partial.release();
     if (stream) cudaStreamDestroy(stream);
@@ -223,6 +224,18 @@ void upload_tables(fwi_b200_plan &pl) {
       loc[(size_t)i * pl.nrp + k] = (s.z_rec[r] % TILE_Z) | ((s.x_rec[r] % TILE_X) << 16);
       rid[(size_t)i * pl.nrp + k] = r;
     }
+  }
+  if (pl.para.if_win) {
+    std::vector<float> w((size_t)G * 3 * std::max(pl.max_nrec, 1), 0.0f);
+    for (int i = 0; i < G; i++) {
+      const Shot &s = pl.survey.shots[i];
+      float *b = w.data() + (size_t)i * 3 * pl.max_nrec;
+      std::copy(s.win_start.begin(), s.win_start.end(), b);
+      std::copy(s.win_end.begin(), s.win_end.end(), b + pl.max_nrec);
+      std::copy(s.weights.begin(), s.weights.end(), b + 2 * pl.max_nrec);
+    }
+    pl.win.alloc(w.size());
+    CUDA_OK(cudaMemcpy(pl.win.p, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
   }
   pl.src_z.alloc(G); pl.src_x.alloc(G); pl.rec_ptr.alloc(ptr.size()); pl.rec_loc.alloc(loc.size()); pl.rec_id.alloc(rid.size());
   CUDA_OK(cudaMemcpy(pl.src_z.p, sz.data(), G * sizeof(int), cudaMemcpyHostToDevice));
@@ -425,6 +438,12 @@ void run_locked(fwi_b200_plan &pl, int calc_id, cudaStream_t s) {
       ra.syn_tr = pl.syn_tr.p + (size_t)k * N * pl.nrp;
       ra.obs_rt = pl.obs_rt.p + (size_t)(first + k) * pl.trace_stride;
       ra.w2 = pl.w2.p;
+      ra.dt = pl.para.dt;
+      if (pl.para.if_win) {
+        ra.win_start = pl.win.p + (size_t)(first + k) * 3 * pl.max_nrec;
+        ra.win_end = ra.win_start + pl.max_nrec;
+        ra.weights = ra.win_end + pl.max_nrec;
+      }
       ra.res_tr = pl.res_tr.p + (size_t)k * N * pl.nrp;
       const bool keep = pl.para.save_scratch && with_adj;
       ra.syn_rt = keep ? pl.syn_rt.p + (size_t)(first + k) * pl.trace_stride : nullptr;
@@ -504,7 +523,7 @@ extern "C" int fwi_b200_plan_create(fwi_b200_plan **out, const char *para_fname,
     *out = nullptr;
     std::unique_ptr<fwi_b200_plan> pl(new fwi_b200_plan());
     pl->para = read_para(para_fname);
-    pl->survey = read_survey(pl->para.survey_fname, pl->para.nPml, group_size, shot_ids);
+    pl->survey = read_survey(pl->para.survey_fname, pl->para.nPml, group_size, shot_ids, pl->para.if_win);
     pl->group = group_size;
     pl->shot_ids.assign(shot_ids, shot_ids + group_size);
     pl->obs_set.assign(group_size, 0);

@@ -75,10 +75,12 @@ class Case:
         para = os.path.join(workdir, "para_file.json")
         survey = os.path.join(workdir, "survey_file.json")
         data = os.path.join(workdir, "Data")
+        win = self.extra.get("windows")          # {"shot<i>": {"start": [...], "end": [...]}} -> para "if_win"
         paraGen(self.nz_pad, self.nx_pad, self.dz, self.dx, self.nSteps, self.dt, self.f0, self.nPml,
-                self.nPad, para, survey, data,
+                self.nPad, para, survey, data, if_win=win is not None,
                 scratch_dir_name=os.path.join(workdir, "Scratch") if scratch else "")
-        surveyGen(self.z_src, self.x_src, self.z_rec, self.x_rec, survey)
+        surveyGen(self.z_src, self.x_src, self.z_rec, self.x_rec, survey, Windows=win,
+                  Weights=self.extra.get("weights"))
         return para
 
 
@@ -177,6 +179,29 @@ def case_small(name="S", nz=60, nx=80, nSteps=600, nshots=2, elastic=True, nlaye
     """Small layered case for CPU-sized parity tests (padded 128x144)."""
     return make_layered_case(name, nz, nx, dz, dt, nSteps, f0, nlayers=nlayers, nshots=nshots,
                              smooth_sigma=4.0, seed=seed, elastic=elastic, vmax=3500.0)
+
+
+def case_small_windows(name="small_windows", seed=11):
+    """case_small with per-trace time windows and trace weights (para "if_win", Src_Rec.cu:157-200): a moveout-like
+    window per receiver, random weights, and the edge cases of cuda_window (utilities.cu:654-706) -- limits outside
+    the record (clamped), an empty window (the reference then leaves the trace untouched) and a zero weight."""
+    c = case_small(name, elastic=True, seed=seed)
+    rng = np.random.default_rng(seed)
+    t_max = c.nSteps * c.dt
+    windows, weights = {}, {}
+    for i in range(c.nShots):
+        off = np.abs((c.x_rec - c.x_src[i]) * c.dx)
+        start = 0.08 + off / 3500.0 + 0.02 * rng.random(c.nrec)
+        end = np.minimum(start + 0.45 + 0.1 * rng.random(c.nrec), 1.4 * t_max)
+        w = 0.5 + rng.random(c.nrec)
+        start[1], end[1] = -0.3, 2.0 * t_max       # clamped to [0, t_max]
+        start[3], end[3] = 0.7, 0.2                # empty window: trace untouched, weight ignored
+        w[5] = 0.0                                 # muted trace
+        windows[f"shot{i}"] = {"start": [float(v) for v in start], "end": [float(v) for v in end]}
+        weights[f"shot{i}"] = {"weights": [float(v) for v in w]}
+    c.extra["windows"] = windows
+    c.extra["weights"] = weights
+    return c
 
 
 def case_gradtest_small(n=110, nSteps=500):

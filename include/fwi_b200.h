@@ -47,7 +47,7 @@ extern "C" {
 #define FWI_B200_ERR_JSON (-3)    /* malformed or incomplete JSON                  */
 #define FWI_B200_ERR_CFL (-4)     /* Courant number > 1 (utilities.cu:225-240)     */
 #define FWI_B200_ERR_CUDA (-5)    /* CUDA runtime error / no device                */
-#define FWI_B200_ERR_UNSUPPORTED (-6) /* if_win / filter / if_src_update requested */
+#define FWI_B200_ERR_UNSUPPORTED (-6) /* filter / if_src_update requested (if_win IS supported) */
 #define FWI_B200_ERR_GEOM (-7)    /* source / receiver outside the grid, grid too small */
 
 /* ---- reference-compatible host-buffer entry points ------------------------- */

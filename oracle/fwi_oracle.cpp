@@ -152,6 +152,39 @@ void taper(float *data, int nrec, int nt, float dt, float ratio) {
   }
 }
 
+// ---- per-trace windows + weights (para "if_win") ----------------------------
+// utilities.cu:654-706 (cuda_window with d_win_start / d_win_end / d_weights), applied at libCUFD.cu:257-266 to the
+// observed and synthetic traces with ratio win_ratio and at libCUFD.cu:304-309 to the residual with ratio 0.1.
+// An empty window ("Window error 1") leaves the trace untouched, weight included.
+void trace_windows(float *data, int nrec, int nt, float dt, const float *win_start, const float *win_end,
+                   const float *weights, float ratio) {
+  const double PI = 3.141592653589793238462643383279502884197169;
+  for (int r = 0; r < nrec; r++) {
+    float t0 = win_start[r], t3 = win_end[r];
+    const float t_max = nt * dt;
+    if (t0 < 0.0f) t0 = 0.0f;
+    if (t0 > t_max) t0 = t_max;
+    if (t3 < 0.0f) t3 = 0.0f;
+    if (t3 > t_max) t3 = t_max;
+    const float offset = (t3 - t0) * ratio;
+    if (offset <= 0.0f) continue;
+    const float t1 = t0 + offset, t2 = t3 - offset;
+    for (int it = 0; it < nt; it++) {
+      const float t = it * dt;
+      float amp;
+      if (t >= t0 && t < t1)
+        amp = (float)std::sin(PI / 2.0 * (double)(t - t0) / (double)(t1 - t0));
+      else if (t >= t1 && t < t2)
+        amp = 1.0f;
+      else if (t >= t2 && t < t3)
+        amp = (float)std::cos(PI / 2.0 * (double)(t - t2) / (double)(t3 - t2));
+      else
+        amp = 0.0f;
+      data[(int64_t)r * nt + it] *= amp * amp * weights[r];
+    }
+  }
+}
+
 // ---- sum of squares with the reference's reduction order --------------------
 // utilities.cu:169-205: 512 lanes each accumulate a strided subsequence with
 // powf(a,2), then a halving tree.
@@ -509,7 +542,7 @@ inline int64_t frame_cell(const Geom &g, const Frames &F, int k) {
 // (libCUFD.cu:210-213, 429-431) for shot 0 of the group.
 // returns 0, or 1 when the Courant limit is violated (utilities.cu:239).
 // =============================================================================
-extern "C" int fwi_oracle_cufd(
+static int cufd_impl(
     int nz, int nx, int nPml, int nPad, int nSteps, float dz, float dx, float dt, float f0,
     int calc_id, int group_size, const int *shot_ids,
     const double *Lambda, const double *Mu, const double *Den, const double *stf,
@@ -519,7 +552,8 @@ extern "C" int fwi_oracle_cufd(
     const float *obs_in,                         // calc 0/1: concatenated [rec][time]
     double *misfit, double *grad_Lambda, double *grad_Mu, double *grad_Den, double *grad_stf,
     float *syn_out, float *res_out, float *obs_cond_out,
-    int snap_it, float *snap_fwd, float *snap_back) {
+    int snap_it, float *snap_fwd, float *snap_back,
+    const float *win_start, const float *win_end, const float *weights) {   // per receiver (rec_off), or all NULL
   State S;
   S.g = Geom{nz, nx, nPml, nPad, nSteps, dz, dx, dt, f0};
   const Geom &g = S.g;
@@ -593,15 +627,25 @@ extern "C" int fwi_oracle_cufd(
 
     // ---- residual: libCUFD.cu:254-330 ----
     if (if_res) {
-      taper(obs.data(), nrec, nSteps, dt, win_ratio);
-      taper(data.data(), nrec, nSteps, dt, win_ratio);
+      const bool if_win = win_start != nullptr;
+      const float *w0 = if_win ? win_start + rec_off[iShot] : nullptr;
+      const float *w1 = if_win ? win_end + rec_off[iShot] : nullptr;
+      const float *ww = if_win ? weights + rec_off[iShot] : nullptr;
+      if (if_win) {  // libCUFD.cu:257-266
+        trace_windows(obs.data(), nrec, nSteps, dt, w0, w1, ww, win_ratio);
+        trace_windows(data.data(), nrec, nSteps, dt, w0, w1, ww, win_ratio);
+      } else {
+        taper(obs.data(), nrec, nSteps, dt, win_ratio);
+        taper(data.data(), nrec, nSteps, dt, win_ratio);
+      }
       for (int r = 0; r < nrec; r++)  // gpuMinus: utilities.cu:154-167
         for (int t = 0; t < nSteps; t++) {
           const int64_t k = (int64_t)r * nSteps + t;
           res[k] = (t > 0) ? obs[k] - data[k] : 0.0f;
         }
       h_l2Obj += sum_sq_512(res.data(), (int64_t)nrec * nSteps);
-      taper(res.data(), nrec, nSteps, dt, win_ratio);
+      if (if_win) trace_windows(res.data(), nrec, nSteps, dt, w0, w1, ww, 0.1f);   // libCUFD.cu:304-309
+      else taper(res.data(), nrec, nSteps, dt, win_ratio);
     }
 
     // ---- backward: libCUFD.cu:334-457 ----
@@ -668,6 +712,36 @@ extern "C" int fwi_oracle_cufd(
     if (misfit) *misfit = h_l2Obj;
   }
   return 0;
+}
+
+extern "C" int fwi_oracle_cufd(
+    int nz, int nx, int nPml, int nPad, int nSteps, float dz, float dx, float dt, float f0,
+    int calc_id, int group_size, const int *shot_ids,
+    const double *Lambda, const double *Mu, const double *Den, const double *stf,
+    const int *z_src, const int *x_src, const int *rec_off, const int *z_rec, const int *x_rec,
+    const float *obs_in,
+    double *misfit, double *grad_Lambda, double *grad_Mu, double *grad_Den, double *grad_stf,
+    float *syn_out, float *res_out, float *obs_cond_out,
+    int snap_it, float *snap_fwd, float *snap_back) {
+  return cufd_impl(nz, nx, nPml, nPad, nSteps, dz, dx, dt, f0, calc_id, group_size, shot_ids, Lambda, Mu, Den, stf,
+                   z_src, x_src, rec_off, z_rec, x_rec, obs_in, misfit, grad_Lambda, grad_Mu, grad_Den, grad_stf,
+                   syn_out, res_out, obs_cond_out, snap_it, snap_fwd, snap_back, nullptr, nullptr, nullptr);
+}
+
+// same, with the per-trace windows / weights of para "if_win" (concatenated per receiver like z_rec)
+extern "C" int fwi_oracle_cufd_win(
+    int nz, int nx, int nPml, int nPad, int nSteps, float dz, float dx, float dt, float f0,
+    int calc_id, int group_size, const int *shot_ids,
+    const double *Lambda, const double *Mu, const double *Den, const double *stf,
+    const int *z_src, const int *x_src, const int *rec_off, const int *z_rec, const int *x_rec,
+    const float *obs_in,
+    double *misfit, double *grad_Lambda, double *grad_Mu, double *grad_Den, double *grad_stf,
+    float *syn_out, float *res_out, float *obs_cond_out,
+    int snap_it, float *snap_fwd, float *snap_back,
+    const float *win_start, const float *win_end, const float *weights) {
+  return cufd_impl(nz, nx, nPml, nPad, nSteps, dz, dx, dt, f0, calc_id, group_size, shot_ids, Lambda, Mu, Den, stf,
+                   z_src, x_src, rec_off, z_rec, x_rec, obs_in, misfit, grad_Lambda, grad_Mu, grad_Den, grad_stf,
+                   syn_out, res_out, obs_cond_out, snap_it, snap_fwd, snap_back, win_start, win_end, weights);
 }
 
 // CPML profiles for inspection by the tests: out = [K,a,b,K_half,a_half,b_half] x N

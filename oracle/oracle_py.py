@@ -92,6 +92,13 @@ def oracle_cufd(calc_id, lam, mu, den, stf, shot_ids, para_fname, obs=None, snap
         rec_off[i + 1] = rec_off[i] + sh["nrec"]
     zr = np.ascontiguousarray(np.concatenate(zr), np.int32)
     xr = np.ascontiguousarray(np.concatenate(xr), np.int32)
+    win = None
+    if para.get("if_win", False):   # Src_Rec.cu:157-200: per-receiver windows (s) and trace weights
+        win = [np.ascontiguousarray(np.concatenate([np.asarray(survey[f"shot{int(s)}"][k], np.float64) for s in shot_ids]),
+                                    np.float32) for k in ("win_start", "win_end", "weights")]
+        assert all(w.size == rec_off[-1] for w in win)
+    if "filter" in para or para.get("if_src_update", False):
+        raise NotImplementedError("oracle: band-pass filter / source update are not restated")
     ntr = int(rec_off[-1]) * nSteps
     obs_in = None
     if calc_id in (0, 1):
@@ -115,13 +122,17 @@ def oracle_cufd(calc_id, lam, mu, den, stf, shot_ids, para_fname, obs=None, snap
     snap_b = np.zeros(nz * nx, np.float32) if snap_it >= 0 else None
     if threads is not None:
         os.environ["OMP_NUM_THREADS"] = str(threads)
-    rc = oracle_lib().fwi_oracle_cufd(
+    args = [
         ctypes.c_int(nz), ctypes.c_int(nx), ctypes.c_int(nPml), ctypes.c_int(nPad), ctypes.c_int(nSteps),
         ctypes.c_float(para["dz"]), ctypes.c_float(para["dx"]), ctypes.c_float(para["dt"]),
         ctypes.c_float(para["f0"]), ctypes.c_int(calc_id), ctypes.c_int(G), _ip(shot_ids),
         _dp(lam), _dp(mu), _dp(den), _dp(stf), _ip(zs), _ip(xs), _ip(rec_off), _ip(zr), _ip(xr),
         _fp(obs_in), _dp(misfit), _dp(gl), _dp(gm), _dp(gd), _dp(gs), _fp(syn), _fp(res), None,
-        ctypes.c_int(snap_it), _fp(snap_f), _fp(snap_b))
+        ctypes.c_int(snap_it), _fp(snap_f), _fp(snap_b)]
+    if win is None:
+        rc = oracle_lib().fwi_oracle_cufd(*args)
+    else:
+        rc = oracle_lib().fwi_oracle_cufd_win(*args, _fp(win[0]), _fp(win[1]), _fp(win[2]))
     if rc != 0:
         raise RuntimeError(f"oracle: Courant limit violated (rc={rc})")
     out = {"misfit": float(misfit[0]), "grad_lambda": gl, "grad_mu": gm, "grad_den": gd, "grad_stf": gs}

@@ -104,13 +104,20 @@ def test_unsupported_keys_are_rejected_not_ignored(lib_built):
     c, wd, para = _case_files()
     lam, mu, rho = c.moduli("true")
     p = json.loads(open(para).read())
-    for extra in ({"filter": [0.0, 0.1, 100.0, 200.0]}, {"if_win": True}, {"if_src_update": True}):
+    for extra in ({"filter": [0.0, 0.1, 100.0, 200.0]}, {"if_src_update": True}):
         q = dict(p); q.update(extra)
         fn = os.path.join(wd, "para_bad.json")
         open(fn, "w").write(json.dumps(q))
         with pytest.raises(ops.FwiError) as ei:
             ops.fwi_obs_op(lam, mu, rho, c.stf, 0, [0], fn)
         assert ei.value.code == -6
+    # per-trace windows ARE supported: if_win=true then needs win_start / win_end / weights in the survey file
+    q = dict(p); q.update({"if_win": True})
+    fn = os.path.join(wd, "para_win.json")
+    open(fn, "w").write(json.dumps(q))
+    with pytest.raises(ops.FwiError) as ei:
+        ops.fwi_obs_op(lam, mu, rho, c.stf, 0, [0], fn)
+    assert ei.value.code == -3 and "win_start" in str(ei.value)
     q = dict(p); q.update({"if_win": False, "if_src_update": False, "isAc": True})   # the reference's sample file
     fn = os.path.join(wd, "para_ok.json")
     open(fn, "w").write(json.dumps(q, indent=1))      # multi-line is tolerated
