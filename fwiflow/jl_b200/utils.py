@@ -144,3 +144,56 @@ def nPad_rule(nz, nPml=32):
 def symmetric_pad(a, nPml, nPad):
     """tf.pad(a, [nPml (nPml+nPad); nPml nPml], "SYMMETRIC") (src/FWI.jl:202)."""
     return np.pad(np.asarray(a, dtype=np.float64), ((nPml, nPml + nPad), (nPml, nPml)), mode="symmetric")
+
+
+def klauderWave(fmin, fmax, t_sweep, nStepTotal, nStepDelay, delta_t):
+    """Klauder wavelet, shape (1, nStepTotal) like the reference's crop (src/Utils.jl:163-183): the symmetric
+    autocorrelation of a linear sweep, centre sample 1.0, cropped to start `nStepDelay` samples before the centre."""
+    nStep = int(nStepTotal) - int(nStepDelay)
+    K = (fmax - fmin) / t_sweep
+    f0 = (fmin + fmax) / 2.0
+    t = delta_t * np.arange(1, nStep, dtype=np.float64)
+    half = np.sin(np.pi * K * t * (t_sweep - t)) * np.cos(2.0 * np.pi * f0 * t) / (np.pi * K * t * t_sweep)
+    source = np.empty(2 * nStep - 1, dtype=np.float64)
+    source[:nStep - 1] = half[::-1]
+    source[nStep - 1] = 1.0
+    source[nStep:] = half
+    return source[nStep - int(nStepDelay) - 1:].reshape(1, -1)      # Julia 1-based source[:, nStep-nStepDelay:end]
+
+
+def cs_bounds_cloud(cpImg, Bounds):
+    """Upper / lower cs bounds from a (vp, vs_high, vs_low) reference cloud by piecewise-linear interpolation, held
+    constant outside the cloud like Dierckx `Spline1D(...; k=1)` with its default "nearest" boundary
+    (src/Utils.jl:144-156)."""
+    cp = np.asarray(cpImg, dtype=np.float64)
+    B = np.asarray(Bounds, dtype=np.float64)
+    order = np.argsort(B[0])
+    return np.interp(cp, B[0][order], B[1][order]), np.interp(cp, B[0][order], B[2][order])
+
+
+def resize_bilinear(a, nz, nx):
+    """tf.image.resize_bilinear(a, (nz, nx)) with its default align_corners=False / legacy sampling
+    (source coordinate = destination index * in/out), as src/Utils.jl:192-200 applies it."""
+    a = np.asarray(a, dtype=np.float64)
+
+    def axis_weights(n_in, n_out):
+        pos = np.arange(n_out, dtype=np.float64) * (n_in / float(n_out))
+        lo = np.minimum(np.floor(pos).astype(np.int64), n_in - 1)
+        hi = np.minimum(lo + 1, n_in - 1)
+        return lo, hi, pos - lo
+
+    zl, zh, zw = axis_weights(a.shape[0], nz)
+    xl, xh, xw = axis_weights(a.shape[1], nx)
+    top = a[zl][:, xl] * (1.0 - xw) + a[zl][:, xh] * xw
+    bot = a[zh][:, xl] * (1.0 - xw) + a[zh][:, xh] * xw
+    return top * (1.0 - zw)[:, None] + bot * zw[:, None]
+
+
+def padding(cp, cs, den, nz_orig, nx_orig, nz, nx, nPml, nPad):
+    """Resample the (nz_orig, nx_orig) model to (nz, nx), then pad symmetrically with the PML and the nPad rows
+    (src/Utils.jl:192-214)."""
+    out = []
+    for a in (cp, cs, den):
+        a = np.asarray(a, dtype=np.float64).reshape(nz_orig, nx_orig)
+        out.append(symmetric_pad(resize_bilinear(a, nz, nx), nPml, nPad))
+    return tuple(out)

@@ -168,3 +168,26 @@ def test_synthetic_cases_have_baseline_shapes():
     assert (c2.nz_pad, c2.nx_pad, c2.nShots, c2.nrec) == (224, 448, 30, 378 + 0) or c2.nrec in (378, 379)
     c1 = synthetic.case_c1(nSteps=10)
     assert (c1.nz_pad, c1.nx_pad, c1.nShots, c1.nrec) == (192, 164, 1, 94)
+
+
+def test_klauder_bounds_and_resampled_padding():
+    """Host helpers of src/Utils.jl that sit beside the op: klauderWave, cs_bounds_cloud, padding with resampling."""
+    from fwiflow.jl_b200 import utils
+    w = utils.klauderWave(2.0, 20.0, 4.0, 500, 100, 0.002)
+    n = 500 - 100
+    assert w.shape == (1, n + 100) and w[0, 100] == 1.0                      # centre sample after the delay
+    assert np.allclose(w[0, 100 - 50:100], w[0, 101:151][::-1])              # symmetric about the centre
+    t = 0.002 * 3
+    K, f0 = (20.0 - 2.0) / 4.0, 11.0
+    assert w[0, 103] == pytest.approx(np.sin(np.pi * K * t * (4.0 - t)) * np.cos(2 * np.pi * f0 * t) / (np.pi * K * t * 4.0))
+    hi, lo = utils.cs_bounds_cloud(np.array([[1500.0, 2500.0], [3500.0, 9000.0]]),
+                                   np.array([[2000.0, 3000.0, 4000.0], [1200.0, 1800.0, 2400.0], [900.0, 1300.0, 1700.0]]))
+    assert hi[0, 1] == pytest.approx(1500.0) and lo[0, 1] == pytest.approx(1100.0)
+    assert hi[0, 0] == 1200.0 and lo[1, 1] == 1700.0                         # held constant outside the cloud
+    a = np.arange(12.0).reshape(3, 4)
+    assert np.array_equal(utils.resize_bilinear(a, 3, 4), a)
+    up = utils.resize_bilinear(a, 6, 8)
+    assert up.shape == (6, 8) and up[0, 0] == 0.0 and up[2, 2] == pytest.approx(a[1, 1]) and up[1, 0] == pytest.approx(2.0)
+    cp, cs, den = utils.padding(a, a / 2, a + 1, 3, 4, 6, 8, 4, 2)
+    assert cp.shape == (6 + 2 * 4 + 2, 8 + 2 * 4) and np.array_equal(cp[4:10, 4:12], up)
+    assert np.array_equal(cp[3, 4:12], up[0]) and np.array_equal(cp[2, 4:12], up[1])   # SYMMETRIC (edge repeated)
