@@ -75,7 +75,8 @@ rev_image_kernel(const __grid_constant__ BwdArgs a, int tz_first, int tx_first, 
   const int P = g.P;
   const long long pl = g.plane;
 
-  pdl_launch_dependents();
+  // (griddepcontrol.launch_dependents is issued AFTER the wait below: the adjoint step that follows does not wait in its
+  //  prologue, so it may only be let loose once this grid knows that the previous adjoint step has completed)
   if (tid == 0) {
     for (int s = 0; s < NS; s++) mbar_init(&full[s], 1);
     fence_barrier_init();
@@ -118,6 +119,7 @@ rev_image_kernel(const __grid_constant__ BwdArgs a, int tz_first, int tx_first, 
       if (blockIdx.x + s * stride < nitems) produce(blockIdx.x + s * stride, s, s, s == 0);
   __syncthreads();   // the first descriptors are visible: per-item global loads may start before the TMA data lands
   pdl_wait();
+  pdl_launch_dependents();
 
   const float dt = g.dt;
   const float kz1 = C1 * g.rdz, kz2 = C2 * g.rdz, kx1 = C1 * g.rdx, kx2 = C2 * g.rdx;
@@ -366,7 +368,7 @@ __global__ void __launch_bounds__(NCOMPUTE, 1) adj_step_kernel(const __grid_cons
     sdesc[ds] = d;
     unsigned char *sb = base + stage * ASTAGE_BYTES;
     const int p0 = shot * S_COUNT + ain;
-    if (first) pdl_wait();   // everything above reads static tables only
+    if (first && !a.indep) pdl_wait();   // everything above reads static tables only
     mbar_arrive_expect_tx(&full[stage], AS_BYTES + AV_BYTES);
     tma_load_3d(sb, &a.tm.s3, z0 - 8, x0 - 3 + XM, p0 + F_SZZ, &full[stage]);
     tma_load_3d(sb + AS_PAD, &a.tm.vn, z0 - 4, x0 - 2 + XM, p0 + F_VZ, &full[stage]);
@@ -395,7 +397,12 @@ __global__ void __launch_bounds__(NCOMPUTE, 1) adj_step_kernel(const __grid_cons
     for (int s = 0; s < ANS; s++)
       if (blockIdx.x + s * stride < nitems) produce(blockIdx.x + s * stride, s, s, s == 0);
   __syncthreads();   // the first descriptors are visible
-  pdl_wait();
+  // Inside the backward loop the previous launch is rev_image of the same time index: it reads what this kernel reads
+  // and writes nothing this kernel touches, and it only passed its own griddepcontrol.wait after the adjoint step
+  // before it had completed.  So this launch starts working while the reverse step's last (partial) round of items
+  // drains, and waits at its END instead -- that keeps "this grid complete => everything before it complete" for
+  // the launch that follows.
+  if (!a.indep) pdl_wait();
 
   const float dt = g.dt;
   // adjoint-kernel spelling of the differences: (-c1 (..) + c2 (..)) / h  (el_stress_adj.cu:54-61)
@@ -676,6 +683,7 @@ __global__ void __launch_bounds__(NCOMPUTE, 1) adj_step_kernel(const __grid_cons
     if (++ds == ANS + 1) ds = 0;
     if (++stage == ANS) { stage = 0; phase ^= 1; }
   }
+  if (a.indep) pdl_wait();
 }
 
 }  // namespace

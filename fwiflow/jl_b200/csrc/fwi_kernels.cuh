@@ -130,6 +130,8 @@ struct BwdArgs {
   int cur_f;           // forward-field buffer holding state it+1
   int cur_a;           // adjoint buffer holding the pre-update adjoint state
   int order;           // item order of this launch (0 ascending, 1 descending)
+  int indep;           // adjoint step only: the launch before it in the stream is the reverse step of the same time
+                       // index, whose output it does not touch -> no wait in the prologue (see adj_step_kernel)
   TmaMaps tm;
 };
 

@@ -118,6 +118,10 @@ struct fwi_b200_plan {
   }
 };
 
+#ifndef FWI_ADJ_INDEP
+#define FWI_ADJ_INDEP 1
+#endif
+
 namespace {
 
 int round_up(int v, int m) { return (v + m - 1) / m * m; }
@@ -475,7 +479,9 @@ void run_locked(fwi_b200_plan &pl, int calc_id, cudaStream_t s) {
       launch_reverse_imaging(ba, s);
       pl.launches++;
       // (at it == 0 only the source_grad part of this launch is observable; kept for grad_stf[0])
+      ba.indep = FWI_ADJ_INDEP;   // follows the reverse step of the same time index: independent of it
       launch_adjoint_step(ba, s);
+      ba.indep = 0;
       pl.launches++;
       cur_f ^= 1;
       cur_a ^= 1;
