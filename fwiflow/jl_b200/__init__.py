@@ -11,6 +11,7 @@ Layout:
 """
 from .utils import (paraGen, surveyGen, sourceGene, velocity_to_moduli, klauderWave, cs_bounds_cloud,  # noqa: F401
                     resize_bilinear)
-from .ops import fwi_op, fwi_obs_op, fwi_op_grad, fwi_op_and_grad, Plan, FwiError, release  # noqa: F401
+from .ops import (fwi_op, fwi_obs_op, fwi_op_grad, fwi_op_and_grad, fwi_op_and_grad_multi, Plan, FwiError,  # noqa: F401
+                  release)
 from .fwi import (FWI, FWIExample, compute_observation, compute_misfit, compute_misfit_and_gradient,  # noqa: F401
                   timelapse_misfit_and_gradients)

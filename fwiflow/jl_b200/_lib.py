@@ -21,7 +21,7 @@ c_ip = ctypes.POINTER(ctypes.c_int)
 # every symbol include/fwi_b200.h declares
 SYMBOLS = [
     "fwi_b200_cufd", "fwi_b200_forward", "fwi_b200_backward", "fwi_b200_obscalc",
-    "fwi_b200_misfit_and_gradient", "fwi_b200_last_error", "fwi_b200_release",
+    "fwi_b200_misfit_and_gradient", "fwi_b200_gradient_multi", "fwi_b200_last_error", "fwi_b200_release",
     "fwi_b200_plan_create", "fwi_b200_plan_destroy", "fwi_b200_plan_set_model", "fwi_b200_plan_set_stf",
     "fwi_b200_plan_set_obs", "fwi_b200_plan_load_obs_files", "fwi_b200_plan_run",
     "fwi_b200_plan_result_device", "fwi_b200_plan_result_count", "fwi_b200_plan_get_result",
@@ -68,6 +68,7 @@ def lib():
                 c_ip, ctypes.c_char_p]
     L.fwi_b200_cufd.argtypes = host_sig
     L.fwi_b200_misfit_and_gradient.argtypes = [c_dp] * 9 + [ctypes.c_int, ctypes.c_int, c_ip, ctypes.c_char_p]
+    L.fwi_b200_gradient_multi.argtypes = [c_dp] * 9 + [ctypes.c_int, c_ip, ctypes.c_int, c_ip, ctypes.c_char_p]
     L.fwi_b200_forward.argtypes = [c_dp] * 5 + [ctypes.c_int, ctypes.c_int, c_ip, ctypes.c_char_p]
     L.fwi_b200_obscalc.argtypes = [c_dp] * 5 + [ctypes.c_int, ctypes.c_int, c_ip, ctypes.c_char_p]
     L.fwi_b200_backward.argtypes = [c_dp] * 8 + [ctypes.c_int, ctypes.c_int, c_ip, ctypes.c_char_p]

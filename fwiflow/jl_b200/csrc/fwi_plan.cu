@@ -943,6 +943,62 @@ extern "C" int fwi_b200_misfit_and_gradient(double *misfit, double *gl, double *
   return host_call(misfit, gl, gm, gd, gs, Lambda, Mu, Den, stf, 1, true, gpu_id, group_size, shot_ids, para_fname);
 }
 
+extern "C" int fwi_b200_gradient_multi(double *misfit, double *gl, double *gm, double *gd, double *gs,
+                                       const double *Lambda, const double *Mu, const double *Den, const double *stf,
+                                       int ngpu, const int *gpu_ids, int group_size, const int *shot_ids,
+                                       const char *para_fname) {
+  return guarded([&] {
+    if (ngpu <= 0 || !gpu_ids || group_size <= 0 || !shot_ids || !para_fname)
+      throw Error(FWI_B200_ERR_ARG, "gradient_multi: bad arguments");
+    const Para para = read_para(para_fname);
+    const size_t n = (size_t)para.nz * para.nx;
+    const int N = para.nSteps;
+    struct Shard {
+      int gpu = 0;
+      std::vector<int> ids, pos;            // shot ids and their positions in the caller's group
+      std::vector<double> gl, gm, gd, gs;
+      double misfit = 0.0;
+      int rc = FWI_B200_OK;
+      std::string err;
+    };
+    std::vector<Shard> shards(std::min(ngpu, group_size));
+    for (int k = 0; k < group_size; k++) {   // round-robin, a true partition of the group
+      Shard &sh = shards[k % shards.size()];
+      sh.ids.push_back(shot_ids[k]);
+      sh.pos.push_back(k);
+    }
+    std::vector<std::thread> workers;
+    for (size_t r = 0; r < shards.size(); r++) {
+      Shard &sh = shards[r];
+      sh.gpu = gpu_ids[r];
+      sh.gl.assign(n, 0.0); sh.gm.assign(n, 0.0); sh.gd.assign(n, 0.0);
+      sh.gs.assign(sh.ids.size() * (size_t)N, 0.0);
+      workers.emplace_back([&sh, Lambda, Mu, Den, stf, para_fname] {
+        sh.rc = host_call(&sh.misfit, sh.gl.data(), sh.gm.data(), sh.gd.data(), sh.gs.data(), Lambda, Mu, Den, stf, 1, true,
+                          sh.gpu, (int)sh.ids.size(), sh.ids.data(), para_fname);
+        if (sh.rc != FWI_B200_OK) sh.err = last_error_cstr();   // the error text is thread-local
+      });
+    }
+    for (auto &w : workers) w.join();
+    for (const Shard &sh : shards)
+      if (sh.rc != FWI_B200_OK) throw Error(sh.rc, "gpu " + std::to_string(sh.gpu) + ": " + sh.err);
+    double j = 0.0;
+    for (const Shard &sh : shards) j += sh.misfit;
+    if (misfit) *misfit = j;
+    for (size_t i = 0; i < n; i++) {
+      double a = 0.0, b = 0.0, c = 0.0;
+      for (const Shard &sh : shards) { a += sh.gl[i]; b += sh.gm[i]; c += sh.gd[i]; }
+      if (gl) gl[i] = a;
+      if (gm) gm[i] = b;
+      if (gd) gd[i] = c;
+    }
+    if (gs)
+      for (const Shard &sh : shards)
+        for (size_t k = 0; k < sh.ids.size(); k++)
+          std::copy(sh.gs.begin() + k * N, sh.gs.begin() + (k + 1) * N, gs + (size_t)sh.pos[k] * N);
+  });
+}
+
 extern "C" void fwi_b200_release(void) {
   std::lock_guard<std::mutex> lk(g_cache_mu);
   g_cache.clear();

@@ -91,6 +91,22 @@ def fwi_op_and_grad(lam, mu, den, stf, gpu_id, shot_ids, para_fname):
     return float(misfit.value), gl, gm, gd, gs
 
 
+def fwi_op_and_grad_multi(lam, mu, den, stf, gpu_ids, shot_ids, para_fname):
+    """Loss and gradients with the shots of the group sharded over several GPUs of THIS process
+    (fwi_b200_gradient_multi): shot k goes to gpu_ids[k % len(gpu_ids)], the devices run concurrently."""
+    lam, mu, den, stf, ids = _prep(lam, mu, den, stf, shot_ids)
+    gpus = np.ascontiguousarray(np.asarray(gpu_ids, dtype=np.int32).ravel())
+    gl, gm, gd = np.zeros_like(lam), np.zeros_like(lam), np.zeros_like(lam)
+    gs_group = np.zeros((len(ids), stf.shape[1]), np.float64)
+    misfit = ctypes.c_double(0.0)
+    check(_lib.lib().fwi_b200_gradient_multi(
+        ctypes.cast(ctypes.byref(misfit), c_dp), _dp(gl), _dp(gm), _dp(gd), _dp(gs_group), _dp(lam), _dp(mu), _dp(den),
+        _dp(stf), len(gpus), gpus.ctypes.data_as(c_ip), len(ids), ids.ctypes.data_as(c_ip), str(para_fname).encode()))
+    gs = np.zeros_like(stf)
+    gs[ids] = gs_group
+    return float(misfit.value), gl, gm, gd, gs
+
+
 def release():
     """Free the cached device contexts behind the host-buffer entry points."""
     _lib.lib().fwi_b200_release()

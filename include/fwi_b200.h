@@ -78,6 +78,17 @@ int fwi_b200_misfit_and_gradient(double *misfit, double *grad_Lambda, double *gr
                                  int gpu_id, int group_size, const int *shot_ids,
                                  const char *para_fname);
 
+/* The same evaluation with the shots of the group sharded over `ngpu` devices of this process:
+ * shot k of the group goes to gpu_ids[k % ngpu], every device evaluates its shard concurrently (one host thread and
+ * one cached plan per device), and the per-device misfits / gradients are summed.  Replaces the reference's manual
+ * sharding over several fwi_op calls with different gpu_id (test/TestFWI.jl:63-69) -- without its doubly counted
+ * boundary shots.  grad_stf rows are in the order of shot_ids.  Any output pointer may be NULL.
+ * (Across PROCESSES, one per GPU, use the plan API + an NCCL all-reduce of fwi_b200_plan_result_device(): dist.py.) */
+int fwi_b200_gradient_multi(double *misfit, double *grad_Lambda, double *grad_Mu, double *grad_Den,
+                            double *grad_stf, const double *Lambda, const double *Mu,
+                            const double *Den, const double *stf, int ngpu, const int *gpu_ids,
+                            int group_size, const int *shot_ids, const char *para_fname);
+
 /* Text of the last error raised on the calling thread ("" if none). */
 const char *fwi_b200_last_error(void);
 
