@@ -135,7 +135,7 @@ rev_image_kernel(const __grid_constant__ BwdArgs a, int tz_first, int tx_first, 
   for (int item = blockIdx.x; item < nitems; item += stride) {
     const TileDesc d = sdesc[ds];   // written by the producer >= 1 block barrier ago
     const int gz = d.z0 - 4 + 4 * q, gx = d.x0 - 2 + c;
-    const bool inb = (unsigned)gx < (unsigned)g.nx && (unsigned)gz < (unsigned)g.nz;
+    const bool inb = (unsigned)gx < (unsigned)g.nx && (unsigned)gz < (unsigned)g.zlive;
     const bool owner = inner && inb;
     const long long toff = d.soff + ((long long)(c - 2) * P + 4 * q - 4);
     float *sq = a.state + g.origin + toff;                                       // + slot * pl
@@ -418,7 +418,7 @@ __global__ void __launch_bounds__(NCOMPUTE, 1) adj_step_kernel(const __grid_cons
   for (int item = blockIdx.x; item < nitems; item += stride) {
     const TileDesc d = sdesc[ds];   // written by the producer >= 1 block barrier ago
     const int gz = d.z0 - 4 + 4 * q, gx = d.x0 - 2 + c;
-    const bool inb = (unsigned)gx < (unsigned)g.nx && (unsigned)gz < (unsigned)g.nz;
+    const bool inb = (unsigned)gx < (unsigned)g.nx && (unsigned)gz < (unsigned)g.zlive;
     const bool owner = inner && inb;
     float *sq = a.state + g.origin + d.soff + ((long long)(c - 2) * P + 4 * q - 4);   // + slot * pl
     const float *mq = a.m.ldt + ((long long)min(gx, gx_max) * P + gz);

@@ -37,6 +37,9 @@ namespace {
 #ifndef FWI_L2PF
 #define FWI_L2PF 1
 #endif
+#ifndef FWI_TMA_L2PROMO
+#define FWI_TMA_L2PROMO CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+#endif
 #ifndef FWI_ZIGZAG
 #define FWI_ZIGZAG 1
 #endif
@@ -163,7 +166,7 @@ __global__ void __launch_bounds__(NTHREADS_FWD, 1) fwd_step_kernel(const __grid_
     mbar_wait(&full[stage], phase);
     const TileDesc d = sdesc[ds];
     const int gz = d.z0 - 4 + 4 * q, gx = d.x0 - 2 + c;
-    const bool inb = (unsigned)gx < (unsigned)g.nx && (unsigned)gz < (unsigned)g.nz;
+    const bool inb = (unsigned)gx < (unsigned)g.nx && (unsigned)gz < (unsigned)g.zlive;
     const bool owner = inner && inb;
     float *sq = a.state + g.origin + d.soff + ((long long)(c - 2) * P + 4 * q - 4);   // + slot * pl
     const bool pml = (d.flags & TF_PML) && inb;
@@ -390,12 +393,13 @@ EncodeTiledFn encode_fn() {
 
 void encode_one(CUtensorMap *m, const Grid &g, float *plane0, long long nplanes, int bz, int bx, int bp) {
   // plane0 points at the allocation base of the first plane; element (z, x, p) lives at plane0 + p*plane + SLACK + (x+XM)*P + z
-  const cuuint64_t dims[3] = {(cuuint64_t)g.P, (cuuint64_t)(g.nx + 2 * XM), (cuuint64_t)nplanes};
+  // the tensor ends at zlive: rows beyond it hold zeros for ever and are zero-filled by the TMA unit without a read
+  const cuuint64_t dims[3] = {(cuuint64_t)g.zlive, (cuuint64_t)(g.nx + 2 * XM), (cuuint64_t)nplanes};
   const cuuint64_t strides[2] = {(cuuint64_t)g.P * sizeof(float), (cuuint64_t)g.plane * sizeof(float)};
   const cuuint32_t box[3] = {(cuuint32_t)bz, (cuuint32_t)bx, (cuuint32_t)bp};
   const cuuint32_t es[3] = {1, 1, 1};
   CUresult r = encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, plane0 + SLACK, dims, strides, box, es,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, FWI_TMA_L2PROMO,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) throw Error(FWI_B200_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
 }

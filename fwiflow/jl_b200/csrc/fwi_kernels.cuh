@@ -49,6 +49,9 @@ struct Grid {
   long long plane;     // floats per plane (incl. margins and slack)
   long long origin;    // offset of (z=0,x=0) inside a plane allocation
   int az_hi, ax_hi;    // last active cell: nz-nPad-3, nx-3 (first active = 2)
+  int zlive;           // rows >= zlive (az_hi + 1 rounded up to a quad) are never updated: every field, CPML memory and
+                       // dt-scaled coefficient is identically zero there, so they are neither loaded (the TMA tensor
+                       // ends at zlive and zero-fills beyond it) nor stored
   int zlo, zhi, xlo, xhi;  // inner box (reconstruction / imaging region)
   int tiles_z, tiles_x;    // tile grid covering [0,nz) x [0,nx)
   float dt, rdz, rdx;      // 1/dz, 1/dx

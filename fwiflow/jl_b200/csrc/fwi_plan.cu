@@ -118,6 +118,9 @@ struct fwi_b200_plan {
   }
 };
 
+#ifndef FWI_SKIP_DEAD_ROWS
+#define FWI_SKIP_DEAD_ROWS 1
+#endif
 #ifndef FWI_ADJ_INDEP
 #define FWI_ADJ_INDEP 1
 #endif
@@ -143,6 +146,7 @@ void build_grid(const Para &p, Grid &g) {
   g.plane = (g.plane + 31) / 32 * 32;
   g.origin = SLACK + (long long)XM * g.P;
   g.az_hi = p.nz - p.nPad - 3;
+  g.zlive = FWI_SKIP_DEAD_ROWS ? std::min(p.nz, (g.az_hi + 1 + 3) / 4 * 4) : p.nz;
   g.ax_hi = p.nx - 3;
   g.zlo = p.nPml; g.zhi = p.nz - p.nPad - 1 - p.nPml;
   g.xlo = p.nPml; g.xhi = p.nx - 1 - p.nPml;
@@ -206,6 +210,8 @@ void upload_tables(fwi_b200_plan &pl) {
     // the reference stamps a 9x9 patch around the source (utilities.cu:529-536): keep it inside the grid
     if (s.z_src < 4 || s.z_src > g.nz - 5 || s.x_src < 4 || s.x_src > g.nx - 5)
       throw Error(FWI_B200_ERR_GEOM, "shot" + std::to_string(s.id) + ": source outside the padded grid");
+    if (s.z_src > g.az_hi)   // a source in the nPad rows never radiates (its cell is not updated); refuse it instead
+      throw Error(FWI_B200_ERR_GEOM, "shot" + std::to_string(s.id) + ": source inside the inactive nPad rows");
     sz[i] = s.z_src;
     sx[i] = s.x_src;
     const int nrec = (int)s.z_rec.size();
