@@ -1,127 +1,20 @@
-// Hand-written CUDA kernels (sm_100a) for the 2-D elastic FWI hot path.
-//
-// Three fused per-time-step kernels, each advancing a whole BATCH of shots per launch:
-//   fwd_step_kernel     stress + source + velocity + record (+ boundary-frame save)
-//                       replaces el_stress / add_source / el_velocity / recording / from_bnd x5
-//                       (reference: libCUFD.cu:202-240)
-//   rev_image_kernel    reverse velocity + frame restore + source removal + reverse stress
-//                       + frame restore + lambda/mu/rho imaging (deterministic gather)
-//                       replaces el_velocity(false) / to_bnd x5 / add_source(false) / el_stress(false)
-//                       (reference: libCUFD.cu:380-403)
-//   adj_step_kernel     source_grad + adjoint velocity + residual injection + adjoint stress
-//                       replaces source_grad / el_velocity_adj / res_injection / el_stress_adj
-//                       (reference: libCUFD.cu:376,405-427)
-// All three use shared-memory tiles with halos (the second half-step is computed from the
-// first half-step's tile without a round trip to HBM), staged with cp.async, one float4 "quad"
-// of 4 consecutive z cells per thread (16-byte loads / stores everywhere), ping-pong state
-// buffers, and the reference's arithmetic (float storage; with FWI_FP64_PROMOTE=1 the double
-// promotion of the reference's C expressions is reproduced).  Derivatives multiply by 1/dz
-// instead of dividing (<= 1 ulp per derivative).
+// Support kernels of the FWI hot path (sm_100a): everything that runs once per gradient or once per shot rather than
+// once per time step.  The three time-step kernels live in fwi_forward.cu / fwi_backward.cu.
+//   model_transpose / model_derive   caller's double row-major MPa -> float planes, derived coefficients, max cp
+//                                    (reference: Model.cu:36-87, utilities.cu:109-152)
+//   residual / sum_partials / misfit taper or per-trace windows, res = obs - syn, sum res^2
+//                                    (reference: libCUFD.cu:254-330, utilities.cu:154-205,654-747)
+//   traces_to_rt                     [step][receiver] -> [receiver][time] (Shot<id>.bin layout)
+//   finalize                         per-slot imaging accumulators -> [grad_lambda|grad_mu|grad_den|misfit], with the
+//                                    reference's 4-point spray applied as a gather (el_stress.cu:113-124,
+//                                    el_velocity.cu:101-110)
 #include <cstdio>
 #include <cstdlib>
 
 #include "fwi_kernels.cuh"
 
-#ifndef FWI_FP64_PROMOTE
-#define FWI_FP64_PROMOTE 0
-#endif
-
 namespace fwi {
 namespace {
-
-constexpr float C1 = 1.125f;
-constexpr float C2 = (float)(1.0 / 24.0);
-constexpr float SRC_SCALE = 2250000.0f;  // pow(1500,2)  utilities.cu:528
-
-__device__ __forceinline__ float *plane_of(float *state, const Grid &g, int shot, int slot) {
-  return state + ((long long)shot * S_COUNT + slot) * g.plane + g.origin;
-}
-
-// staggered first derivatives on a tile pointer p (center), stride s
-__device__ __forceinline__ float d_minus(const float *p, int s, float rh) {
-  return (C1 * (p[0] - p[-s]) - C2 * (p[s] - p[-2 * s])) * rh;
-}
-__device__ __forceinline__ float d_plus(const float *p, int s, float rh) {
-  return (C1 * (p[s] - p[0]) - C2 * (p[2 * s] - p[-s])) * rh;
-}
-// adjoint-kernel spelling (el_stress_adj.cu:54-61): (-c1*(..) + c2*(..))/h
-__device__ __forceinline__ float ad_minus(const float *p, int s, float rh) {
-  return (-C1 * (p[0] - p[-s]) + C2 * (p[s] - p[-2 * s])) * rh;
-}
-__device__ __forceinline__ float ad_plus(const float *p, int s, float rh) {
-  return (-C1 * (p[s] - p[0]) + C2 * (p[2 * s] - p[-s])) * rh;
-}
-__device__ __forceinline__ float ad_minus4(float m2, float m1, float c0, float p1, float rh) {
-  return (-C1 * (c0 - m1) + C2 * (p1 - m2)) * rh;
-}
-__device__ __forceinline__ float ad_plus4(float m1, float c0, float p1, float p2, float rh) {
-  return (-C1 * (p1 - c0) + C2 * (p2 - m1)) * rh;
-}
-
-// sigma += ((lam+2mu) e1 + lam e2) dt  with the reference's promotion (el_stress.cu:66-67)
-__device__ __forceinline__ float stress_inc(float s, float lam, float mu, float e1, float e2, float dt, float sign) {
-#if FWI_FP64_PROMOTE
-  const double l2m = (double)lam + 2.0 * (double)mu;
-  const double t = (l2m * (double)e1 + (double)(lam * e2)) * (double)dt;
-  return (float)((double)s + (double)sign * t);
-#else
-  return s + sign * (((lam + 2.0f * mu) * e1 + lam * e2) * dt);
-#endif
-}
-
-__device__ __forceinline__ bool z_in_pml(const Grid &g, int z) { return z < g.nPml || z > g.nz - g.nPml - g.nPad - 1; }
-__device__ __forceinline__ bool x_in_pml_s(const Grid &g, int x) { return x < g.nPml || x > g.nx - g.nPml - 1; }
-__device__ __forceinline__ bool x_in_pml_v(const Grid &g, int x) { return x < g.nPml || x > g.nx - g.nPml; }
-__device__ __forceinline__ bool is_active(const Grid &g, int z, int x) {
-  return z >= 2 && z <= g.az_hi && x >= 2 && x <= g.ax_hi;
-}
-__device__ __forceinline__ bool in_box(const Grid &g, int z, int x) {
-  return z >= g.zlo && z <= g.zhi && x >= g.xlo && x <= g.xhi;
-}
-
-// =================================================================================================
-// forward step: one float4 "quad" (4 consecutive z cells) per thread, 16 quads = one sigma-tile
-// column per half-warp.  Velocity tile (halo rounded up to whole quads) staged with cp.async.
-// =================================================================================================
-struct F4 {
-  float v[4];
-};
-__device__ __forceinline__ F4 ld4(const float *p) {
-  const float4 t = *reinterpret_cast<const float4 *>(p);
-  return F4{{t.x, t.y, t.z, t.w}};
-}
-__device__ __forceinline__ void st4(float *p, const F4 &a) {
-  *reinterpret_cast<float4 *>(p) = make_float4(a.v[0], a.v[1], a.v[2], a.v[3]);
-}
-__device__ __forceinline__ void cp_async16(float *smem_dst, const float *gsrc) {
-  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc));
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
-
-// 7 consecutive samples w[0..6] = f[z-2 .. z+4]  ->  D-z at the 4 cells z..z+3
-__device__ __forceinline__ void dz_minus4(const F4 &A, const F4 &B, const F4 &C, float rh, float *out) {
-  const float w[7] = {A.v[2], A.v[3], B.v[0], B.v[1], B.v[2], B.v[3], C.v[0]};
-#pragma unroll
-  for (int k = 0; k < 4; k++) out[k] = (C1 * (w[k + 2] - w[k + 1]) - C2 * (w[k + 3] - w[k])) * rh;
-}
-// samples u[0..6] = f[z-1 .. z+5]  ->  D+z at the 4 cells
-__device__ __forceinline__ void dz_plus4(const F4 &A, const F4 &B, const F4 &C, float rh, float *out) {
-  const float u[7] = {A.v[3], B.v[0], B.v[1], B.v[2], B.v[3], C.v[0], C.v[1]};
-#pragma unroll
-  for (int k = 0; k < 4; k++) out[k] = (C1 * (u[k + 2] - u[k + 1]) - C2 * (u[k + 3] - u[k])) * rh;
-}
-// columns x-2, x-1, x, x+1 -> D-x ;  columns x-1, x, x+1, x+2 -> D+x   (same expression shape)
-__device__ __forceinline__ void dx4(const F4 &m2, const F4 &m1, const F4 &c0, const F4 &p1, float rh, float *out) {
-#pragma unroll
-  for (int k = 0; k < 4; k++) out[k] = (C1 * (c0.v[k] - m1.v[k]) - C2 * (p1.v[k] - m2.v[k])) * rh;
-}
-
-constexpr int QS = (TILE_Z + 8) / 4;      // 16 quads: sigma-tile rows z0-4 .. z0+TILE_Z+3
-constexpr int QV = (TILE_Z + 16) / 4;     // 18 quads: velocity-tile rows z0-8 .. z0+TILE_Z+7
-constexpr int VP = QV * 4, SP = QS * 4;   // row pitches (floats)
-constexpr int VC = TILE_X + 6, SC = TILE_X + 4;
-static_assert(TILE_Z % 4 == 0 && QS == 16, "half-warp per sigma column");
 
 // =================================================================================================
 // model preparation

@@ -20,7 +20,6 @@ constexpr int XM = 4;        // margin columns in x
 constexpr int SLACK = 256;   // floats before / after each plane
 constexpr int TILE_Z = 56;   // owner tile (z fastest): 14 float4 quads, 7 sectors of 32 B
 constexpr int TILE_X = 28;   // owner tile columns: stress region 32 columns, velocity-input region 34
-constexpr int NTHREADS = 256;     // two-kernel backward path
 constexpr int NT_STEP = 512;      // persistent TMA-fed step kernels: 16 quads x 32 columns, one quad per thread
 
 // state slots
