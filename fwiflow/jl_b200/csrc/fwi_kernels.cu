@@ -289,6 +289,7 @@ void launch_misfit(const float *j_shot, int n, float *misfit_half, cudaStream_t 
 }
 
 void launch_traces_to_rt(const float *tr, float *rt, int nrec, int nrp, int nSteps, cudaStream_t s) {
+  if (nrec <= 0) return;   // a shot without receivers records nothing (empty Shot<id>.bin)
   dim3 tb(32, 8);
   dim3 tg((nSteps + 31) / 32, (nrec + 31) / 32);
   traces_to_rt_kernel<<<tg, tb, 0, s>>>(tr, rt, nrec, nrp, nSteps);

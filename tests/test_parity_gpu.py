@@ -101,6 +101,46 @@ def test_ragged_receivers_against_oracle(ops):
     assert rel(g_b["grad_stf"], g_or["grad_stf"]) <= 5e-3
 
 
+def _collision_case():
+    """receiver collisions and an empty shot: two receivers in the SAME cell (their residuals must both be injected),
+    a receiver on the source cell, receivers inside the absorbing layers, and a shot without any receiver."""
+    from fwiflow.jl_b200 import synthetic
+    c = synthetic.case_small("collide", nz=50, nx=70, nSteps=400, nshots=2, seed=5)
+    wd = tempfile.mkdtemp(prefix="collide_")
+    para = c.write_files(wd)
+    sv = json.loads(open(os.path.join(wd, "survey_file.json")).read())
+    zs, xs = sv["shot0"]["z_src"], sv["shot0"]["x_src"]
+    sv["shot0"]["z_rec"] = [5, 5, 9, zs, -10, 20, 20]
+    sv["shot0"]["x_rec"] = [7, 7, 20, xs, 30, -12, 80]        # (-10, 30): top layer; (20, -12), (20, 80): side layers
+    sv["shot0"]["nrec"] = 7
+    sv["shot1"]["z_rec"], sv["shot1"]["x_rec"], sv["shot1"]["nrec"] = [], [], 0
+    open(os.path.join(wd, "survey_file.json"), "w").write(json.dumps(sv))
+    return c, para
+
+
+def test_colliding_and_empty_receivers_against_oracle(ops):
+    from oracle import oracle_py as op
+    c, para = _collision_case()
+    ids = np.array([0, 1], np.int32)
+    lam, mu, rho = c.moduli("true")
+    lam0, mu0, rho0 = c.moduli("init")
+    mine = b200_cufd(2, lam, mu, rho, c.stf, ids, para)
+    obs = [t.copy() for t in mine["syn"]]
+    assert [t.shape for t in obs] == [(7, 400), (0, 400)]
+    assert np.array_equal(obs[0][0], obs[0][1]) and np.abs(obs[0][0]).max() > 0      # same cell, same trace
+    orc = op.oracle_cufd(2, lam, mu, rho, c.stf, ids, para)
+    assert rel(obs[0][:, 1:], orc["syn"][0][:, 1:]) <= TOL_TRACE
+    g_or = op.oracle_cufd(1, lam0, mu0, rho0, c.stf, ids, para)
+    j_or = op.oracle_cufd(0, lam0, mu0, rho0, c.stf, ids, para)["misfit"]
+    g_b = b200_cufd(1, lam0, mu0, rho0, c.stf, ids, para)
+    j_b = b200_cufd(0, lam0, mu0, rho0, c.stf, ids, para)["misfit"]
+    assert abs(j_b - j_or) <= TOL_MISFIT * j_or
+    far = away_from_sources(c)
+    for k in ("grad_lambda", "grad_mu", "grad_den"):
+        assert rel(g_b[k][far], g_or[k][far]) <= TOL_GRAD, k
+    assert np.all(g_b["grad_stf"][1] == 0.0)                       # the shot without receivers has no adjoint source
+
+
 def test_shot_and_receiver_indices_bit_exact(ops):
     """Src_Rec.cu:86-113: json + nPml, row order = order in the file; file names Shot<id>.bin."""
     c, para = _ragged_case()
