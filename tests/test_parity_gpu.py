@@ -141,6 +141,32 @@ def test_colliding_and_empty_receivers_against_oracle(ops):
     assert np.all(g_b["grad_stf"][1] == 0.0)                       # the shot without receivers has no adjoint source
 
 
+def test_dense_receiver_block_against_oracle(ops):
+    """More receivers in one tile than the CTA has threads (a 36 x 26 block on every cell, 936 receivers): the
+    recording and injection loops run several rounds per tile and the injection table takes one entry per cell."""
+    from oracle import oracle_py as op
+    from fwiflow.jl_b200 import synthetic
+    c = synthetic.case_small("dense", nz=50, nx=70, nSteps=300, nshots=1, seed=9)
+    wd = tempfile.mkdtemp(prefix="dense_")
+    para = c.write_files(wd)
+    sv = json.loads(open(os.path.join(wd, "survey_file.json")).read())
+    zz, xx = np.meshgrid(np.arange(6, 42), np.arange(10, 36), indexing="ij")
+    sv["shot0"]["z_rec"], sv["shot0"]["x_rec"] = zz.ravel().tolist(), xx.ravel().tolist()
+    sv["shot0"]["nrec"] = int(zz.size)
+    open(os.path.join(wd, "survey_file.json"), "w").write(json.dumps(sv))
+    ids = np.array([0], np.int32)
+    lam, mu, rho = c.moduli("true")
+    lam0, mu0, rho0 = c.moduli("init")
+    mine = b200_cufd(2, lam, mu, rho, c.stf, ids, para)["syn"][0].copy()
+    orc = op.oracle_cufd(2, lam, mu, rho, c.stf, ids, para)["syn"][0]
+    assert mine.shape == (936, 300) and rel(mine[:, 1:], orc[:, 1:]) <= TOL_TRACE
+    g_or = op.oracle_cufd(1, lam0, mu0, rho0, c.stf, ids, para)
+    g_b = b200_cufd(1, lam0, mu0, rho0, c.stf, ids, para)
+    far = away_from_sources(c)
+    for k in ("grad_lambda", "grad_mu", "grad_den"):
+        assert rel(g_b[k][far], g_or[k][far]) <= TOL_GRAD, k
+
+
 def test_shot_and_receiver_indices_bit_exact(ops):
     """Src_Rec.cu:86-113: json + nPml, row order = order in the file; file names Shot<id>.bin."""
     c, para = _ragged_case()
