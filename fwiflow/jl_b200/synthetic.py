@@ -204,6 +204,26 @@ def case_small_windows(name="small_windows", seed=11):
     return c
 
 
+def case_aniso(name="aniso", seed=21):
+    """Unequal grid spacings (dz = 16 m, dx = 24 m), a 20-cell absorbing layer, receivers on a dipping line and two
+    sources at different depths: everything the other golden cases keep equal or default."""
+    nz, nx, nPml, nSteps, dt, f0 = 44, 66, 20, 520, 0.0016, 7.0
+    rng = np.random.default_rng(seed)
+    cp = layered_cp(nz, nx, 3, rng, vmax=3200.0)
+    cp0 = smooth_1d(cp, 3.0)
+    cs, rho = _elastic_from_cp(cp)
+    cs0, rho0 = _elastic_from_cp(cp0)
+    x_rec = np.arange(3, nx - 3, dtype=np.int64)
+    z_rec = 2 + (x_rec // 12)
+    c = Case(name=name, nz=nz, nx=nx, dz=16.0, dx=24.0, dt=dt, nSteps=nSteps, f0=f0, z_src=np.array([3, 9]),
+             x_src=np.array([12, 50]), z_rec=z_rec, x_rec=x_rec, nPml=nPml)
+    pad = lambda a: symmetric_pad(a, c.nPml, c.nPad)
+    c.cp_true, c.cs_true, c.rho_true = pad(cp), pad(cs), pad(rho)
+    c.cp_init, c.cs_init, c.rho_init = pad(cp0), pad(cs0), pad(rho0)
+    c.stf = np.repeat(sourceGene(f0, nSteps, dt), 2, axis=0)
+    return c
+
+
 def case_gradtest_small(n=110, nSteps=500):
     """gradtest.jl-like: grid given INCLUDING the PML, nPad = 0, nz not a multiple of 32,
     one centre source, a lattice of receivers throughout the volume

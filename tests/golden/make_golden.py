@@ -32,6 +32,7 @@ def golden_cases():
         "small_acoustic": syn.case_small("small_acoustic", elastic=False, seed=7),
         "gradtest": syn.case_gradtest_small(n=112, nSteps=500),
         "small_windows": syn.case_small_windows(),
+        "aniso": syn.case_aniso(),
     }
 
 
