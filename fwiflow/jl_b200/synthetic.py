@@ -160,6 +160,8 @@ def case_c2(nshots=30, nSteps=2000):
     xs = np.arange(4, 384, 13, dtype=np.int64)[:nshots] if nshots <= 30 else c.x_src
     c.x_src = xs
     c.z_src = np.full(xs.shape, 2, dtype=np.int64)
+    c.x_rec = np.arange(3, 382, dtype=np.int64)          # x = 3..381 at z = 2: the 379 receivers of src/FWI.jl:90
+    c.z_rec = np.full(c.x_rec.shape, 2, dtype=np.int64)
     c.stf = np.repeat(sourceGene(4.5, nSteps, 0.0025), len(xs), axis=0)
     return c
 

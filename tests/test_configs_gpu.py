@@ -28,6 +28,35 @@ def ops():
     o.release()
 
 
+# ---- configs[1] at FULL record length, directly against the reference's own op -------------------------------------
+def test_c2_full_length_against_reference_op(ops):
+    """C2 geometry, 2000 steps, 4 of the 30 shots: traces, misfit and gradients of the CUDA path against the unmodified
+    reference op rebuilt for this box (oracle/_ref/libCUFD_ref.so -- test infrastructure; it travels with the repo)."""
+    from oracle import oracle_py as op
+    from fwiflow.jl_b200 import synthetic
+    if not op.ref_available():
+        pytest.skip("oracle/_ref/libCUFD_ref.so not built")
+    c = synthetic.case_c2(nshots=30, nSteps=2000)
+    ids = np.array([0, 9, 17, 29], dtype=np.int32)
+    lam, mu, rho = c.moduli("true")
+    lam0, mu0, rho0 = c.moduli("init")
+    para_r = c.write_files(tempfile.mkdtemp(prefix="c2ref_"))
+    para_b = c.write_files(tempfile.mkdtemp(prefix="c2b200_"))
+    ref_obs = op.ref_cufd(2, lam, mu, rho, c.stf, ids, para_r)["syn"]
+    b_obs = b200_cufd(2, lam, mu, rho, c.stf, ids, para_b)["syn"]
+    for a, b in zip(b_obs, ref_obs):
+        assert a.shape == b.shape == (379, 2000) and rel(a[:, 1:], b[:, 1:]) <= TOL_TRACE
+    j_r = op.ref_cufd(0, lam0, mu0, rho0, c.stf, ids, para_r)["misfit"]
+    j_b = b200_cufd(0, lam0, mu0, rho0, c.stf, ids, para_b)["misfit"]
+    assert abs(j_b - j_r) <= 1e-4 * j_r
+    g_r = op.ref_cufd(1, lam0, mu0, rho0, c.stf, ids, para_r)
+    g_b = b200_cufd(1, lam0, mu0, rho0, c.stf, ids, para_b)
+    inner = interior_mask(c)
+    for k in ("grad_lambda", "grad_mu", "grad_den"):
+        assert rel(g_b[k][inner], g_r[k][inner]) <= TOL_GRAD, k
+        assert rel(g_b[k], g_r[k]) <= 5 * TOL_GRAD, k          # incl. the ill-conditioned cells at the sources
+
+
 # ---- configs[2]: 1000 x 3000 model, gradient with boundary-saving checkpoints -----------------------------------
 def test_c3_grid_properties(ops):
     from fwiflow.jl_b200 import synthetic
