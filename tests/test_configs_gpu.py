@@ -57,6 +57,31 @@ def test_c2_full_length_against_reference_op(ops):
         assert rel(g_b[k], g_r[k]) <= 5 * TOL_GRAD, k          # incl. the ill-conditioned cells at the sources
 
 
+# ---- the large grids of configs[2] and configs[4], one shot, directly against the reference's own op ---------------
+@pytest.mark.parametrize("which,nsteps", [("c3", 900), ("c5", 260)])
+def test_large_grids_against_reference_op(ops, which, nsteps):
+    from oracle import oracle_py as op
+    from fwiflow.jl_b200 import synthetic
+    from fwiflow.jl_b200.utils import sourceGene
+    if not op.ref_available():
+        pytest.skip("oracle/_ref/libCUFD_ref.so not built")
+    c = {"c3": synthetic.case_c3, "c5": synthetic.case_c5}[which](nshots=1, nSteps=nsteps)
+    c.stf = sourceGene(15.0, nsteps, c.dt)                 # early onset: the short record carries reflections
+    ids = np.array([0], dtype=np.int32)
+    lam, mu, rho = c.moduli("true")
+    lam0, mu0, rho0 = 0.96 * lam, 0.97 * mu, rho
+    para_r = c.write_files(tempfile.mkdtemp(prefix=f"{which}ref_"))
+    para_b = c.write_files(tempfile.mkdtemp(prefix=f"{which}b200_"))
+    ref_obs = op.ref_cufd(2, lam, mu, rho, c.stf, ids, para_r)["syn"][0]
+    b_obs = b200_cufd(2, lam, mu, rho, c.stf, ids, para_b)["syn"][0]
+    assert np.abs(ref_obs).max() > 0 and rel(b_obs[:, 1:], ref_obs[:, 1:]) <= TOL_TRACE
+    g_r = op.ref_cufd(1, lam0, mu0, rho0, c.stf, ids, para_r)
+    g_b = b200_cufd(1, lam0, mu0, rho0, c.stf, ids, para_b)
+    far = interior_mask(c)
+    for k in ("grad_lambda", "grad_mu", "grad_den"):
+        assert np.abs(g_r[k]).max() > 0 and rel(g_b[k][far], g_r[k][far]) <= TOL_GRAD, k
+
+
 # ---- configs[2]: 1000 x 3000 model, gradient with boundary-saving checkpoints -----------------------------------
 def test_c3_grid_properties(ops):
     from fwiflow.jl_b200 import synthetic
