@@ -40,6 +40,9 @@ namespace {
 #ifndef FWI_TMA_L2PROMO
 #define FWI_TMA_L2PROMO CU_TENSOR_MAP_L2_PROMOTION_L2_128B
 #endif
+#ifndef FWD_SNEW_SINGLE
+#define FWD_SNEW_SINGLE 1   // one new-stress tile handed over with an arrive / wait pair: 113 KB of shared memory -> 124 KB of L1
+#endif
 #ifndef FWI_ZIGZAG
 #define FWI_ZIGZAG 1
 #endif
@@ -53,7 +56,8 @@ constexpr int S_BYTES = 3 * SCOLS * SPITCH * 4;
 constexpr int STAGE_BYTES = V_BYTES + S_BYTES;
 constexpr int SNEW_BYTES = 3 * SCOLS * SPITCH * 4;
 constexpr int DESC_BYTES = 64;
-constexpr size_t FWD_SMEM = (size_t)NS * STAGE_BYTES + 2 * SNEW_BYTES + (NS + 1) * DESC_BYTES + NS * 8 + 128;
+constexpr int NSNEW = FWD_SNEW_SINGLE ? 1 : 2;
+constexpr size_t FWD_SMEM = (size_t)NS * STAGE_BYTES + NSNEW * SNEW_BYTES + (NS + 1) * DESC_BYTES + (NS + 1) * 8 + 128;
 static_assert(V_BYTES % 128 == 0 && S_BYTES % 128 == 0, "TMA destination alignment");
 
 template <bool SAVE>
@@ -61,8 +65,8 @@ __global__ void __launch_bounds__(NTHREADS_FWD, 1) fwd_step_kernel(const __grid_
   extern __shared__ unsigned char smem_raw[];
   unsigned char *base = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
   float *s_new_base = reinterpret_cast<float *>(base + NS * STAGE_BYTES);                     // [2][3][SCOLS][SPITCH]
-  TileDesc *sdesc = reinterpret_cast<TileDesc *>(base + NS * STAGE_BYTES + 2 * SNEW_BYTES);   // [NS + 1]
-  uint64_t *full = reinterpret_cast<uint64_t *>(base + NS * STAGE_BYTES + 2 * SNEW_BYTES + (NS + 1) * DESC_BYTES);
+  TileDesc *sdesc = reinterpret_cast<TileDesc *>(base + NS * STAGE_BYTES + NSNEW * SNEW_BYTES);   // [NS + 1]
+  uint64_t *full = reinterpret_cast<uint64_t *>(base + NS * STAGE_BYTES + NSNEW * SNEW_BYTES + (NS + 1) * DESC_BYTES);   // [NS] ring + [1] "s_new free"
 
   const Grid &g = a.g;
   const int tid = threadIdx.x;
@@ -81,6 +85,7 @@ __global__ void __launch_bounds__(NTHREADS_FWD, 1) fwd_step_kernel(const __grid_
   pdl_launch_dependents();
   if (tid == 0) {
     for (int s = 0; s < NS; s++) mbar_init(&full[s], 1);
+    mbar_init(&full[NS], NCOMPUTE / 32);   // "every warp has finished the velocity half of the previous item"
     fence_barrier_init();
   }
   __syncthreads();
@@ -161,7 +166,7 @@ __global__ void __launch_bounds__(NTHREADS_FWD, 1) fwd_step_kernel(const __grid_
   }
 
   pdl_wait();
-  int stage = 0, phase = 0, nb = 0, ds = 0;
+  int stage = 0, phase = 0, nb = 0, ds = 0, kdone = 0;
   for (int item = blockIdx.x; item < nitems; item += stride) {
     mbar_wait(&full[stage], phase);
     const TileDesc d = sdesc[ds];
@@ -186,7 +191,7 @@ __global__ void __launch_bounds__(NTHREADS_FWD, 1) fwd_step_kernel(const __grid_
     const unsigned char *sb = base + stage * STAGE_BYTES;
     const float *sv = reinterpret_cast<const float *>(sb);             // [2][VCOLS][VPITCH]
     const float *so = reinterpret_cast<const float *>(sb + V_BYTES);   // [3][SCOLS][SPITCH]
-    float *s_new = s_new_base + nb * (SNEW_BYTES / 4);
+    float *s_new = s_new_base + (FWD_SNEW_SINGLE ? 0 : nb) * (SNEW_BYTES / 4);
 
     // ---- stress on 16 quads x 32 columns (el_stress.cu:50-88) ----
     const float *vzc = sv + (c + 1) * VPITCH + 4 * (q + 1);
@@ -260,6 +265,9 @@ __global__ void __launch_bounds__(NTHREADS_FWD, 1) fwd_step_kernel(const __grid_
         sxx.v[kk] = (kk == ks) ? (float)((double)sxx.v[kk] + axx) : sxx.v[kk];
       }
     }
+    // single-buffered tile: the velocity half of the previous item (and its recording) has read it everywhere; the
+    // arrive was posted at the end of that item, a whole stress half ago
+    if (FWD_SNEW_SINGLE && kdone > 0) mbar_wait(&full[NS], (kdone - 1) & 1);
     st4(s_new + sj, szz);
     st4(s_new + SCOLS * SPITCH + sj, sxx);
     st4(s_new + 2 * SCOLS * SPITCH + sj, sxz);
@@ -352,6 +360,11 @@ __global__ void __launch_bounds__(NTHREADS_FWD, 1) fwd_step_kernel(const __grid_
     if (more) {
       byadt = ld4(mq_next + 3 * pl);
       bybdt = ld4(mq_next + 4 * pl);
+    }
+    if (FWD_SNEW_SINGLE) {   // this warp is done with the new-stress tile
+      __syncwarp();
+      if ((tid & 31) == 0) mbar_arrive(&full[NS]);
+      kdone++;
     }
     nb ^= 1;
     if (++ds == NS + 1) ds = 0;
