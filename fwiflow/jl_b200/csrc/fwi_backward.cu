@@ -42,6 +42,9 @@ namespace {
 #ifndef FWI_ZIGZAG
 #define FWI_ZIGZAG 1
 #endif
+#ifndef REV_LEAN_AUTO
+#define REV_LEAN_AUTO 1
+#endif
 #ifndef ADJ_SPLIT
 #define ADJ_SPLIT 1   // single-buffered phi / injection tiles are handed over with an arrive / wait pair instead of a block barrier
 #endif
@@ -53,18 +56,33 @@ constexpr int RV_BYTES = 2 * SCOLS * SPITCH * 4;   // velocity pair, rows z0-4..
 constexpr int RSTAGE_BYTES = RW_BYTES + RV_BYTES;
 constexpr int SV_BYTES = 2 * SCOLS * SPITCH * 4;   // rewound velocities
 constexpr int NS = REV_NS;   // ring stages of the reverse kernel
-constexpr int FRM_BYTES = NCOMPUTE * 3 * 16;       // per-thread landing zone of the quad's saved stress frame values
-constexpr size_t REV_SMEM = (size_t)NS * RSTAGE_BYTES + 2 * SV_BYTES + FRM_BYTES + (NS + 1) * sizeof(TileDesc) + NS * 8 + 128;
+constexpr int NOWN = (TILE_Z / 4) * TILE_X;        // 392 owner quads per tile
+// Two builds of the reverse kernel.  LEAN = false: double-buffered rewound-velocity tile, one landing slot per thread
+// for the saved stress frame values (152.7 KB of shared memory, 92 KB of L1).  LEAN = true: ONE velocity tile handed
+// over with an arrive / wait pair at the top of every item and landing slots for the owner quads only (130.5 KB ->
+// the 132 KB carve-out -> 124 KB of L1).  The wait at the top costs a little where the kernel is latency-bound
+// (C2: 42.7 -> 44.0 us), the larger L1 wins where it is bound by the streams of its direct loads (C3: 482 -> 461 us);
+// launch_reverse_imaging picks by the size of the working set.
+template <bool LEAN> constexpr int frm_bytes() { return (LEAN ? NOWN : NCOMPUTE) * 3 * 16; }
+template <bool LEAN> constexpr size_t rev_smem() {
+  return (size_t)NS * RSTAGE_BYTES + (LEAN ? 1 : 2) * SV_BYTES + frm_bytes<LEAN>() + (NS + 1) * sizeof(TileDesc) + (NS + 1) * 8 + 128;
+}
+constexpr size_t REV_SMEM = rev_smem<false>();
 static_assert(RW_BYTES % 128 == 0 && RV_BYTES % 128 == 0, "TMA destination alignment");
 
+template <bool LEAN>
 __global__ void __launch_bounds__(NCOMPUTE, 1)
 rev_image_kernel(const __grid_constant__ BwdArgs a, int tz_first, int tx_first, int ntz, int ntiles) {
+  constexpr int NSV = LEAN ? 1 : 2;
+  constexpr int NFRM = LEAN ? NOWN : NCOMPUTE;
+  constexpr int FRM_BYTES = NFRM * 3 * 16;
   extern __shared__ unsigned char smem_raw[];
   unsigned char *base = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
   float *s_v_base = reinterpret_cast<float *>(base + NS * RSTAGE_BYTES);                            // [2][2][SCOLS][SPITCH]
-  float *s_frm = reinterpret_cast<float *>(base + NS * RSTAGE_BYTES + 2 * SV_BYTES);                // [3][NCOMPUTE] quads: szz sxx sxz
-  TileDesc *sdesc = reinterpret_cast<TileDesc *>(base + NS * RSTAGE_BYTES + 2 * SV_BYTES + FRM_BYTES);   // [NS + 1]
-  uint64_t *full = reinterpret_cast<uint64_t *>(base + NS * RSTAGE_BYTES + 2 * SV_BYTES + FRM_BYTES + (NS + 1) * sizeof(TileDesc));
+  float *s_frm = reinterpret_cast<float *>(base + NS * RSTAGE_BYTES + NSV * SV_BYTES);              // [3][NFRM] quads: szz sxx sxz
+  unsigned char *rtail = base + NS * RSTAGE_BYTES + NSV * SV_BYTES + FRM_BYTES;
+  TileDesc *sdesc = reinterpret_cast<TileDesc *>(rtail);   // [NS + 1]
+  uint64_t *full = reinterpret_cast<uint64_t *>(rtail + (NS + 1) * sizeof(TileDesc));   // [NS] ring + [1] "velocity tile free"
 
   const Grid &g = a.g;
   const int tid = threadIdx.x;
@@ -79,6 +97,7 @@ rev_image_kernel(const __grid_constant__ BwdArgs a, int tz_first, int tx_first, 
   //  prologue, so it may only be let loose once this grid knows that the previous adjoint step has completed)
   if (tid == 0) {
     for (int s = 0; s < NS; s++) mbar_init(&full[s], 1);
+    mbar_init(&full[NS], NCOMPUTE / 32);   // LEAN: "every warp has finished reading the velocity tile of the previous item"
     fence_barrier_init();
   }
   __syncthreads();
@@ -131,7 +150,7 @@ rev_image_kernel(const __grid_constant__ BwdArgs a, int tz_first, int tx_first, 
   const int sj = c * SPITCH + 4 * q;
   const int gx_max = g.nx + XM - 1;
 
-  int stage = 0, phase = 0, nb = 0, ds = 0;
+  int stage = 0, phase = 0, nb = 0, ds = 0, kdone = 0;
   for (int item = blockIdx.x; item < nitems; item += stride) {
     const TileDesc d = sdesc[ds];   // written by the producer >= 1 block barrier ago
     const int gz = d.z0 - 4 + 4 * q, gx = d.x0 - 2 + c;
@@ -151,14 +170,18 @@ rev_image_kernel(const __grid_constant__ BwdArgs a, int tz_first, int tx_first, 
     // landing zone.  State slots hold F_VZ F_VX F_SZZ F_SXX F_SXZ in that order.
     int fq = -1;
     if ((d.flags & TF_FRAME) && in_rect) fq = frame_quad(g, gz, gx);
-    float *s_v = s_v_base + nb * (SV_BYTES / 4);
-    float *my_frm = s_frm + 4 * tid;
+    float *s_v = s_v_base + (LEAN ? 0 : nb) * (SV_BYTES / 4);
+    float *my_frm = s_frm + 4 * (LEAN ? (q - 1) + (TILE_Z / 4) * (c - 2) : tid);   // LEAN: owner quads only (nobody else uses them)
+    // LEAN: the frame copies below are the first writes into the single velocity tile
+    if (LEAN && kdone > 0) mbar_wait(&full[NS], (kdone - 1) & 1);
     if (fq >= 0) {
       const float *frm = a.frames + ((long long)d.shot * g.nSteps + a.it) * 5 * g.f_len + 4 * fq;
       cp_async16(s_v + sj, frm + F_VZ * g.f_len);
       cp_async16(s_v + SCOLS * SPITCH + sj, frm + F_VX * g.f_len);
+      if (!LEAN || inner) {
 #pragma unroll
-      for (int f = 0; f < 3; f++) cp_async16(my_frm + f * 4 * NCOMPUTE, frm + (F_SZZ + f) * g.f_len);
+        for (int f = 0; f < 3; f++) cp_async16(my_frm + f * 4 * NFRM, frm + (F_SZZ + f) * g.f_len);
+      }
     }
 
     // global operands of the velocity half, requested before waiting for the ring: buoyancies, adjoint velocities
@@ -277,12 +300,17 @@ rev_image_kernel(const __grid_constant__ BwdArgs a, int tz_first, int tx_first, 
       }
       if (fq >= 0) {  // to_bnd(sigma) (libCUFD.cu:403)
         szz = ld4(my_frm);
-        sxx = ld4(my_frm + 4 * NCOMPUTE);
-        sxz = ld4(my_frm + 8 * NCOMPUTE);
+        sxx = ld4(my_frm + 4 * NFRM);
+        sxz = ld4(my_frm + 8 * NFRM);
       }
       st4(fo + F_SZZ * pl, szz);
       st4(fo + F_SXX * pl, sxx);
       st4(fo + F_SXZ * pl, sxz);
+    }
+    if (LEAN) {   // this warp is done with the velocity tile
+      __syncwarp();
+      if ((tid & 31) == 0) mbar_arrive(&full[NS]);
+      kdone++;
     }
     nb ^= 1;
     if (++ds == NS + 1) ds = 0;
@@ -693,7 +721,8 @@ size_t reverse_smem_bytes() { return REV_SMEM; }
 size_t adjoint_smem_bytes() { return ADJ_SMEM; }
 
 void configure_backward_kernels() {
-  cudaFuncSetAttribute(rev_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)REV_SMEM);
+  cudaFuncSetAttribute(rev_image_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rev_smem<false>());
+  cudaFuncSetAttribute(rev_image_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rev_smem<true>());
   cudaFuncSetAttribute(adj_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ADJ_SMEM);
 }
 
@@ -716,7 +745,13 @@ void launch_reverse_imaging(const BwdArgs &a_in, cudaStream_t s) {
   const int ntz = tz1 - tz0 + 1, ntx = tx1 - tx0 + 1;
   const int nitems = a.batch * ntz * ntx;
   const int blocks = nitems < sm_count() ? nitems : sm_count();
-  launch_step(rev_image_kernel, blocks, NCOMPUTE, REV_SMEM, s, a, tz0, tx0, ntz, ntz * ntx);
+  // working set of one launch = forward + adjoint fields and accumulators of every box cell of the batch; beyond a few
+  // L2 capacities the kernel is bound by its streams and wants the larger L1 (see rev_smem)
+  const double working_set = 100.0 * a.batch * (double)(g.zhi - g.zlo + 1) * (g.xhi - g.xlo + 1);
+  if (REV_LEAN_AUTO && working_set > 512e6)
+    launch_step(rev_image_kernel<true>, blocks, NCOMPUTE, rev_smem<true>(), s, a, tz0, tx0, ntz, ntz * ntx);
+  else
+    launch_step(rev_image_kernel<false>, blocks, NCOMPUTE, rev_smem<false>(), s, a, tz0, tx0, ntz, ntz * ntx);
 }
 
 }  // namespace fwi
