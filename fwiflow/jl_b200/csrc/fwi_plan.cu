@@ -270,7 +270,13 @@ void choose_batch(fwi_b200_plan &pl, int max_batch) {
   const size_t resident = (size_t)2 * pl.group * pl.trace_stride * sizeof(float) + (size_t)8 * pl.g.plane * sizeof(float);
   const size_t budget = free_b > resident ? (size_t)((free_b - resident) * 0.85) : 0;
   size_t fit = budget / per_shot_bytes(pl, true);
-  if (fit < 1) throw Error(FWI_B200_ERR_CUDA, "not enough device memory for one shot (incl. boundary frames)");
+  if (fit < 1)
+    throw Error(FWI_B200_ERR_CUDA,
+                "not enough device memory: the observed + synthetic traces of the whole group (" +
+                    std::to_string(resident >> 20) + " MiB for " + std::to_string(pl.group) +
+                    " shots) stay resident and one shot needs " + std::to_string(per_shot_bytes(pl, true) >> 20) +
+                    " MiB more (wavefields + boundary frames) out of " + std::to_string(free_b >> 20) +
+                    " MiB free; call with fewer shots per group");
   int b = (int)std::min<size_t>(fit, (size_t)pl.group);
   // enough tiles to fill the machine, no more: beyond ~64 concurrent shots nothing is gained
   b = std::min(b, 64);
