@@ -191,3 +191,38 @@ def test_klauder_bounds_and_resampled_padding():
     cp, cs, den = utils.padding(a, a / 2, a + 1, 3, 4, 6, 8, 4, 2)
     assert cp.shape == (6 + 2 * 4 + 2, 8 + 2 * 4) and np.array_equal(cp[4:10, 4:12], up)
     assert np.array_equal(cp[3, 4:12], up[0]) and np.array_equal(cp[2, 4:12], up[1])   # SYMMETRIC (edge repeated)
+
+
+def test_julia_binding_matches_the_header():
+    """julia/FwiB200.jl cannot be executed here (no Julia in the image): check statically that every `ccall` in it names
+    a function the header declares, with as many argument types as the C prototype has parameters, doubles / ints /
+    strings in the same positions."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "fwi_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"(?:int|void|const char \*|float \*|size_t|long long)\s*\*?\s*(fwi_b200_\w+)\s*\(([^)]*)\)\s*;", hdr):
+        args = [a.strip() for a in m.group(2).split(",") if a.strip() and a.strip() != "void"]
+        kinds = []
+        for a in args:
+            if "char" in a:
+                kinds.append("str")
+            elif "double" in a:
+                kinds.append("f64p")
+            elif "*" in a and "int" in a:
+                kinds.append("i32p")
+            elif "*" in a:
+                kinds.append("ptr")
+            else:
+                kinds.append("int")
+        protos[m.group(1)] = kinds
+    assert "fwi_b200_backward" in protos and len(protos["fwi_b200_backward"]) == 12
+    jl = open(os.path.join(root, "julia", "FwiB200.jl")).read()
+    calls = re.findall(r"ccall\(\(:(fwi_b200_\w+), LIBFWI\), (\w+),\s*\(([^)]*)\)", jl)
+    assert len(calls) >= 6
+    jmap = {"Ref{Cdouble}": "f64p", "Ptr{Cdouble}": "f64p", "Cint": "int", "Ptr{Cint}": "i32p", "Cstring": "str"}
+    for name, ret, types in calls:
+        assert name in protos, name
+        jt = [t.strip() for t in types.split(",") if t.strip()]
+        assert [jmap[t] for t in jt] == protos[name], (name, jt, protos[name])
