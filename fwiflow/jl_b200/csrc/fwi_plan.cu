@@ -222,6 +222,9 @@ void upload_tables(fwi_b200_plan &pl) {
       if (z < 0 || z >= g.nz || x < 0 || x >= g.nx)
         throw Error(FWI_B200_ERR_GEOM, "shot" + std::to_string(s.id) + ": receiver " + std::to_string(r) +
                                            " outside the padded grid");
+      if (z > g.az_hi)   // the nPad rows are never updated and are not stored by this implementation (Grid::zlive)
+        throw Error(FWI_B200_ERR_GEOM, "shot" + std::to_string(s.id) + ": receiver " + std::to_string(r) +
+                                           " inside the inactive nPad rows");
       tile_of[r] = (x / TILE_X) * g.tiles_z + (z / TILE_Z);
       cnt[tile_of[r] + 1]++;
     }

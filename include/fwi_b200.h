@@ -49,6 +49,8 @@ extern "C" {
 #define FWI_B200_ERR_CUDA (-5)    /* CUDA runtime error / no device                */
 #define FWI_B200_ERR_UNSUPPORTED (-6) /* filter / if_src_update requested (if_win IS supported) */
 #define FWI_B200_ERR_GEOM (-7)    /* source / receiver outside the grid, grid too small */
+/*   (incl. a source or receiver inside the nPad rows below the bottom layer: those rows are never updated and this
+ *    implementation neither stores nor loads them; the reference would run with a dead source / an injection nobody sees) */
 
 /* ---- reference-compatible host-buffer entry points ------------------------- */
 

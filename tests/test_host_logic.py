@@ -226,3 +226,4 @@ def test_julia_binding_matches_the_header():
         assert name in protos, name
         jt = [t.strip() for t in types.split(",") if t.strip()]
         assert [jmap[t] for t in jt] == protos[name], (name, jt, protos[name])
+

@@ -389,3 +389,24 @@ def test_gradient_multi_matches_single_device(ops):
         assert rel(got[k], ref[k]) <= 1e-6, k
     with pytest.raises(ops.FwiError):
         ops.fwi_op_and_grad_multi(lam0, mu0, rho0, c.stf, [0, 77], [0, 1], para)    # no such device
+
+
+def test_sources_and_receivers_in_the_nPad_rows_are_refused(ops):
+    """Rows below the bottom absorbing layer (nPad) are never updated; this implementation does not even store them,
+    so geometry that points into them is a GEOM error at plan creation."""
+    c = CASES["small_elastic"]
+    wd = tempfile.mkdtemp()
+    para = c.write_files(wd)
+    sv = json.loads(open(os.path.join(wd, "survey_file.json")).read())
+    dead_z = c.nz_pad - c.nPad - 2 - c.nPml    # unpadded offset of the first never-updated row (az_hi + 1 after + nPml)
+    lam, mu, rho = c.moduli("true")
+    for key in ("z_rec", "z_src"):
+        bad = json.loads(json.dumps(sv))
+        if key == "z_rec":
+            bad["shot0"]["z_rec"][0] = dead_z
+        else:
+            bad["shot0"]["z_src"] = dead_z
+        open(os.path.join(wd, "survey_file.json"), "w").write(json.dumps(bad))
+        with pytest.raises(ops.FwiError) as ei:
+            ops.fwi_obs_op(lam, mu, rho, c.stf, 0, [0], para)
+        assert ei.value.code == -7 and "nPad" in str(ei.value), str(ei.value)
