@@ -380,7 +380,7 @@ __global__ void __launch_bounds__(NCOMPUTE, 1) adj_step_kernel(const __grid_cons
   auto produce = [&](int item, int stage, int ds, bool first = false) {
     const int io = a.order ? nitems - 1 - item : item;
     const int tile = io / a.batch, shot = io - tile * a.batch;   // shot fastest
-    const int z0 = (tile % g.tiles_z) * TILE_Z, x0 = (tile / g.tiles_z) * TILE_X;
+    const int z0 = (tile % g.tiles_z) * TILE_Z + g.z_off, x0 = (tile / g.tiles_z) * TILE_X;
     const int sz = a.st.src_z[shot], sx = a.st.src_x[shot];
     TileDesc d;
     d.soff = (long long)shot * S_COUNT * pl + (long long)x0 * P + z0;

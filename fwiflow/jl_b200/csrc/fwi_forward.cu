@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(NTHREADS_FWD, 1) fwd_step_kernel(const __grid_
     const int io = a.order ? nitems - 1 - item : item;             // zig-zag over launches (launch_forward_step)
     const int tile = io / a.batch, shot = io - tile * a.batch;      // shot fastest: the shots of a tile share its coefficients in L2
     const int tz = tile % g.tiles_z, tx = tile / g.tiles_z;
-    const int z0 = tz * TILE_Z, x0 = tx * TILE_X;
+    const int z0 = tz * TILE_Z + g.z_off, x0 = tx * TILE_X;
     const int sz = a.st.src_z[shot], sx = a.st.src_x[shot];
     TileDesc d;
     d.soff = (long long)shot * S_COUNT * pl + (long long)x0 * P + z0;
@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(NTHREADS_FWD, 1) fwd_step_kernel(const __grid_
     const float *mq_next = a.m.ldt;
     if (more) {
       const int tn = (a.order ? nitems - 1 - (item + stride) : item + stride) / a.batch;
-      const int gzn = (tn % g.tiles_z) * TILE_Z - 4 + 4 * q, gxn = min((tn / g.tiles_z) * TILE_X - 2 + c, gx_max);
+      const int gzn = (tn % g.tiles_z) * TILE_Z + g.z_off - 4 + 4 * q, gxn = min((tn / g.tiles_z) * TILE_X - 2 + c, gx_max);
       mq_next = a.m.ldt + ((long long)gxn * P + gzn);
       ldt = ld4(mq_next); l2mdt = ld4(mq_next + pl); amudt = ld4(mq_next + 2 * pl);
     }

@@ -52,7 +52,10 @@ struct Grid {
                        // dt-scaled coefficient is identically zero there, so they are neither loaded (the TMA tensor
                        // ends at zlive and zero-fills beyond it) nor stored
   int zlo, zhi, xlo, xhi;  // inner box (reconstruction / imaging region)
-  int tiles_z, tiles_x;    // tile grid covering [0,nz) x [0,nx)
+  int tiles_z, tiles_x;    // tile grid of the forward / adjoint kernels covering [z_off, zlive) x [0, nx)
+  int z_off;               // <= 0, multiple of 4: row of the first tile.  Chosen so that a tile boundary falls just below
+                           // the top absorbing layer (+ its 2-cell fringe + the 4-row halo): the tile rows between the
+                           // layers then carry no CPML code at all (C2: 2 of 4 tile rows instead of 1 of 4)
   float dt, rdz, rdx;      // 1/dz, 1/dx
   // boundary frames
   // boundary frames, stored at float4-quad granularity (every quad that intersects the 5-cell ring)

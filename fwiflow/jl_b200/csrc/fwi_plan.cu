@@ -118,6 +118,9 @@ struct fwi_b200_plan {
   }
 };
 
+#ifndef FWI_TILE_ZOFF
+#define FWI_TILE_ZOFF 1
+#endif
 #ifndef FWI_SKIP_DEAD_ROWS
 #define FWI_SKIP_DEAD_ROWS 1
 #endif
@@ -150,7 +153,28 @@ void build_grid(const Para &p, Grid &g) {
   g.ax_hi = p.nx - 3;
   g.zlo = p.nPml; g.zhi = p.nz - p.nPad - 1 - p.nPml;
   g.xlo = p.nPml; g.xhi = p.nx - 1 - p.nPml;
-  g.tiles_z = (p.nz + TILE_Z - 1) / TILE_Z;
+  {
+    // Row offset of the tile grid (a multiple of 4, so that quads stay 16-byte aligned): among the offsets that do not
+    // cost an extra row of tiles, take the one with the fewest tile rows whose region (rows z0-4 .. z0+TILE_Z+3)
+    // touches an absorbing layer or its 2-cell fringe -- only those rows of tiles execute CPML code.
+    const int rows = std::min(p.nz, g.zlive);
+    const int t0 = (rows + TILE_Z - 1) / TILE_Z;
+    const int zq_lo = p.nPml + 2, zq_hi = p.nz - p.nPad - p.nPml - 3;
+    int best_off = 0, best_cnt = 1 << 30;
+    for (int off = 0; off > -TILE_Z; off -= 4) {
+      const int t = (rows - off + TILE_Z - 1) / TILE_Z;
+      if (t > t0) continue;
+      int cnt = 0;
+      for (int k = 0; k < t; k++) {
+        const int z0 = k * TILE_Z + off;
+        if (z0 - 4 < zq_lo || z0 + TILE_Z + 3 > zq_hi) cnt++;
+      }
+      if (cnt < best_cnt) { best_cnt = cnt; best_off = off; }
+      if (!FWI_TILE_ZOFF) break;
+    }
+    g.z_off = best_off;
+    g.tiles_z = (rows - g.z_off + TILE_Z - 1) / TILE_Z;
+  }
   g.tiles_x = (p.nx + TILE_X - 1) / TILE_X;
   g.dt = p.dt;
   g.rdz = (float)(1.0 / (double)p.dz);
@@ -225,7 +249,7 @@ void upload_tables(fwi_b200_plan &pl) {
       if (z > g.az_hi)   // the nPad rows are never updated and are not stored by this implementation (Grid::zlive)
         throw Error(FWI_B200_ERR_GEOM, "shot" + std::to_string(s.id) + ": receiver " + std::to_string(r) +
                                            " inside the inactive nPad rows");
-      tile_of[r] = (x / TILE_X) * g.tiles_z + (z / TILE_Z);
+      tile_of[r] = (x / TILE_X) * g.tiles_z + ((z - g.z_off) / TILE_Z);
       cnt[tile_of[r] + 1]++;
     }
     for (int t = 0; t < pl.ntiles; t++) cnt[t + 1] += cnt[t];
@@ -234,7 +258,7 @@ void upload_tables(fwi_b200_plan &pl) {
     std::vector<int> fill(cnt.begin(), cnt.end() - 1);
     for (int r = 0; r < nrec; r++) {  // stable: receivers of a tile keep their file order
       const int k = fill[tile_of[r]]++;
-      loc[(size_t)i * pl.nrp + k] = (s.z_rec[r] % TILE_Z) | ((s.x_rec[r] % TILE_X) << 16);
+      loc[(size_t)i * pl.nrp + k] = ((s.z_rec[r] - g.z_off) % TILE_Z) | ((s.x_rec[r] % TILE_X) << 16);
       rid[(size_t)i * pl.nrp + k] = r;
     }
   }
