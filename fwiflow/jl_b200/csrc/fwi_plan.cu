@@ -855,7 +855,8 @@ extern "C" int fwi_b200_plan_time_kernel(fwi_b200_plan *pl, int which, int iters
 }
 
 extern "C" const char *fwi_b200_version(void) {
-  return "{\"name\":\"fwi_b200\",\"abi\":1,\"arch\":\"sm_100a\",\"tile\":[56,32],\"fp64_promote\":false}";
+  return "{\"name\":\"fwi_b200\",\"abi\":2,\"arch\":\"sm_100a\",\"tile\":[56,28],\"fp64_promote\":false,"
+         "\"if_win\":true,\"multi_gpu\":true}";
 }
 
 extern "C" const char *fwi_b200_last_error(void) { return last_error_cstr(); }
