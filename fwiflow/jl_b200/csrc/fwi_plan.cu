@@ -854,6 +854,17 @@ extern "C" int fwi_b200_plan_time_kernel(fwi_b200_plan *pl, int which, int iters
   });
 }
 
+extern "C" int fwi_b200_grid_info(const char *para_fname, int *out) {
+  return guarded([&] {
+    if (!para_fname || !out) throw Error(FWI_B200_ERR_ARG, "grid_info: null pointer");
+    const Para p = read_para(para_fname);
+    Grid g{};
+    build_grid(p, g);
+    const int v[12] = {g.nz, g.nx, g.P, g.zlive, g.z_off, g.tiles_z, g.tiles_x, g.f_len, g.zlo, g.zhi, g.xlo, g.xhi};
+    std::copy(v, v + 12, out);
+  });
+}
+
 extern "C" const char *fwi_b200_version(void) {
   return "{\"name\":\"fwi_b200\",\"abi\":2,\"arch\":\"sm_100a\",\"tile\":[56,28],\"fp64_promote\":false,"
          "\"if_win\":true,\"multi_gpu\":true}";

@@ -107,6 +107,14 @@ def fwi_op_and_grad_multi(lam, mu, den, stf, gpu_ids, shot_ids, para_fname):
     return float(misfit.value), gl, gm, gd, gs
 
 
+def grid_info(para_fname):
+    """The device layout derived from a parameter file (host-only; fwi_b200_grid_info)."""
+    out = np.zeros(12, np.int32)
+    check(_lib.lib().fwi_b200_grid_info(str(para_fname).encode(), out.ctypes.data_as(c_ip)))
+    keys = ("nz", "nx", "pitch", "zlive", "z_off", "tiles_z", "tiles_x", "frame_len", "zlo", "zhi", "xlo", "xhi")
+    return dict(zip(keys, (int(v) for v in out)))
+
+
 def release():
     """Free the cached device contexts behind the host-buffer entry points."""
     _lib.lib().fwi_b200_release()

@@ -91,6 +91,12 @@ int fwi_b200_gradient_multi(double *misfit, double *grad_Lambda, double *grad_Mu
                             const double *Den, const double *stf, int ngpu, const int *gpu_ids,
                             int group_size, const int *shot_ids, const char *para_fname);
 
+/* Host-only: the device layout this library derives from a parameter file (no GPU needed).
+ * out[12] = { nz, nx, column pitch, zlive (rows >= zlive are never stored), z_off (row of the first forward/adjoint
+ * tile, <= 0, multiple of 4), tiles_z, tiles_x, floats per field of one saved boundary frame, zlo, zhi, xlo, xhi
+ * (inner box = reconstruction / imaging region, Boundary.cu:17-27) }. */
+int fwi_b200_grid_info(const char *para_fname, int *out);
+
 /* Text of the last error raised on the calling thread ("" if none). */
 const char *fwi_b200_last_error(void);
 

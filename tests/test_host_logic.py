@@ -227,3 +227,36 @@ def test_julia_binding_matches_the_header():
         jt = [t.strip() for t in types.split(",") if t.strip()]
         assert [jmap[t] for t in jt] == protos[name], (name, jt, protos[name])
 
+
+
+def test_device_layout_invariants(lib_built):
+    """fwi_b200_grid_info (host-only): tiles cover every stored row, the row offset keeps quads aligned and never costs
+    a row of tiles, the never-stored rows are exactly the inactive nPad rows, and the quad-granular boundary frames
+    hold every cell of the reference's 5-deep ring (Boundary.cu:17-27) at no more than 1.6x its size."""
+    from fwiflow.jl_b200.utils import paraGen, nPad_rule
+    rng = np.random.default_rng(0)
+    sizes = [(100, 100, 32), (134, 384, 32), (1000, 3000, 32), (4000, 8000, 32), (44, 66, 20)]
+    sizes += [(int(rng.integers(20, 400)), int(rng.integers(20, 500)), int(rng.choice([12, 20, 32]))) for _ in range(40)]
+    for nz0, nx0, nPml in sizes:
+        nPad = nPad_rule(nz0, nPml)
+        nz, nx = nz0 + 2 * nPml + nPad, nx0 + 2 * nPml
+        wd = tempfile.mkdtemp()
+        para = os.path.join(wd, "p.json")
+        paraGen(nz, nx, 10.0, 10.0, 100, 0.001, 5.0, nPml, nPad, para, os.path.join(wd, "s.json"), os.path.join(wd, "D"))
+        g = ops.grid_info(para)
+        assert (g["nz"], g["nx"]) == (nz, nx) and g["pitch"] % 32 == 0 and g["pitch"] >= nz
+        az_hi = nz - nPad - 3
+        assert g["zlive"] % 4 == 0 and az_hi < g["zlive"] <= min(nz, az_hi + 4)
+        assert g["z_off"] <= 0 and g["z_off"] % 4 == 0 and g["z_off"] > -56
+        assert g["tiles_z"] * 56 + g["z_off"] >= g["zlive"] and g["tiles_z"] == -(-(g["zlive"] - g["z_off"]) // 56)
+        assert g["tiles_z"] <= -(-g["zlive"] // 56) and g["tiles_x"] == -(-nx // 28)
+        assert (g["zlo"], g["zhi"], g["xlo"], g["xhi"]) == (nPml, nz - nPad - 1 - nPml, nPml, nx - 1 - nPml)
+        len_bnd = 10 * ((nz - 2 * nPml - nPad + 4) + (nx - 2 * nPml + 4))          # Boundary.cu:19-23
+        assert len_bnd <= g["frame_len"] <= 1.6 * len_bnd + 64, (nz0, nx0, nPml, len_bnd, g["frame_len"])
+    c2 = ops.grid_info(os.path.join(_case_c2_para()))
+    assert (c2["tiles_z"], c2["tiles_x"], c2["zlive"]) == (4, 16, 196)
+
+
+def _case_c2_para():
+    c = synthetic.case_c2(nshots=1, nSteps=10)
+    return c.write_files(tempfile.mkdtemp())
