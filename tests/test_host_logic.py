@@ -260,3 +260,25 @@ def test_device_layout_invariants(lib_built):
 def _case_c2_para():
     c = synthetic.case_c2(nshots=1, nSteps=10)
     return c.write_files(tempfile.mkdtemp())
+
+
+def test_timelapse_driver_spreads_surveys_over_gpus(monkeypatch):
+    """timelapse_misfit_and_gradients (flow-coupled FWI driver): survey i runs on gpu_ids[i % n], results come back in
+    survey order, misfits are summed, and an error in one survey is raised in the caller.  The op is mocked: host logic
+    only (the real thing is tests/test_configs_gpu.py::test_c4_timelapse_six_surveys)."""
+    from fwiflow.jl_b200 import fwi as F
+    calls = []
+
+    def fake(fwi, cp, cs, rho, stf, shot_ids=None, gpu_id=0, **kw):
+        calls.append((fwi, gpu_id, kw.get("is_masked")))
+        if fwi == "boom":
+            raise RuntimeError("survey failed")
+        return float(fwi), np.full((2, 2), fwi), np.zeros((2, 2)), np.zeros((2, 2))
+
+    monkeypatch.setattr(F, "compute_misfit_and_gradient", fake)
+    surveys = [(k, None, None, None) for k in range(6)]
+    total, per = F.timelapse_misfit_and_gradients(surveys, None, gpu_ids=(3, 5), is_masked=True)
+    assert total == 15.0 and [p[0] for p in per] == [0.0, 1.0, 2.0, 3.0, 4.0, 5.0]
+    assert sorted(calls) == sorted([(k, (3, 5)[k % 2], True) for k in range(6)])
+    with pytest.raises(RuntimeError, match="survey failed"):
+        F.timelapse_misfit_and_gradients([(1, None, None, None), ("boom", None, None, None)], None, gpu_ids=(0,))
