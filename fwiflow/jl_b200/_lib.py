@@ -27,7 +27,8 @@ SYMBOLS = [
     "fwi_b200_plan_result_device", "fwi_b200_plan_result_count", "fwi_b200_plan_get_result",
     "fwi_b200_plan_get_traces", "fwi_b200_plan_write_obs_files", "fwi_b200_plan_info",
     "fwi_b200_plan_shot_geometry", "fwi_b200_plan_launch_count", "fwi_b200_plan_get_field",
-    "fwi_b200_plan_time_kernel", "fwi_b200_version", "fwi_b200_grid_info",
+    "fwi_b200_plan_time_kernel", "fwi_b200_version", "fwi_b200_grid_info", "fwi_b200_para_info",
+    "fwi_b200_timelapse", "fwi_b200_set_option",
 ]
 
 ERRORS = {-1: "ERR_ARG", -2: "ERR_IO", -3: "ERR_JSON", -4: "ERR_CFL", -5: "ERR_CUDA", -6: "ERR_UNSUPPORTED",
@@ -70,6 +71,11 @@ def lib():
     L.fwi_b200_misfit_and_gradient.argtypes = [c_dp] * 9 + [ctypes.c_int, ctypes.c_int, c_ip, ctypes.c_char_p]
     L.fwi_b200_gradient_multi.argtypes = [c_dp] * 9 + [ctypes.c_int, c_ip, ctypes.c_int, c_ip, ctypes.c_char_p]
     L.fwi_b200_grid_info.argtypes = [ctypes.c_char_p, c_ip]
+    L.fwi_b200_para_info.argtypes = [ctypes.c_char_p, c_ip]
+    L.fwi_b200_set_option.argtypes = [ctypes.c_char_p, ctypes.c_int]
+    pp = ctypes.POINTER(c_dp)
+    L.fwi_b200_timelapse.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_char_p), pp, pp, pp, c_dp, ctypes.c_int, c_ip,
+                                     ctypes.c_int, c_ip, c_dp, pp, pp, pp]
     L.fwi_b200_forward.argtypes = [c_dp] * 5 + [ctypes.c_int, ctypes.c_int, c_ip, ctypes.c_char_p]
     L.fwi_b200_obscalc.argtypes = [c_dp] * 5 + [ctypes.c_int, ctypes.c_int, c_ip, ctypes.c_char_p]
     L.fwi_b200_backward.argtypes = [c_dp] * 8 + [ctypes.c_int, ctypes.c_int, c_ip, ctypes.c_char_p]

@@ -13,6 +13,9 @@
 // velocity pair with halo 4 / 2 (64 x 32) through a 2-stage TMA ring.  Every thread owns one float4 quad of the
 // 64 x 32 region: it rewinds the velocities of its quad (all threads; the result goes to a double-buffered shared
 // tile), then -- owner threads -- rewinds the stresses of the same quad from the neighbours' rewound velocities.
+#include <atomic>
+#include <cstdlib>
+
 #include "fwi_device.cuh"
 #include "fwi_host.hpp"
 
@@ -276,8 +279,13 @@ rev_image_kernel(const __grid_constant__ BwdArgs a, int tz_first, int tx_first, 
 #pragma unroll
         for (int kk = 0; kk < 4; kk++) {
           if (bx[kk]) {
+#if FWI_F64_UPDATE == 1
+            szz.v[kk] = (float)((double)szz.v[kk] - ((double)l2mdt.v[kk] * (double)dvz_dz[kk] + (double)ldt.v[kk] * (double)dvx_dx[kk]));
+            sxx.v[kk] = (float)((double)sxx.v[kk] - ((double)ldt.v[kk] * (double)dvz_dz[kk] + (double)l2mdt.v[kk] * (double)dvx_dx[kk]));
+#else
             szz.v[kk] = fmaf(-l2mdt.v[kk], dvz_dz[kk], fmaf(-ldt.v[kk], dvx_dx[kk], szz.v[kk]));
             sxx.v[kk] = fmaf(-l2mdt.v[kk], dvx_dx[kk], fmaf(-ldt.v[kk], dvz_dz[kk], sxx.v[kk]));
+#endif
             const float e = dvx_dz[kk] + dvz_dx[kk];
             sxz.v[kk] = fmaf(-amudt.v[kk], e, sxz.v[kk]);
             // el_stress.cu:109-116
@@ -455,6 +463,8 @@ __global__ void __launch_bounds__(NCOMPUTE, 1) adj_step_kernel(const __grid_cons
     const bool actq = gx >= 2 && gx <= g.ax_hi && gz + 3 >= 2 && gz <= g.az_hi;
     const F4 ldt = ld4(mq), l2mdt = ld4(mq + pl), amudt = ld4(mq + 2 * pl);
     const F4 byadt = ld4(mq + 3 * pl), bybdt = ld4(mq + 4 * pl);
+    const bool near_src = FWI_F64_UPDATE > 1 && abs(gx - d.sx) <= FWI_F64_UPDATE && gz + 3 >= d.sz - FWI_F64_UPDATE &&
+                          gz <= d.sz + FWI_F64_UPDATE;   // see fwd_step_kernel
     mbar_wait(&full[stage], phase);
 
     const unsigned char *sb = base + stage * ASTAGE_BYTES;
@@ -504,8 +514,16 @@ __global__ void __launch_bounds__(NCOMPUTE, 1) adj_step_kernel(const __grid_cons
     if (!pml_tile) {
 #pragma unroll
       for (int kk = 0; kk < 4; kk++) {  // coefficients carry dt and are 0 on inactive cells
-        vx.v[kk] += fmaf(ldt.v[kk], dszz_dx[kk], fmaf(l2mdt.v[kk], dsxx_dx[kk], amudt.v[kk] * dsxz_dz[kk]));
-        vz.v[kk] += fmaf(l2mdt.v[kk], dszz_dz[kk], fmaf(ldt.v[kk], dsxx_dz[kk], amudt.v[kk] * dsxz_dx[kk]));
+        // el_velocity_adj.cu:69-71,90-92: the (lambda + 2.0 mu) term promotes the sum to double
+        if (FWI_F64_UPDATE == 1 || (FWI_F64_UPDATE > 1 && near_src)) {
+          vx.v[kk] = (float)((double)vx.v[kk] + ((double)ldt.v[kk] * (double)dszz_dx[kk] + (double)l2mdt.v[kk] * (double)dsxx_dx[kk] +
+                                                 (double)amudt.v[kk] * (double)dsxz_dz[kk]));
+          vz.v[kk] = (float)((double)vz.v[kk] + ((double)l2mdt.v[kk] * (double)dszz_dz[kk] + (double)ldt.v[kk] * (double)dsxx_dz[kk] +
+                                                 (double)amudt.v[kk] * (double)dsxz_dx[kk]));
+        } else {
+          vx.v[kk] += fmaf(ldt.v[kk], dszz_dx[kk], fmaf(l2mdt.v[kk], dsxx_dx[kk], amudt.v[kk] * dsxz_dz[kk]));
+          vz.v[kk] += fmaf(l2mdt.v[kk], dszz_dz[kk], fmaf(ldt.v[kk], dsxx_dz[kk], amudt.v[kk] * dsxz_dx[kk]));
+        }
       }
     } else {
       F4 f_szz_z = zero4(), f_sxz_x = zero4(), f_sxz_z = zero4(), f_sxx_x = zero4();   // new phi of the quad
@@ -551,10 +569,19 @@ __global__ void __launch_bounds__(NCOMPUTE, 1) adj_step_kernel(const __grid_cons
         for (int kk = 0; kk < 4; kk++) {
           const int z = gz + kk;
           if (z >= 2 && z <= g.az_hi) {
+            if (FWI_F64_UPDATE == 1 || (FWI_F64_UPDATE > 1 && near_src)) {
+            vx.v[kk] = (float)((double)vx.v[kk] + ((double)tpx1[kk] + (double)(ldt.v[kk] * dszz_dx[kk] * rKx) +
+                                                   (double)l2mdt.v[kk] * (double)(dsxx_dx[kk] * rKx) + (double)tpx2[kk] +
+                                                   (double)(amudt.v[kk] * rKzh.v[kk] * dsxz_dz[kk])));
+            vz.v[kk] = (float)((double)vz.v[kk] + ((double)tpz1[kk] + (double)l2mdt.v[kk] * (double)(dszz_dz[kk] * rKz.v[kk]) +
+                                                   (double)(ldt.v[kk] * dsxx_dz[kk] * rKz.v[kk]) + (double)tpz2[kk] +
+                                                   (double)(amudt.v[kk] * rKxh * dsxz_dx[kk])));
+            } else {
             vx.v[kk] += tpx1[kk] + ldt.v[kk] * dszz_dx[kk] * rKx + l2mdt.v[kk] * dsxx_dx[kk] * rKx + tpx2[kk] +
                         amudt.v[kk] * rKzh.v[kk] * dsxz_dz[kk];
             vz.v[kk] += tpz1[kk] + l2mdt.v[kk] * dszz_dz[kk] * rKz.v[kk] + ldt.v[kk] * dsxx_dz[kk] * rKz.v[kk] + tpz2[kk] +
                         amudt.v[kk] * rKxh * dsxz_dx[kk];
+            }
           }
         }
         // phi memory of the quad, CPML cells only (el_velocity_adj.cu:74-79,95-100); buoyancies are 0 on inactive cells
@@ -612,9 +639,9 @@ __global__ void __launch_bounds__(NCOMPUTE, 1) adj_step_kernel(const __grid_cons
         const F4 r = ld4(s_inj + sj);
         st4(s_inj + sj, zero4());
 #pragma unroll
-        for (int kk = 0; kk < 4; kk++) {
+        for (int kk = 0; kk < 4; kk++) {   // utilities.cu:575-579: RSXXZZ is the double literal 3.0 -> one rounding
           szz.v[kk] += r.v[kk];
-          sxx.v[kk] += 3.0f * r.v[kk];
+          sxx.v[kk] = (float)((double)sxx.v[kk] + 3.0 * (double)r.v[kk]);
         }
       }
       const float *pz = s_v + sj;
@@ -716,6 +743,10 @@ __global__ void __launch_bounds__(NCOMPUTE, 1) adj_step_kernel(const __grid_cons
 
 }  // namespace
 
+// -1: pick the reverse kernel build by working-set size; 0 / 1: force the double-buffered / LEAN build
+std::atomic<int> g_rev_lean_force{-1};
+void set_rev_lean(int v) { g_rev_lean_force.store(v, std::memory_order_relaxed); }
+
 size_t reverse_smem_bytes() { return REV_SMEM; }
 
 size_t adjoint_smem_bytes() { return ADJ_SMEM; }
@@ -748,7 +779,8 @@ void launch_reverse_imaging(const BwdArgs &a_in, cudaStream_t s) {
   // working set of one launch = forward + adjoint fields and accumulators of every box cell of the batch; beyond a few
   // L2 capacities the kernel is bound by its streams and wants the larger L1 (see rev_smem)
   const double working_set = 100.0 * a.batch * (double)(g.zhi - g.zlo + 1) * (g.xhi - g.xlo + 1);
-  if (REV_LEAN_AUTO && working_set > 512e6)
+  const int force = g_rev_lean_force.load(std::memory_order_relaxed);   // A/B switch (fwi_b200_set_option)
+  if (force >= 0 ? force == 1 : (REV_LEAN_AUTO && working_set > 512e6))
     launch_step(rev_image_kernel<true>, blocks, NCOMPUTE, rev_smem<true>(), s, a, tz0, tx0, ntz, ntz * ntx);
   else
     launch_step(rev_image_kernel<false>, blocks, NCOMPUTE, rev_smem<false>(), s, a, tz0, tx0, ntz, ntz * ntx);

@@ -16,6 +16,10 @@
 #define FWI_STREAM_LD 0   // measured: L1::no_allocate loads are slower here (rev C3 447 -> 590 us)
 #endif
 
+#ifndef FWI_F64_UPDATE
+#define FWI_F64_UPDATE 0   // 1: stress / adjoint-velocity increments summed in double like the reference (one rounding per update)
+#endif
+
 namespace fwi {
 namespace dev {
 

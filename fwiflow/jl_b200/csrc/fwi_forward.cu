@@ -248,10 +248,20 @@ __global__ void __launch_bounds__(NTHREADS_FWD, 1) fwd_step_kernel(const __grid_
         st4(sq + (pout + PSI_VZ_X) * pl, px2);
       }
     }
+    // FWI_F64_UPDATE = R > 1: double-precision increments only for quads within R cells of the shot's source (a per-cell
+    // criterion, so every tile that computes the quad agrees)
+    const bool near_src = FWI_F64_UPDATE > 1 && abs(gx - d.sx) <= FWI_F64_UPDATE && gz + 3 >= d.sz - FWI_F64_UPDATE &&
+                          gz <= d.sz + FWI_F64_UPDATE;
 #pragma unroll
     for (int kk = 0; kk < 4; kk++) {  // el_stress.cu:66-67,83; coefficients carry dt and are 0 on inactive cells
-      szz.v[kk] = fmaf(l2mdt.v[kk], dvz_dz[kk], fmaf(ldt.v[kk], dvx_dx[kk], szz.v[kk]));
-      sxx.v[kk] = fmaf(l2mdt.v[kk], dvx_dx[kk], fmaf(ldt.v[kk], dvz_dz[kk], sxx.v[kk]));
+      // the reference's (lambda + 2.0 mu) promotes the whole increment to double: ONE rounding per update
+      if (FWI_F64_UPDATE == 1 || (FWI_F64_UPDATE > 1 && near_src)) {
+        szz.v[kk] = (float)((double)szz.v[kk] + ((double)l2mdt.v[kk] * (double)dvz_dz[kk] + (double)ldt.v[kk] * (double)dvx_dx[kk]));
+        sxx.v[kk] = (float)((double)sxx.v[kk] + ((double)ldt.v[kk] * (double)dvz_dz[kk] + (double)l2mdt.v[kk] * (double)dvx_dx[kk]));
+      } else {
+        szz.v[kk] = fmaf(l2mdt.v[kk], dvz_dz[kk], fmaf(ldt.v[kk], dvx_dx[kk], szz.v[kk]));
+        sxx.v[kk] = fmaf(l2mdt.v[kk], dvx_dx[kk], fmaf(ldt.v[kk], dvz_dz[kk], sxx.v[kk]));
+      }
       sxz.v[kk] = fmaf(amudt.v[kk], dvx_dz[kk] + dvz_dx[kk], sxz.v[kk]);
     }
     if ((d.flags & TF_SRC) && gx == d.sx && (unsigned)(d.sz - gz) < 4u) {  // add_source (utilities.cu:521-537): point stamp

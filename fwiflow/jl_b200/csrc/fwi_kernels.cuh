@@ -185,5 +185,6 @@ size_t forward_smem_bytes();
 size_t reverse_smem_bytes();
 size_t adjoint_smem_bytes();
 void configure_kernels();  // cudaFuncSetAttribute for dynamic smem
+void set_rev_lean(int v);   // A/B switch of the reverse kernel build: -1 auto, 0 double-buffered, 1 LEAN
 
 }  // namespace fwi

@@ -6,6 +6,8 @@
 // whole batch), all buffers live for the life of the plan, results stay on the device
 // until asked for.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
 
 #include <algorithm>
 #include <cmath>
@@ -33,6 +35,11 @@ using namespace fwi;
 
 namespace {
 
+// cudaMalloc failed: the host-buffer entry points answer it by evicting idle cached plans of the device and retrying
+struct OomError : Error {
+  explicit OomError(const std::string &m) : Error(FWI_B200_ERR_CUDA, m) {}
+};
+
 template <typename T>
 struct DevBuf {
   T *p = nullptr;
@@ -40,7 +47,14 @@ struct DevBuf {
   void alloc(size_t count) {
     if (count <= n && p) return;
     release();
-    CUDA_OK(cudaMalloc(reinterpret_cast<void **>(&p), std::max<size_t>(count, 1) * sizeof(T)));
+    const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+    const cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&p), bytes);
+    if (e == cudaErrorMemoryAllocation) {
+      cudaGetLastError();   // not sticky: clear it
+      p = nullptr;
+      throw OomError("out of device memory: cudaMalloc of " + std::to_string(bytes >> 20) + " MiB failed");
+    }
+    CUDA_OK(e);
     n = count;
   }
   void release() {
@@ -62,6 +76,8 @@ struct fwi_b200_plan {
   std::vector<int> shot_ids;
   cudaStream_t stream = nullptr;
   std::mutex mu;  // one evaluation at a time per plan
+  std::mutex call_mu;  // held by a host-buffer entry point for its whole set_model .. get_result sequence on a cached plan
+  int max_batch_req = 0;  // the caller's max_batch (0 = from free memory); kept for re-planning after an eviction
   long long launches = 0;
   bool model_set = false, stf_set = false;
   std::vector<char> obs_set;
@@ -339,6 +355,13 @@ void alloc_run_buffers(fwi_b200_plan &pl, int calc_id) {
   }
 }
 
+// give the per-run buffers back (after an out-of-memory failure, before the batch is planned again)
+void release_run_buffers(fwi_b200_plan &pl) {
+  pl.state.release(); pl.gacc.release(); pl.frames.release(); pl.syn_tr.release(); pl.res_tr.release();
+  pl.partial.release(); pl.syn_rt.release(); pl.res_rt.release(); pl.obs_cond_rt.release();
+  pl.tm_state = nullptr; pl.tm_gacc = nullptr; pl.tm_state_n = 0;
+}
+
 ShotTables tables_for(fwi_b200_plan &pl, int first) {
   ShotTables st;
   st.src_z = pl.src_z.p + first;
@@ -593,6 +616,7 @@ extern "C" int fwi_b200_plan_create(fwi_b200_plan **out, const char *para_fname,
     CUDA_OK(cudaMemset(pl->result.p, 0, pl->result.bytes()));
     CUDA_OK(cudaMemset(pl->misfit_half.p, 0, sizeof(float)));
     CUDA_OK(cudaMemset(pl->stf_grad.p, 0, pl->stf_grad.bytes()));
+    pl->max_batch_req = max_batch;
     choose_batch(*pl, max_batch);
     *out = pl.release();
   });
@@ -600,55 +624,59 @@ extern "C" int fwi_b200_plan_create(fwi_b200_plan **out, const char *para_fname,
 
 extern "C" void fwi_b200_plan_destroy(fwi_b200_plan *plan) { delete plan; }
 
+static void plan_set_model_impl(fwi_b200_plan *pl, const double *Lambda, const double *Mu, const double *Den) {
+  if (!pl || !Lambda || !Mu || !Den) throw Error(FWI_B200_ERR_ARG, "set_model: null pointer");
+  std::lock_guard<std::mutex> lk(pl->mu);
+  use_device(pl->gpu);
+  const Grid &g = pl->g;
+  const size_t n = (size_t)g.nz * g.nx;
+  cudaStream_t s = pl->stream;
+  CUDA_OK(cudaMemcpyAsync(pl->model_in.p, Lambda, n * sizeof(double), cudaMemcpyHostToDevice, s));
+  CUDA_OK(cudaMemcpyAsync(pl->model_in.p + n, Mu, n * sizeof(double), cudaMemcpyHostToDevice, s));
+  CUDA_OK(cudaMemcpyAsync(pl->model_in.p + 2 * n, Den, n * sizeof(double), cudaMemcpyHostToDevice, s));
+  CUDA_OK(cudaMemsetAsync(pl->cpmax.p, 0, sizeof(unsigned int), s));
+  launch_model_prep(g, pl->model_in.p, pl->model_in.p + n, pl->model_in.p + 2 * n, pl->model.p, pl->cpmax.p, s);
+  pl->launches += 2;
+  unsigned int bits = 0;
+  CUDA_OK(cudaMemcpyAsync(&bits, pl->cpmax.p, sizeof(bits), cudaMemcpyDeviceToHost, s));
+  CUDA_OK(cudaStreamSynchronize(s));
+  float cpmax;
+  std::memcpy(&cpmax, &bits, sizeof(float));
+  const float cn = courant_number(cpmax, pl->para.dt, pl->para.dz, pl->para.dx);
+  pl->model_set = false;
+  if (cn > 1.0f)  // utilities.cu:239 exits silently; we report
+    throw Error(FWI_B200_ERR_CFL, "Courant number " + std::to_string(cn) + " > 1 (max cp " + std::to_string(cpmax) + ")");
+  pl->model_set = true;
+}
+
 extern "C" int fwi_b200_plan_set_model(fwi_b200_plan *pl, const double *Lambda, const double *Mu, const double *Den) {
-  return guarded([&] {
-    if (!pl || !Lambda || !Mu || !Den) throw Error(FWI_B200_ERR_ARG, "set_model: null pointer");
-    std::lock_guard<std::mutex> lk(pl->mu);
-    use_device(pl->gpu);
-    const Grid &g = pl->g;
-    const size_t n = (size_t)g.nz * g.nx;
-    cudaStream_t s = pl->stream;
-    CUDA_OK(cudaMemcpyAsync(pl->model_in.p, Lambda, n * sizeof(double), cudaMemcpyHostToDevice, s));
-    CUDA_OK(cudaMemcpyAsync(pl->model_in.p + n, Mu, n * sizeof(double), cudaMemcpyHostToDevice, s));
-    CUDA_OK(cudaMemcpyAsync(pl->model_in.p + 2 * n, Den, n * sizeof(double), cudaMemcpyHostToDevice, s));
-    CUDA_OK(cudaMemsetAsync(pl->cpmax.p, 0, sizeof(unsigned int), s));
-    launch_model_prep(g, pl->model_in.p, pl->model_in.p + n, pl->model_in.p + 2 * n, pl->model.p, pl->cpmax.p, s);
-    pl->launches += 2;
-    unsigned int bits = 0;
-    CUDA_OK(cudaMemcpyAsync(&bits, pl->cpmax.p, sizeof(bits), cudaMemcpyDeviceToHost, s));
-    CUDA_OK(cudaStreamSynchronize(s));
-    float cpmax;
-    std::memcpy(&cpmax, &bits, sizeof(float));
-    const float cn = courant_number(cpmax, pl->para.dt, pl->para.dz, pl->para.dx);
-    pl->model_set = false;
-    if (cn > 1.0f)  // utilities.cu:239 exits silently; we report
-      throw Error(FWI_B200_ERR_CFL, "Courant number " + std::to_string(cn) + " > 1 (max cp " + std::to_string(cpmax) + ")");
-    pl->model_set = true;
-  });
+  return guarded([&] { plan_set_model_impl(pl, Lambda, Mu, Den); });
+}
+
+static void plan_set_stf_impl(fwi_b200_plan *pl, const double *stf) {
+  if (!pl || !stf) throw Error(FWI_B200_ERR_ARG, "set_stf: null pointer");
+  std::lock_guard<std::mutex> lk(pl->mu);
+  use_device(pl->gpu);
+  const int N = pl->g.nSteps;
+  std::vector<float> w2;
+  const bool ok = taper_weights(N, pl->para.dt, 0.001f, w2);  // Src_Rec.cu:140
+  std::vector<float> h((size_t)pl->group * N);
+  for (int i = 0; i < pl->group; i++) {
+    if (pl->shot_ids[i] < 0) throw Error(FWI_B200_ERR_ARG, "negative shot id");
+    const double *row = stf + (size_t)pl->shot_ids[i] * N;  // row = GLOBAL shot id (Src_Rec.cu:135)
+    for (int t = 0; t < N; t++) {
+      float v = (float)row[t];
+      if (ok) v *= w2[t];
+      h[(size_t)i * N + t] = v;
+    }
+  }
+  CUDA_OK(cudaMemcpyAsync(pl->stf.p, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice, pl->stream));
+  CUDA_OK(cudaStreamSynchronize(pl->stream));
+  pl->stf_set = true;
 }
 
 extern "C" int fwi_b200_plan_set_stf(fwi_b200_plan *pl, const double *stf) {
-  return guarded([&] {
-    if (!pl || !stf) throw Error(FWI_B200_ERR_ARG, "set_stf: null pointer");
-    std::lock_guard<std::mutex> lk(pl->mu);
-    use_device(pl->gpu);
-    const int N = pl->g.nSteps;
-    std::vector<float> w2;
-    const bool ok = taper_weights(N, pl->para.dt, 0.001f, w2);  // Src_Rec.cu:140
-    std::vector<float> h((size_t)pl->group * N);
-    for (int i = 0; i < pl->group; i++) {
-      if (pl->shot_ids[i] < 0) throw Error(FWI_B200_ERR_ARG, "negative shot id");
-      const double *row = stf + (size_t)pl->shot_ids[i] * N;  // row = GLOBAL shot id (Src_Rec.cu:135)
-      for (int t = 0; t < N; t++) {
-        float v = (float)row[t];
-        if (ok) v *= w2[t];
-        h[(size_t)i * N + t] = v;
-      }
-    }
-    CUDA_OK(cudaMemcpyAsync(pl->stf.p, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice, pl->stream));
-    CUDA_OK(cudaStreamSynchronize(pl->stream));
-    pl->stf_set = true;
-  });
+  return guarded([&] { plan_set_stf_impl(pl, stf); });
 }
 
 extern "C" int fwi_b200_plan_set_obs(fwi_b200_plan *pl, int ishot, const float *obs) {
@@ -683,45 +711,49 @@ extern "C" int fwi_b200_plan_load_obs_files(fwi_b200_plan *pl) {
   });
 }
 
+static void plan_run_impl(fwi_b200_plan *pl, int calc_id, void *stream, int sync) {
+  if (!pl) throw Error(FWI_B200_ERR_ARG, "run: null plan");
+  std::lock_guard<std::mutex> lk(pl->mu);
+  use_device(pl->gpu);
+  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : pl->stream;
+  run_locked(*pl, calc_id, s);
+  if (sync) CUDA_OK(cudaStreamSynchronize(s));
+}
+
 extern "C" int fwi_b200_plan_run(fwi_b200_plan *pl, int calc_id, void *stream, int sync) {
-  return guarded([&] {
-    if (!pl) throw Error(FWI_B200_ERR_ARG, "run: null plan");
-    std::lock_guard<std::mutex> lk(pl->mu);
-    use_device(pl->gpu);
-    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : pl->stream;
-    run_locked(*pl, calc_id, s);
-    if (sync) CUDA_OK(cudaStreamSynchronize(s));
-  });
+  return guarded([&] { plan_run_impl(pl, calc_id, stream, sync); });
 }
 
 extern "C" float *fwi_b200_plan_result_device(fwi_b200_plan *pl) { return pl ? pl->result.p : nullptr; }
 extern "C" size_t fwi_b200_plan_result_count(fwi_b200_plan *pl) { return pl ? (size_t)3 * pl->g.nz * pl->g.nx + 1 : 0; }
 
+static void plan_get_result_impl(fwi_b200_plan *pl, double *misfit, double *gl, double *gm, double *gd, double *gs) {
+  if (!pl) throw Error(FWI_B200_ERR_ARG, "get_result: null plan");
+  std::lock_guard<std::mutex> lk(pl->mu);
+  use_device(pl->gpu);
+  CUDA_OK(cudaDeviceSynchronize());
+  const size_t n = (size_t)pl->g.nz * pl->g.nx;
+  if (gl || gm || gd) {
+    std::vector<float> h(3 * n + 1);
+    CUDA_OK(cudaMemcpy(h.data(), pl->result.p, h.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    if (gl) for (size_t i = 0; i < n; i++) gl[i] = h[i];
+    if (gm) for (size_t i = 0; i < n; i++) gm[i] = h[n + i];
+    if (gd) for (size_t i = 0; i < n; i++) gd[i] = h[2 * n + i];
+    if (misfit) *misfit = h[3 * n];
+  } else if (misfit) {
+    float m = 0;
+    CUDA_OK(cudaMemcpy(&m, pl->result.p + 3 * n, sizeof(float), cudaMemcpyDeviceToHost));
+    *misfit = m;
+  }
+  if (gs) {
+    std::vector<float> h((size_t)pl->group * pl->g.nSteps);
+    CUDA_OK(cudaMemcpy(h.data(), pl->stf_grad.p, h.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < h.size(); i++) gs[i] = h[i];
+  }
+}
+
 extern "C" int fwi_b200_plan_get_result(fwi_b200_plan *pl, double *misfit, double *gl, double *gm, double *gd, double *gs) {
-  return guarded([&] {
-    if (!pl) throw Error(FWI_B200_ERR_ARG, "get_result: null plan");
-    std::lock_guard<std::mutex> lk(pl->mu);
-    use_device(pl->gpu);
-    CUDA_OK(cudaDeviceSynchronize());
-    const size_t n = (size_t)pl->g.nz * pl->g.nx;
-    if (gl || gm || gd) {
-      std::vector<float> h(3 * n + 1);
-      CUDA_OK(cudaMemcpy(h.data(), pl->result.p, h.size() * sizeof(float), cudaMemcpyDeviceToHost));
-      if (gl) for (size_t i = 0; i < n; i++) gl[i] = h[i];
-      if (gm) for (size_t i = 0; i < n; i++) gm[i] = h[n + i];
-      if (gd) for (size_t i = 0; i < n; i++) gd[i] = h[2 * n + i];
-      if (misfit) *misfit = h[3 * n];
-    } else if (misfit) {
-      float m = 0;
-      CUDA_OK(cudaMemcpy(&m, pl->result.p + 3 * n, sizeof(float), cudaMemcpyDeviceToHost));
-      *misfit = m;
-    }
-    if (gs) {
-      std::vector<float> h((size_t)pl->group * pl->g.nSteps);
-      CUDA_OK(cudaMemcpy(h.data(), pl->stf_grad.p, h.size() * sizeof(float), cudaMemcpyDeviceToHost));
-      for (size_t i = 0; i < h.size(); i++) gs[i] = h[i];
-    }
-  });
+  return guarded([&] { plan_get_result_impl(pl, misfit, gl, gm, gd, gs); });
 }
 
 extern "C" int fwi_b200_plan_get_traces(fwi_b200_plan *pl, int ishot, int which, float *out) {
@@ -746,15 +778,17 @@ static void write_group_files(fwi_b200_plan *pl, DevBuf<float> &buf, const std::
   }
 }
 
+static void plan_write_obs_files_impl(fwi_b200_plan *pl) {
+  if (!pl) throw Error(FWI_B200_ERR_ARG, "write_obs_files: null plan");
+  std::lock_guard<std::mutex> lk(pl->mu);
+  use_device(pl->gpu);
+  CUDA_OK(cudaDeviceSynchronize());
+  if (pl->last_calc != 2 || !pl->syn_rt.p) throw Error(FWI_B200_ERR_ARG, "write_obs_files: last run was not calc_id 2");
+  write_group_files(pl, pl->syn_rt, pl->para.data_dir_name, "Shot");  // libCUFD.cu:514-521
+}
+
 extern "C" int fwi_b200_plan_write_obs_files(fwi_b200_plan *pl) {
-  return guarded([&] {
-    if (!pl) throw Error(FWI_B200_ERR_ARG, "write_obs_files: null plan");
-    std::lock_guard<std::mutex> lk(pl->mu);
-    use_device(pl->gpu);
-    CUDA_OK(cudaDeviceSynchronize());
-    if (pl->last_calc != 2 || !pl->syn_rt.p) throw Error(FWI_B200_ERR_ARG, "write_obs_files: last run was not calc_id 2");
-    write_group_files(pl, pl->syn_rt, pl->para.data_dir_name, "Shot");  // libCUFD.cu:514-521
-  });
+  return guarded([&] { plan_write_obs_files_impl(pl); });
 }
 
 extern "C" int fwi_b200_plan_info(fwi_b200_plan *pl, int *nz, int *nx, int *nSteps, int *nPml, int *nPad, int *group_size,
@@ -883,13 +917,30 @@ struct CacheEntry {
   std::shared_ptr<fwi_b200_plan> plan;   // shared: a call in flight keeps its plan alive if another thread evicts the entry
 };
 std::mutex g_cache_mu;
-std::list<CacheEntry> g_cache;
-constexpr size_t kCacheMax = 8;   // baseline + 5 monitor surveys of a time-lapse inversion stay resident
+std::list<CacheEntry> g_cache;           // most recently used first
+constexpr size_t kCachePerGpu = 8;       // per device: baseline + 5 monitor surveys of a time-lapse inversion stay resident (C4)
 
 std::string cache_key(const char *para_fname, const Para &p, const std::string &survey_text, int group, const int *ids) {
   std::string k = std::string(para_fname) + "\n" + p.text + "\n" + survey_text + "\n";
   for (int i = 0; i < group; i++) k += std::to_string(ids[i]) + ",";
   return k;
+}
+
+// g_cache_mu held.  Drops cached plans of `gpu` that no call holds (use_count() == 1), least recently used first, until
+// at most `max_left` entries of that device remain.  Their device memory is returned by the plan destructor.
+size_t evict_idle_locked(int gpu, size_t max_left) {
+  size_t n = 0, freed = 0;
+  for (const CacheEntry &e : g_cache) n += e.gpu == gpu;
+  auto it = g_cache.end();
+  while (it != g_cache.begin() && n > max_left) {
+    --it;
+    if (it->gpu == gpu && it->plan.use_count() == 1) {
+      it = g_cache.erase(it);
+      --n;
+      ++freed;
+    }
+  }
+  return freed;
 }
 
 std::shared_ptr<fwi_b200_plan> cached_plan(const char *para_fname, int gpu, int group, const int *ids) {
@@ -910,16 +961,67 @@ std::shared_ptr<fwi_b200_plan> cached_plan(const char *para_fname, int gpu, int 
       g_cache.splice(g_cache.begin(), g_cache, it);
       return g_cache.front().plan;
     }
-  while (g_cache.size() >= kCacheMax) g_cache.pop_back();
+  evict_idle_locked(gpu, kCachePerGpu - 1);
   fwi_b200_plan *raw = nullptr;
   int rc = fwi_b200_plan_create(&raw, para_fname, gpu, group, ids, 0);
+  if (rc == FWI_B200_ERR_CUDA && evict_idle_locked(gpu, 0) > 0)   // idle plans were holding the memory: drop them, plan again
+    rc = fwi_b200_plan_create(&raw, para_fname, gpu, group, ids, 0);
   if (rc != FWI_B200_OK) throw Error(rc, last_error_cstr());
-  g_cache.push_front(CacheEntry{gpu, key, std::shared_ptr<fwi_b200_plan>(raw)});
-  return g_cache.front().plan;
+  std::shared_ptr<fwi_b200_plan> plan(raw);
+  // a batch squeezed by what idle cached plans still hold: give their memory back and size the batch again
+  if (plan->batch < std::min(plan->group, 64) && evict_idle_locked(gpu, 0) > 0) choose_batch(*plan, 0);
+  g_cache.push_front(CacheEntry{gpu, key, plan});
+  return plan;
 }
 
-void check(int rc) {
-  if (rc != FWI_B200_OK) throw Error(rc, last_error_cstr());
+// one evaluation through a cached plan with host buffers.  fetch == false leaves the result on the device (the
+// multi-GPU driver reduces it there); the caller holds pl->call_mu.
+void host_eval(fwi_b200_plan *pl, const double *Lambda, const double *Mu, const double *Den, const double *stf,
+               int calc_id, bool sync) {
+  plan_set_model_impl(pl, Lambda, Mu, Den);
+  plan_set_stf_impl(pl, stf);
+  for (int attempt = 0;; attempt++) {
+    try {
+      if (calc_id != 2) {   // Data/Shot<id>.bin -> device, overlapped with the forward time loop
+        std::lock_guard<std::mutex> lk(pl->mu);
+        use_device(pl->gpu);
+        start_obs_load(*pl);
+      }
+      plan_run_impl(pl, calc_id, nullptr, sync ? 1 : 0);
+      return;
+    } catch (const OomError &) {
+      // Buffers are allocated lazily, so plans created back to back budget the same free memory; and idle cached plans
+      // of this device may hold most of it.  Drop the idle ones, return this plan's own run buffers, size the batch
+      // for what is free now, and try once more.
+      if (attempt) throw;
+      {
+        std::lock_guard<std::mutex> lk(pl->mu);
+        use_device(pl->gpu);
+        settle_obs_load(*pl);
+        CUDA_OK(cudaDeviceSynchronize());
+        release_run_buffers(*pl);
+      }
+      {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        evict_idle_locked(pl->gpu, 0);
+      }
+      std::lock_guard<std::mutex> lk(pl->mu);
+      use_device(pl->gpu);
+      choose_batch(*pl, pl->max_batch_req);
+    }
+  }
+}
+
+void write_scratch(fwi_b200_plan *pl) {   // libCUFD.cu:493-511
+  std::lock_guard<std::mutex> lk(pl->mu);
+  write_group_files(pl, pl->res_rt, pl->para.scratch_dir_name, "Residual_Shot");
+  write_group_files(pl, pl->syn_rt, pl->para.scratch_dir_name, "Syn_Shot");
+  write_group_files(pl, pl->obs_cond_rt, pl->para.scratch_dir_name, "CondObs_Shot");
+  std::vector<float> h((size_t)pl->group * pl->g.nSteps);
+  CUDA_OK(cudaMemcpy(h.data(), pl->stf.p, h.size() * sizeof(float), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < pl->group; i++)
+    write_f32(pl->para.scratch_dir_name + "/src_updated" + std::to_string(pl->shot_ids[i]) + ".bin",
+              h.data() + (size_t)i * pl->g.nSteps, pl->g.nSteps);
 }
 
 int host_call(double *misfit, double *gl, double *gm, double *gd, double *gs, const double *Lambda, const double *Mu,
@@ -933,33 +1035,19 @@ int host_call(double *misfit, double *gl, double *gm, double *gd, double *gs, co
       throw Error(FWI_B200_ERR_ARG, "cufd: calc_id 1 needs the four gradient outputs");
     const std::shared_ptr<fwi_b200_plan> hold = cached_plan(para_fname, gpu_id, group_size, shot_ids);
     fwi_b200_plan *pl = hold.get();
-    check(fwi_b200_plan_set_model(pl, Lambda, Mu, Den));
-    check(fwi_b200_plan_set_stf(pl, stf));
-    if (calc_id != 2) {   // Data/Shot<id>.bin -> device, overlapped with the forward time loop
-      std::lock_guard<std::mutex> lk(pl->mu);
-      use_device(pl->gpu);
-      start_obs_load(*pl);
-    }
-    check(fwi_b200_plan_run(pl, calc_id, nullptr, 1));
+    // one caller at a time per cached plan, for the WHOLE sequence: two threads with the same (para, gpu, shot ids) but
+    // different models must not interleave set_model / run / get_result
+    std::lock_guard<std::mutex> call(pl->call_mu);
+    host_eval(pl, Lambda, Mu, Den, stf, calc_id, true);
     if (calc_id == 2) {
-      check(fwi_b200_plan_write_obs_files(pl));
+      plan_write_obs_files_impl(pl);
       if (misfit) *misfit = 0.0;  // FwiOp.cpp:316
     } else if (calc_id == 0) {
-      check(fwi_b200_plan_get_result(pl, misfit, nullptr, nullptr, nullptr, nullptr));
+      plan_get_result_impl(pl, misfit, nullptr, nullptr, nullptr, nullptr);
     } else {
       // the reference never writes *misfit for calc_id 1 (libCUFD.cu:528); the fused entry point does
-      check(fwi_b200_plan_get_result(pl, also_misfit ? misfit : nullptr, gl, gm, gd, gs));
-      if (pl->para.save_scratch) {  // libCUFD.cu:493-511
-        std::lock_guard<std::mutex> lk(pl->mu);
-        write_group_files(pl, pl->res_rt, pl->para.scratch_dir_name, "Residual_Shot");
-        write_group_files(pl, pl->syn_rt, pl->para.scratch_dir_name, "Syn_Shot");
-        write_group_files(pl, pl->obs_cond_rt, pl->para.scratch_dir_name, "CondObs_Shot");
-        std::vector<float> h((size_t)pl->group * pl->g.nSteps);
-        CUDA_OK(cudaMemcpy(h.data(), pl->stf.p, h.size() * sizeof(float), cudaMemcpyDeviceToHost));
-        for (int i = 0; i < pl->group; i++)
-          write_f32(pl->para.scratch_dir_name + "/src_updated" + std::to_string(pl->shot_ids[i]) + ".bin",
-                    h.data() + (size_t)i * pl->g.nSteps, pl->g.nSteps);
-      }
+      plan_get_result_impl(pl, also_misfit ? misfit : nullptr, gl, gm, gd, gs);
+      if (pl->para.save_scratch) write_scratch(pl);
     }
   });
 }
@@ -994,63 +1082,219 @@ extern "C" int fwi_b200_misfit_and_gradient(double *misfit, double *gl, double *
   return host_call(misfit, gl, gm, gd, gs, Lambda, Mu, Den, stf, 1, true, gpu_id, group_size, shot_ids, para_fname);
 }
 
+// =================================================================================================
+// several GPUs inside ONE process: shots sharded over the devices, gradients summed with NCCL
+// =================================================================================================
+namespace {
+
+// NCCL is bound at run time (dlopen of libnccl.so.2): inside a process that already carries a copy (PyTorch bundles
+// one) that copy is the one found, and the library has no link-time dependency a single-GPU user would have to satisfy.
+struct NcclApi {
+  void *h = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+  ncclResult_t (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+};
+
+NcclApi &nccl_api() {
+  static NcclApi api;
+  static std::once_flag once;
+  static std::string err;
+  std::call_once(once, [] {
+    for (const char *name : {"libnccl.so.2", "libnccl.so"}) {
+      api.h = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+      if (api.h) break;
+    }
+    if (!api.h) { err = std::string("cannot load libnccl.so.2: ") + dlerror(); return; }
+    auto sym = [&](const char *n) {
+      void *p = dlsym(api.h, n);
+      if (!p && err.empty()) err = std::string("libnccl: missing symbol ") + n;
+      return p;
+    };
+    api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
+    api.CommInitAll = reinterpret_cast<decltype(api.CommInitAll)>(sym("ncclCommInitAll"));
+    api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
+    api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(sym("ncclAllReduce"));
+    api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(sym("ncclGroupStart"));
+    api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(sym("ncclGroupEnd"));
+  });
+  if (!err.empty()) throw Error(FWI_B200_ERR_CUDA, "gradient_multi needs NCCL for more than one device: " + err);
+  return api;
+}
+
+#define NCCL_OK(call)                                                                                       \
+  do {                                                                                                      \
+    ncclResult_t r_ = (call);                                                                               \
+    if (r_ != ncclSuccess)                                                                                  \
+      throw Error(FWI_B200_ERR_CUDA, std::string("NCCL: ") + nccl_api().GetErrorString(r_) + " (" #call ")"); \
+  } while (0)
+
+// one communicator set per ordered device list, created once (ncclCommInitAll) and kept until fwi_b200_release()
+struct CommSet {
+  std::vector<int> devs;
+  std::vector<ncclComm_t> comms;
+};
+std::mutex g_comm_mu;            // also serialises the collectives of concurrent gradient_multi calls
+std::list<CommSet> g_comms;
+
+CommSet &comm_set_locked(const std::vector<int> &devs) {
+  for (CommSet &c : g_comms)
+    if (c.devs == devs) return c;
+  CommSet c;
+  c.devs = devs;
+  c.comms.resize(devs.size());
+  NCCL_OK(nccl_api().CommInitAll(c.comms.data(), (int)devs.size(), devs.data()));
+  g_comms.push_back(std::move(c));
+  return g_comms.back();
+}
+
+void destroy_comms() {
+  std::lock_guard<std::mutex> lk(g_comm_mu);
+  for (CommSet &c : g_comms)
+    for (ncclComm_t m : c.comms) nccl_api().CommDestroy(m);
+  g_comms.clear();
+}
+
+struct Shard {
+  int gpu = 0;
+  std::vector<int> ids, pos;            // shot ids and their positions in the caller's group
+  std::shared_ptr<fwi_b200_plan> plan;
+  std::unique_lock<std::mutex> call;    // the plan's call lock, held from the evaluation to the last copy
+  int rc = FWI_B200_OK;
+  std::string err;
+};
+
+}  // namespace
+
 extern "C" int fwi_b200_gradient_multi(double *misfit, double *gl, double *gm, double *gd, double *gs,
                                        const double *Lambda, const double *Mu, const double *Den, const double *stf,
                                        int ngpu, const int *gpu_ids, int group_size, const int *shot_ids,
                                        const char *para_fname) {
   return guarded([&] {
-    if (ngpu <= 0 || !gpu_ids || group_size <= 0 || !shot_ids || !para_fname)
+    if (ngpu <= 0 || !gpu_ids || group_size <= 0 || !shot_ids || !para_fname || !Lambda || !Mu || !Den || !stf)
       throw Error(FWI_B200_ERR_ARG, "gradient_multi: bad arguments");
+    for (int a = 0; a < ngpu; a++)
+      for (int b = a + 1; b < ngpu; b++)
+        if (gpu_ids[a] == gpu_ids[b]) throw Error(FWI_B200_ERR_ARG, "gradient_multi: duplicate gpu id");
     const Para para = read_para(para_fname);
     const size_t n = (size_t)para.nz * para.nx;
     const int N = para.nSteps;
-    struct Shard {
-      int gpu = 0;
-      std::vector<int> ids, pos;            // shot ids and their positions in the caller's group
-      std::vector<double> gl, gm, gd, gs;
-      double misfit = 0.0;
-      int rc = FWI_B200_OK;
-      std::string err;
-    };
     std::vector<Shard> shards(std::min(ngpu, group_size));
     for (int k = 0; k < group_size; k++) {   // round-robin, a true partition of the group
       Shard &sh = shards[k % shards.size()];
       sh.ids.push_back(shot_ids[k]);
       sh.pos.push_back(k);
     }
+    const bool reduce = shards.size() > 1;
+    if (reduce) nccl_api();   // fail before any work if NCCL cannot be loaded
+    // one host thread per device: cached plan, inputs H2D, observations, forward + backward enqueued on the plan's
+    // stream.  Nothing synchronises: the gradient of the shard stays in the plan's packed result buffer.
     std::vector<std::thread> workers;
     for (size_t r = 0; r < shards.size(); r++) {
       Shard &sh = shards[r];
       sh.gpu = gpu_ids[r];
-      sh.gl.assign(n, 0.0); sh.gm.assign(n, 0.0); sh.gd.assign(n, 0.0);
-      sh.gs.assign(sh.ids.size() * (size_t)N, 0.0);
       workers.emplace_back([&sh, Lambda, Mu, Den, stf, para_fname] {
-        sh.rc = host_call(&sh.misfit, sh.gl.data(), sh.gm.data(), sh.gd.data(), sh.gs.data(), Lambda, Mu, Den, stf, 1, true,
-                          sh.gpu, (int)sh.ids.size(), sh.ids.data(), para_fname);
+        sh.rc = guarded([&] {
+          sh.plan = cached_plan(para_fname, sh.gpu, (int)sh.ids.size(), sh.ids.data());
+          sh.call = std::unique_lock<std::mutex>(sh.plan->call_mu);
+          host_eval(sh.plan.get(), Lambda, Mu, Den, stf, 1, false);
+        });
         if (sh.rc != FWI_B200_OK) sh.err = last_error_cstr();   // the error text is thread-local
       });
     }
     for (auto &w : workers) w.join();
     for (const Shard &sh : shards)
       if (sh.rc != FWI_B200_OK) throw Error(sh.rc, "gpu " + std::to_string(sh.gpu) + ": " + sh.err);
-    double j = 0.0;
-    for (const Shard &sh : shards) j += sh.misfit;
-    if (misfit) *misfit = j;
-    for (size_t i = 0; i < n; i++) {
-      double a = 0.0, b = 0.0, c = 0.0;
-      for (const Shard &sh : shards) { a += sh.gl[i]; b += sh.gm[i]; c += sh.gd[i]; }
-      if (gl) gl[i] = a;
-      if (gm) gm[i] = b;
-      if (gd) gd[i] = c;
+    if (reduce) {
+      // ONE ncclAllReduce(sum, float32, 3 nz nx + 1) over [grad_Lambda | grad_Mu | grad_Den | misfit], in place in the
+      // buffer finalize_kernel wrote, on each plan's own stream right behind its last kernel (NVLink / NVSwitch)
+      std::vector<int> devs;
+      for (const Shard &sh : shards) devs.push_back(sh.gpu);
+      std::lock_guard<std::mutex> lk(g_comm_mu);
+      CommSet &cs = comm_set_locked(devs);
+      NcclApi &nc = nccl_api();
+      NCCL_OK(nc.GroupStart());
+      for (size_t r = 0; r < shards.size(); r++) {
+        fwi_b200_plan *pl = shards[r].plan.get();
+        NCCL_OK(nc.AllReduce(pl->result.p, pl->result.p, 3 * n + 1, ncclFloat32, ncclSum, cs.comms[r], pl->stream));
+      }
+      NCCL_OK(nc.GroupEnd());
     }
-    if (gs)
-      for (const Shard &sh : shards)
-        for (size_t k = 0; k < sh.ids.size(); k++)
-          std::copy(sh.gs.begin() + k * N, sh.gs.begin() + (k + 1) * N, gs + (size_t)sh.pos[k] * N);
+    // a single D2H of the reduced buffer from the first device; the per-shot grad_stf rows are gathered from their owners
+    plan_get_result_impl(shards[0].plan.get(), misfit, gl, gm, gd, nullptr);
+    for (Shard &sh : shards) {
+      fwi_b200_plan *pl = sh.plan.get();
+      if (gs || pl->para.save_scratch || &sh != &shards[0]) {
+        std::lock_guard<std::mutex> lk(pl->mu);
+        use_device(pl->gpu);
+        CUDA_OK(cudaStreamSynchronize(pl->stream));
+        if (gs) {
+          std::vector<float> h(sh.ids.size() * (size_t)N);
+          CUDA_OK(cudaMemcpy(h.data(), pl->stf_grad.p, h.size() * sizeof(float), cudaMemcpyDeviceToHost));
+          for (size_t k = 0; k < sh.ids.size(); k++)
+            for (int t = 0; t < N; t++) gs[(size_t)sh.pos[k] * N + t] = h[k * N + t];
+        }
+      }
+      if (pl->para.save_scratch) write_scratch(pl);
+      sh.call.unlock();
+    }
+  });
+}
+
+// =================================================================================================
+// time-lapse surveys (baseline + monitors) in one call
+// =================================================================================================
+extern "C" int fwi_b200_timelapse(int nsurveys, const char *const *para_fnames, const double *const *Lambda,
+                                  const double *const *Mu, const double *const *Den, const double *stf, int ngpu,
+                                  const int *gpu_ids, int group_size, const int *shot_ids, double *misfit,
+                                  double *const *gl, double *const *gm, double *const *gd) {
+  return guarded([&] {
+    if (nsurveys <= 0 || !para_fnames || !Lambda || !Mu || !Den || !stf || ngpu <= 0 || !gpu_ids || group_size <= 0 ||
+        !shot_ids || !misfit)
+      throw Error(FWI_B200_ERR_ARG, "timelapse: bad arguments");
+    struct Job { int rc = FWI_B200_OK; std::string err; };
+    std::vector<Job> jobs(nsurveys);
+    const int nw = std::min(ngpu, nsurveys);
+    std::vector<std::thread> workers;
+    for (int w = 0; w < nw; w++)
+      workers.emplace_back([&, w] {   // survey i on gpu_ids[i % ngpu] (main_two_phase_flow_inversion.jl:84-93)
+        for (int i = w; i < nsurveys; i += nw) {
+          jobs[i].rc = host_call(&misfit[i], gl ? gl[i] : nullptr, gm ? gm[i] : nullptr, gd ? gd[i] : nullptr, nullptr,
+                                 Lambda[i], Mu[i], Den[i], stf, 1, true, gpu_ids[w], group_size, shot_ids, para_fnames[i]);
+          if (jobs[i].rc != FWI_B200_OK) jobs[i].err = last_error_cstr();
+        }
+      });
+    for (auto &t : workers) t.join();
+    for (int i = 0; i < nsurveys; i++)
+      if (jobs[i].rc != FWI_B200_OK) throw Error(jobs[i].rc, "survey " + std::to_string(i) + ": " + jobs[i].err);
+  });
+}
+
+extern "C" int fwi_b200_set_option(const char *name, int value) {
+  return guarded([&] {
+    if (!name) throw Error(FWI_B200_ERR_ARG, "set_option: null name");
+    const std::string k(name);
+    if (k == "rev_lean") set_rev_lean(value);
+    else throw Error(FWI_B200_ERR_ARG, "set_option: unknown option '" + k + "'");
+  });
+}
+
+extern "C" int fwi_b200_para_info(const char *para_fname, int *out) {
+  return guarded([&] {
+    if (!para_fname || !out) throw Error(FWI_B200_ERR_ARG, "para_info: null pointer");
+    const Para p = read_para(para_fname);
+    const int v[8] = {p.nz, p.nx, p.nSteps, p.nPml, p.nPad, p.if_win ? 1 : 0, p.save_scratch ? 1 : 0, 0};
+    std::copy(v, v + 8, out);
   });
 }
 
 extern "C" void fwi_b200_release(void) {
-  std::lock_guard<std::mutex> lk(g_cache_mu);
-  g_cache.clear();
+  {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    g_cache.clear();
+  }
+  if (!g_comms.empty()) destroy_comms();
 }

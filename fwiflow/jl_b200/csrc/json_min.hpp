@@ -88,6 +88,19 @@ class JsonParser {
     p_ += static_cast<size_t>(end - start);
     return v;
   }
+  unsigned hex4() {
+    if (p_ + 4 > s_.size()) fail("bad \\u escape");
+    unsigned code = 0;
+    for (int k = 0; k < 4; k++) {
+      const char h = s_[p_++];
+      code <<= 4;
+      if (h >= '0' && h <= '9') code |= static_cast<unsigned>(h - '0');
+      else if (h >= 'a' && h <= 'f') code |= static_cast<unsigned>(h - 'a' + 10);
+      else if (h >= 'A' && h <= 'F') code |= static_cast<unsigned>(h - 'A' + 10);
+      else fail("bad \\u escape");
+    }
+    return code;
+  }
   std::string string() {
     expect('"');
     std::string out;
@@ -104,11 +117,35 @@ class JsonParser {
           case 'r': out += '\r'; break;
           case 'b': out += '\b'; break;
           case 'f': out += '\f'; break;
-          case 'u': {  // keep ASCII range only (paths)
-            if (p_ + 4 > s_.size()) fail("bad \\u escape");
-            unsigned code = static_cast<unsigned>(std::strtoul(s_.substr(p_, 4).c_str(), nullptr, 16));
-            p_ += 4;
-            out += static_cast<char>(code & 0x7f);
+          case 'u': {  // \uXXXX (with surrogate pairs) -> UTF-8, like rapidjson in the reference
+            unsigned code = hex4();
+            if (code >= 0xD800 && code <= 0xDBFF) {   // high surrogate: a low one must follow
+              if (p_ + 2 <= s_.size() && s_[p_] == '\\' && s_[p_ + 1] == 'u') {
+                p_ += 2;
+                const unsigned lo = hex4();
+                if (lo < 0xDC00 || lo > 0xDFFF) fail("bad surrogate pair");
+                code = 0x10000 + ((code - 0xD800) << 10) + (lo - 0xDC00);
+              } else {
+                fail("lone surrogate");
+              }
+            } else if (code >= 0xDC00 && code <= 0xDFFF) {
+              fail("lone surrogate");
+            }
+            if (code < 0x80) {
+              out += static_cast<char>(code);
+            } else if (code < 0x800) {
+              out += static_cast<char>(0xC0 | (code >> 6));
+              out += static_cast<char>(0x80 | (code & 0x3F));
+            } else if (code < 0x10000) {
+              out += static_cast<char>(0xE0 | (code >> 12));
+              out += static_cast<char>(0x80 | ((code >> 6) & 0x3F));
+              out += static_cast<char>(0x80 | (code & 0x3F));
+            } else {
+              out += static_cast<char>(0xF0 | (code >> 18));
+              out += static_cast<char>(0x80 | ((code >> 12) & 0x3F));
+              out += static_cast<char>(0x80 | ((code >> 6) & 0x3F));
+              out += static_cast<char>(0x80 | (code & 0x3F));
+            }
             break;
           }
           default: out += e;  // \" \\ \/

@@ -56,17 +56,21 @@ def sharded_gradient(plan_factory, shot_ids, rank, world_size, lam, mu, den, stf
     identical on every rank.
     """
     local = shard_shots(shot_ids, rank, world_size)
-    plan = plan_factory(local)
     if len(local):
+        plan = plan_factory(local)
         plan.set_model(lam, mu, den)
         plan.set_stf(stf)
         plan.load_obs_files()
         plan.run(1)
-    buf = plan.result_tensor()
-    if len(local) == 0:
-        buf.zero_()
+        buf = plan.result_tensor()
+        nz, nx = plan.nz, plan.nx
+    else:
+        # more ranks than shots: this rank owns nothing.  No plan is created (a plan needs at least one shot); it
+        # contributes zeros of the right size to the all-reduce so that the other ranks do not block.
+        import torch
+        nz, nx = np.asarray(lam).shape
+        buf = torch.zeros(3 * nz * nx + 1, dtype=torch.float32, device=device if device is not None else "cpu")
     allreduce_result(buf)
-    nz, nx = plan.nz, plan.nx
     h = buf.detach().cpu().numpy().astype(np.float64)
     n = nz * nx
     return float(h[3 * n]), h[:n].reshape(nz, nx), h[n:2 * n].reshape(nz, nx), h[2 * n:3 * n].reshape(nz, nx)

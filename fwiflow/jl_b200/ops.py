@@ -21,7 +21,8 @@ import numpy as np
 from . import _lib
 from ._lib import FwiError, c_dp, c_fp, c_ip, check
 
-__all__ = ["fwi_op", "fwi_obs_op", "fwi_op_grad", "fwi_op_and_grad", "FwiOp", "Plan", "release", "FwiError"]
+__all__ = ["fwi_op", "fwi_obs_op", "fwi_op_grad", "fwi_op_and_grad", "fwi_op_and_grad_multi", "timelapse", "para_info",
+           "grid_info", "FwiOp", "Plan", "release", "FwiError"]
 
 
 def _f64(a):
@@ -32,19 +33,44 @@ def _dp(a):
     return None if a is None else a.ctypes.data_as(c_dp)
 
 
-def _prep(lam, mu, den, stf, shot_ids):
+def para_info(para_fname):
+    """What the parameter file says (host-only; fwi_b200_para_info): the sizes the C ABI will read and write."""
+    out = np.zeros(8, np.int32)
+    check(_lib.lib().fwi_b200_para_info(str(para_fname).encode(), out.ctypes.data_as(c_ip)))
+    keys = ("nz", "nx", "nSteps", "nPml", "nPad", "if_win", "save_scratch")
+    return dict(zip(keys, (int(v) for v in out)))
+
+
+def _check_shapes(nz, nx, nSteps, lam, mu, den, stf, ids):
+    """The C ABI carries no sizes (like the reference's): it reads nz*nx doubles per model array, row shot_id of stf
+    for every shot, and writes nz*nx doubles per gradient.  Refuse anything else here, before pointers are handed over."""
+    for name, a in (("lambda", lam), ("mu", mu), ("den", den)):
+        if a is not None and a.shape != (nz, nx):
+            raise FwiError(-1, f"{name} has shape {a.shape}; the parameter file says (nz, nx) = ({nz}, {nx}) "
+                               "(padded sizes: src/FWI.jl:13-14)")
+    if stf is not None:
+        if stf.ndim != 2 or stf.shape[1] != nSteps:
+            raise FwiError(-1, f"stf has shape {stf.shape}; expected (nShotsTotal, nSteps = {nSteps})")
+        if len(ids) and (int(ids.min()) < 0 or int(ids.max()) >= stf.shape[0]):
+            raise FwiError(-1, f"shot ids {int(ids.min())}..{int(ids.max())} do not index the {stf.shape[0]} rows of stf "
+                               "(row = global shot id, Src_Rec.cu:135)")
+
+
+def _prep(lam, mu, den, stf, shot_ids, para_fname):
     lam, mu, den, stf = _f64(lam), _f64(mu), _f64(den), _f64(stf)
     if stf.ndim == 1:
         stf = stf.reshape(1, -1)
     ids = np.ascontiguousarray(np.asarray(shot_ids, dtype=np.int32).ravel())
-    if lam.shape != mu.shape or lam.shape != den.shape or lam.ndim != 2:
-        raise FwiError(-1, "lambda, mu, den must be 2-D arrays of the same (nz_pad, nx_pad) shape")
+    if len(ids) == 0:
+        raise FwiError(-1, "shot_ids is empty")
+    p = para_info(para_fname)
+    _check_shapes(p["nz"], p["nx"], p["nSteps"], lam, mu, den, stf, ids)
     return lam, mu, den, stf, ids
 
 
 def fwi_op(lam, mu, den, stf, gpu_id, shot_ids, para_fname):
     """FWI loss 0.5 * sum(residual^2) over the shots in `shot_ids` (calc_id 0)."""
-    lam, mu, den, stf, ids = _prep(lam, mu, den, stf, shot_ids)
+    lam, mu, den, stf, ids = _prep(lam, mu, den, stf, shot_ids, para_fname)
     misfit = ctypes.c_double(0.0)
     check(_lib.lib().fwi_b200_forward(ctypes.cast(ctypes.byref(misfit), c_dp), _dp(lam), _dp(mu), _dp(den), _dp(stf),
                                       int(gpu_id), len(ids), ids.ctypes.data_as(c_ip), str(para_fname).encode()))
@@ -53,7 +79,7 @@ def fwi_op(lam, mu, den, stf, gpu_id, shot_ids, para_fname):
 
 def fwi_obs_op(lam, mu, den, stf, gpu_id, shot_ids, para_fname):
     """Forward modelling: writes data_dir_name/Shot<id>.bin, returns 0.0 (calc_id 2)."""
-    lam, mu, den, stf, ids = _prep(lam, mu, den, stf, shot_ids)
+    lam, mu, den, stf, ids = _prep(lam, mu, den, stf, shot_ids, para_fname)
     misfit = ctypes.c_double(0.0)
     check(_lib.lib().fwi_b200_obscalc(ctypes.cast(ctypes.byref(misfit), c_dp), _dp(lam), _dp(mu), _dp(den), _dp(stf),
                                       int(gpu_id), len(ids), ids.ctypes.data_as(c_ip), str(para_fname).encode()))
@@ -67,7 +93,7 @@ def fwi_op_grad(lam, mu, den, stf, gpu_id, shot_ids, para_fname):
     and leaves the rest uninitialised; here the rows of the group's GLOBAL shot ids
     are filled and every other row is zero, which is what an optimiser over stf needs.
     """
-    lam, mu, den, stf, ids = _prep(lam, mu, den, stf, shot_ids)
+    lam, mu, den, stf, ids = _prep(lam, mu, den, stf, shot_ids, para_fname)
     gl, gm, gd = np.zeros_like(lam), np.zeros_like(lam), np.zeros_like(lam)
     gs_group = np.zeros((len(ids), stf.shape[1]), np.float64)
     check(_lib.lib().fwi_b200_backward(_dp(gl), _dp(gm), _dp(gd), _dp(gs_group), _dp(lam), _dp(mu), _dp(den), _dp(stf),
@@ -79,7 +105,7 @@ def fwi_op_grad(lam, mu, den, stf, gpu_id, shot_ids, para_fname):
 
 def fwi_op_and_grad(lam, mu, den, stf, gpu_id, shot_ids, para_fname):
     """Loss AND gradients from one forward propagation (the reference propagates twice)."""
-    lam, mu, den, stf, ids = _prep(lam, mu, den, stf, shot_ids)
+    lam, mu, den, stf, ids = _prep(lam, mu, den, stf, shot_ids, para_fname)
     gl, gm, gd = np.zeros_like(lam), np.zeros_like(lam), np.zeros_like(lam)
     gs_group = np.zeros((len(ids), stf.shape[1]), np.float64)
     misfit = ctypes.c_double(0.0)
@@ -94,7 +120,7 @@ def fwi_op_and_grad(lam, mu, den, stf, gpu_id, shot_ids, para_fname):
 def fwi_op_and_grad_multi(lam, mu, den, stf, gpu_ids, shot_ids, para_fname):
     """Loss and gradients with the shots of the group sharded over several GPUs of THIS process
     (fwi_b200_gradient_multi): shot k goes to gpu_ids[k % len(gpu_ids)], the devices run concurrently."""
-    lam, mu, den, stf, ids = _prep(lam, mu, den, stf, shot_ids)
+    lam, mu, den, stf, ids = _prep(lam, mu, den, stf, shot_ids, para_fname)
     gpus = np.ascontiguousarray(np.asarray(gpu_ids, dtype=np.int32).ravel())
     gl, gm, gd = np.zeros_like(lam), np.zeros_like(lam), np.zeros_like(lam)
     gs_group = np.zeros((len(ids), stf.shape[1]), np.float64)
@@ -105,6 +131,39 @@ def fwi_op_and_grad_multi(lam, mu, den, stf, gpu_ids, shot_ids, para_fname):
     gs = np.zeros_like(stf)
     gs[ids] = gs_group
     return float(misfit.value), gl, gm, gd, gs
+
+
+def timelapse(surveys, stf, gpu_ids, shot_ids):
+    """fwi_b200_timelapse: misfit + gradients of several surveys (baseline + monitors) in one call.
+    surveys: sequence of (para_fname, lam, mu, den).  Returns [(misfit, gl, gm, gd)] in survey order."""
+    S = len(surveys)
+    if S == 0:
+        return []
+    ids = np.ascontiguousarray(np.asarray(shot_ids, dtype=np.int32).ravel())
+    gpus = np.ascontiguousarray(np.asarray(gpu_ids, dtype=np.int32).ravel())
+    stf = _f64(stf)
+    if stf.ndim == 1:
+        stf = stf.reshape(1, -1)
+    models, paras = [], []
+    for para, lam, mu, den in surveys:
+        lam, mu, den = _f64(lam), _f64(mu), _f64(den)
+        p = para_info(para)
+        _check_shapes(p["nz"], p["nx"], p["nSteps"], lam, mu, den, stf, ids)
+        models.append((lam, mu, den))
+        paras.append(str(para).encode())
+    grads = [tuple(np.zeros_like(m[0]) for _ in range(3)) for m in models]
+    misfit = np.zeros(S, np.float64)
+    arr = lambda items: (c_dp * S)(*[_dp(a) for a in items])
+    check(_lib.lib().fwi_b200_timelapse(
+        S, (ctypes.c_char_p * S)(*paras), arr([m[0] for m in models]), arr([m[1] for m in models]),
+        arr([m[2] for m in models]), _dp(stf), len(gpus), gpus.ctypes.data_as(c_ip), len(ids), ids.ctypes.data_as(c_ip),
+        _dp(misfit), arr([g[0] for g in grads]), arr([g[1] for g in grads]), arr([g[2] for g in grads])))
+    return [(float(misfit[i]),) + grads[i] for i in range(S)]
+
+
+def set_option(name, value):
+    """Developer A/B switches of the library (fwi_b200_set_option)."""
+    check(_lib.lib().fwi_b200_set_option(str(name).encode(), int(value)))
 
 
 def grid_info(para_fname):
@@ -180,18 +239,26 @@ class Plan:
 
     def set_model(self, lam, mu, den):
         lam, mu, den = _f64(lam), _f64(mu), _f64(den)
-        assert lam.shape == (self.nz, self.nx) == mu.shape == den.shape
+        _check_shapes(self.nz, self.nx, self.nSteps, lam, mu, den, None, self.shot_ids)
         check(self._L.fwi_b200_plan_set_model(self._h, _dp(lam), _dp(mu), _dp(den)))
 
     def set_stf(self, stf):
         stf = _f64(stf)
         if stf.ndim == 1:
             stf = stf.reshape(1, -1)
-        assert stf.shape[1] == self.nSteps and stf.shape[0] > int(self.shot_ids.max())
+        _check_shapes(self.nz, self.nx, self.nSteps, None, None, None, stf, self.shot_ids)
         check(self._L.fwi_b200_plan_set_stf(self._h, _dp(stf)))
 
     def set_obs(self, ishot, obs):
+        """Observed data of the i-th shot of the group, (nrec, nSteps) float32 with time fastest (the Shot<id>.bin
+        layout), kept resident on the device: no disk round trip per evaluation."""
         obs = np.ascontiguousarray(np.asarray(obs, dtype=np.float32))
+        if not 0 <= int(ishot) < self.group_size:
+            raise FwiError(-1, f"set_obs: shot position {ishot} outside the group of {self.group_size}")
+        nrec = self.shot_geometry(ishot)[2]
+        if obs.shape != (nrec, self.nSteps):
+            raise FwiError(-1, f"set_obs: obs has shape {obs.shape}; shot {int(self.shot_ids[ishot])} has "
+                               f"(nrec, nSteps) = ({nrec}, {self.nSteps})")
         check(self._L.fwi_b200_plan_set_obs(self._h, int(ishot), obs.ctypes.data_as(c_fp)))
 
     def load_obs_files(self):

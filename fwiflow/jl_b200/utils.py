@@ -67,8 +67,8 @@ def paraGen(nz, nx, dz, dx, nSteps, dt, f0, nPml, nPad, para_fname, survey_fname
         para["scratch_dir_name"] = str(scratch_dir_name)
         if not os.path.isdir(scratch_dir_name):
             os.makedirs(scratch_dir_name, exist_ok=True)
-    with open(para_fname, "w") as f:
-        f.write(json.dumps(para, separators=(",", ":")))  # ONE line: the reference reads one getline
+    with open(para_fname, "w", encoding="utf-8") as f:   # ONE line: the reference reads one getline; paths as raw UTF-8
+        f.write(json.dumps(para, separators=(",", ":"), ensure_ascii=False))
     return para
 
 
@@ -98,8 +98,8 @@ def surveyGen(z_src, x_src, z_rec, x_rec, survey_fname, Windows=None, Weights=No
         if Weights is not None:
             shot["weights"] = list(Weights[f"shot{i}"]["weights"])
         survey[f"shot{i}"] = shot
-    with open(survey_fname, "w") as f:
-        f.write(json.dumps(survey, separators=(",", ":")))
+    with open(survey_fname, "w", encoding="utf-8") as f:
+        f.write(json.dumps(survey, separators=(",", ":"), ensure_ascii=False))
     return survey
 
 

@@ -82,7 +82,10 @@ int fwi_b200_misfit_and_gradient(double *misfit, double *grad_Lambda, double *gr
 
 /* The same evaluation with the shots of the group sharded over `ngpu` devices of this process:
  * shot k of the group goes to gpu_ids[k % ngpu], every device evaluates its shard concurrently (one host thread and
- * one cached plan per device), and the per-device misfits / gradients are summed.  Replaces the reference's manual
+ * one cached plan per device, nothing synchronises), and the packed per-device results [grad_Lambda | grad_Mu |
+ * grad_Den | misfit] are summed ON THE DEVICES with one ncclAllReduce (float32, 3 nz nx + 1 values, communicators from
+ * ncclCommInitAll, created once per device list; NCCL is bound with dlopen("libnccl.so.2")) on each plan's stream;
+ * the reduced buffer is copied to the host once, from the first device.  Replaces the reference's manual
  * sharding over several fwi_op calls with different gpu_id (test/TestFWI.jl:63-69) -- without its doubly counted
  * boundary shots.  grad_stf rows are in the order of shot_ids.  Any output pointer may be NULL.
  * (Across PROCESSES, one per GPU, use the plan API + an NCCL all-reduce of fwi_b200_plan_result_device(): dist.py.) */
@@ -90,6 +93,26 @@ int fwi_b200_gradient_multi(double *misfit, double *grad_Lambda, double *grad_Mu
                             double *grad_stf, const double *Lambda, const double *Mu,
                             const double *Den, const double *stf, int ngpu, const int *gpu_ids,
                             int group_size, const int *shot_ids, const char *para_fname);
+
+/* Time-lapse (flow-coupled) FWI in one call: misfit + gradients of `nsurveys` surveys (baseline + monitors), each with
+ * its own parameter file / survey file / Data directory and its own model, as the reference's coupled inversion
+ * evaluates them with one fwi_op per survey (docs/codes/src_fwi_coupled/main_two_phase_flow_inversion.jl:50-62,84-93).
+ * Survey i runs on gpu_ids[i % ngpu]; devices work concurrently (one host thread each), surveys mapped to the same
+ * device run back to back on cached plans that stay resident between calls.  All surveys use the shots `shot_ids`
+ * and the source time functions `stf`.  misfit[nsurveys]; grad_*[i] may be NULL (per survey or the whole array). */
+int fwi_b200_timelapse(int nsurveys, const char *const *para_fnames, const double *const *Lambda,
+                       const double *const *Mu, const double *const *Den, const double *stf, int ngpu,
+                       const int *gpu_ids, int group_size, const int *shot_ids, double *misfit,
+                       double *const *grad_Lambda, double *const *grad_Mu, double *const *grad_Den);
+
+/* Host-only: what the parameter file says (Parameter.cpp:41-144), so that a binding can check the shapes of the
+ * caller's arrays before handing pointers over -- the entry points above carry no sizes, exactly like the reference's.
+ * out[8] = { nz, nx, nSteps, nPoints_pml, nPad, if_win, scratch_dir_name present, 0 }. */
+int fwi_b200_para_info(const char *para_fname, int *out);
+
+/* Developer A/B switches (not part of the reference's surface).  "rev_lean": -1 pick the build of the reverse-time
+ * kernel by working-set size (default), 0 / 1 force the double-buffered / LEAN build. */
+int fwi_b200_set_option(const char *name, int value);
 
 /* Host-only: the device layout this library derives from a parameter file (no GPU needed).
  * out[12] = { nz, nx, column pitch, zlive (rows >= zlive are never stored), z_off (row of the first forward/adjoint

@@ -29,6 +29,7 @@ class _OraclePlan:
 
     def __init__(self, para, ids, c):
         from oracle import oracle_py as op
+        assert len(ids) > 0, "a plan needs at least one shot (fwi_b200_plan_create refuses group_size <= 0)"
         self.op, self.para, self.ids, self.c = op, para, np.asarray(ids, np.int32), c
         self.nz, self.nx = c.nz_pad, c.nx_pad
         self.buf = torch.zeros(3 * self.nz * self.nx + 1, dtype=torch.float32)
@@ -92,3 +93,23 @@ def test_two_rank_gradient_equals_single_process():
     assert rel(two["gd"], one["grad_den"]) < 1e-5
     assert abs(float(two["misfit"]) - j1) <= 1e-5 * j1
     assert two["gs"][0, 0] == 1.0 and two["gs"][1, 0] == 2.0   # stf rows land on their GLOBAL shot id
+
+
+def test_more_ranks_than_shots():
+    """world_size 3, two shots: the rank without a shot creates no plan and contributes zeros, nobody blocks."""
+    from oracle import oracle_py as op
+    c = golden_cases()["small_elastic"]
+    wd = tempfile.mkdtemp()
+    para = c.write_files(wd)
+    lam, mu, rho = c.moduli("true")
+    lam0, mu0, rho0 = c.moduli("init")
+    ids = np.arange(c.nShots)
+    assert c.nShots == 2
+    op.oracle_cufd(2, lam, mu, rho, c.stf, ids, para)
+    out = os.path.join(wd, "three_rank.npz")
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(3, port, wd, out), nprocs=3, join=True)
+    three = np.load(out)
+    one = op.oracle_cufd(1, lam0, mu0, rho0, c.stf, ids, para)
+    assert rel(three["gl"], one["grad_lambda"]) < 1e-5 and rel(three["gd"], one["grad_den"]) < 1e-5
+    assert three["gs"][0, 0] == 1.0 and three["gs"][1, 0] == 2.0

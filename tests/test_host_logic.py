@@ -282,3 +282,58 @@ def test_timelapse_driver_spreads_surveys_over_gpus(monkeypatch):
     assert sorted(calls) == sorted([(k, (3, 5)[k % 2], True) for k in range(6)])
     with pytest.raises(RuntimeError, match="survey failed"):
         F.timelapse_misfit_and_gradients([(1, None, None, None), ("boom", None, None, None)], None, gpu_ids=(0,))
+
+
+def test_array_shapes_are_checked_against_the_para_file(lib_built):
+    """The C ABI carries no sizes (like the reference's cufd): the binding refuses arrays whose shapes do not match the
+    parameter file instead of letting the library read or write past them."""
+    c, wd, para = _case_files()
+    lam, mu, rho = c.moduli("true")
+    info = ops.para_info(para)
+    assert (info["nz"], info["nx"], info["nSteps"]) == (c.nz_pad, c.nx_pad, c.nSteps)
+    P = c.nPml
+    unpadded = lam[P:P + c.nz, P:P + c.nx]
+    for call in (ops.fwi_op, ops.fwi_obs_op, ops.fwi_op_grad, ops.fwi_op_and_grad):
+        with pytest.raises(ops.FwiError, match="parameter file says"):
+            call(unpadded, unpadded, unpadded, c.stf, 0, [0], para)              # unpadded (nz, nx) model
+        with pytest.raises(ops.FwiError, match="nSteps"):
+            call(lam, mu, rho, c.stf[:, :-1], 0, [0], para)                       # wrong record length
+        with pytest.raises(ops.FwiError, match="rows of stf"):
+            call(lam, mu, rho, c.stf[0], 0, [1], para)                            # 1-D stf = one row, shot id 1
+        with pytest.raises(ops.FwiError, match="empty"):
+            call(lam, mu, rho, c.stf, 0, [], para)
+    with pytest.raises(ops.FwiError):
+        ops.fwi_op_and_grad_multi(lam[:-1], mu[:-1], rho[:-1], c.stf, [0, 1], [0, 1], para)
+    with pytest.raises(ops.FwiError):
+        ops.timelapse([(para, lam, mu, rho), (para, lam.T, mu.T, rho.T)], c.stf, [0], [0, 1])
+
+
+def test_json_unicode_paths(lib_built):
+    """Paths with non-ASCII characters: written raw (UTF-8) by paraGen, and decoded from \\uXXXX escapes -- including a
+    surrogate pair -- when another writer (json.dumps' default, rapidjson) escaped them."""
+    import torch
+    from fwiflow.jl_b200 import synthetic
+    c = synthetic.case_small("u", nz=40, nx=48, nSteps=50, nshots=1)
+    base = tempfile.mkdtemp(prefix="fwi_unicode_")
+    wd = os.path.join(base, "données_é_\U0001F30A")
+    para = c.write_files(wd)
+    raw = open(para, encoding="utf-8").read()
+    assert "données" in raw                                    # written as UTF-8, one line
+    esc = os.path.join(base, "para_escaped.json")
+    open(esc, "w").write(json.dumps(json.loads(raw)))          # ensure_ascii=True: é, 🌊
+    assert "\\u00e9" in open(esc).read() and "\\ud83c\\udf0a" in open(esc).read()
+    lam, mu, rho = c.moduli("true")
+    for fn in (para, esc):
+        assert ops.para_info(fn)["nz"] == c.nz_pad
+        if torch.cuda.is_available():
+            ops.fwi_obs_op(lam, mu, rho, c.stf, 0, [0], fn)
+            assert os.path.exists(os.path.join(wd, "Data", "Shot0.bin"))
+        else:
+            with pytest.raises(ops.FwiError) as ei:
+                ops.fwi_obs_op(lam, mu, rho, c.stf, 0, [0], fn)
+            assert ei.value.code == -5, str(ei.value)          # the survey file WAS found (else -2): only the GPU is missing
+    bad = os.path.join(base, "para_lone.json")
+    open(bad, "w").write(raw.replace("données", "donn\\ud83c"))
+    with pytest.raises(ops.FwiError) as ei:
+        ops.para_info(bad)
+    assert ei.value.code == -3
