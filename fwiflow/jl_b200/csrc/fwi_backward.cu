@@ -741,6 +741,602 @@ __global__ void __launch_bounds__(NCOMPUTE, 1) adj_step_kernel(const __grid_cons
   if (a.indep) pdl_wait();
 }
 
+
+// =================================================================================================
+// bwd_step_kernel: ONE launch per time index of the backward loop.  Per (tile, shot) work item it runs
+//   phase A: the adjoint step of time index it+1 (exactly adj_step_kernel's item), then
+//   phase R: the reverse-time step it+1 -> it with frame restore and the imaging condition (rev_image_kernel's item),
+// on the same thread <-> quad mapping.  The imaging condition of index `it` needs the adjoint state AFTER the adjoint
+// step it+1 (libCUFD.cu:374-427: el_velocity(false) / el_stress(false) run before this index's adjoint kernels), i.e.
+// exactly what phase A has just produced for the quad the thread owns: the five adjoint quads go from phase A to
+// phase R IN REGISTERS.  Against the two separate launches this removes the second read of the adjoint state (20 B per
+// box cell from HBM, plus its L2 prefetch boxes), one launch per time index, and -- with the new adjoint velocities of
+// the whole 64 x 32 region sitting in phase A's shared tile -- lets the density spray (el_velocity.cu:105-110) be
+// gathered in the kernel: four accumulator planes instead of five.
+//   Ring: the two phases of an item are two consecutive "sub-items" of one 2-slot TMA ring (slot = the larger of the two
+//   box sets, 47.5 KB); the producer lane runs two sub-items ahead.  Tiles that lie outside the reconstruction
+//   rectangle have no phase R.  Each phase has ONE block barrier and its own hand-over tiles, so the next write to a
+//   tile is always separated from the last read by the other phase's barrier (tiles without a phase R add one).
+// =================================================================================================
+constexpr int MNS = 2;
+constexpr int MSTAGE_BYTES = RSTAGE_BYTES > ASTAGE_BYTES ? RSTAGE_BYTES : ASTAGE_BYTES;
+constexpr int MFRM_BYTES = NOWN * 3 * 16;                 // landing slots of the saved stress frames: owner quads only
+constexpr int MGB_BYTES = SCOLS * SPITCH * 4;             // rho-b imaging term of the region (x-1 neighbour hand-over)
+constexpr size_t MRG_SMEM = (size_t)MNS * MSTAGE_BYTES + AV_BYTES + APHI_BYTES + AINJ_BYTES + SV_BYTES + MFRM_BYTES + MGB_BYTES +
+                            (MNS + 1) * sizeof(TileDesc) + MNS * 8 + 128;
+static_assert(MSTAGE_BYTES % 128 == 0, "TMA destination alignment");
+enum : int { TF_REV = 8 };   // phase-A descriptor: the tile has a phase R
+
+__global__ void __launch_bounds__(NCOMPUTE, 1) bwd_step_kernel(const __grid_constant__ BwdArgs a) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char *base = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
+  unsigned char *hp = base + MNS * MSTAGE_BYTES;
+  float *s_va = reinterpret_cast<float *>(hp);                                   // [2][SCOLS][SPITCH] new adjoint velocities (phase A)
+  float *s_phi = reinterpret_cast<float *>(hp + AV_BYTES);                       // [4][SCOLS][SPITCH] new phi (phase A)
+  float *s_inj = reinterpret_cast<float *>(hp + AV_BYTES + APHI_BYTES);          // [SCOLS][SPITCH] residual injection table (phase A)
+  float *s_vr = reinterpret_cast<float *>(hp + AV_BYTES + APHI_BYTES + AINJ_BYTES);              // [2][SCOLS][SPITCH] rewound velocities (phase R)
+  float *s_frm = reinterpret_cast<float *>(hp + AV_BYTES + APHI_BYTES + AINJ_BYTES + SV_BYTES);  // [3][NOWN] quads: saved szz sxx sxz (phase R)
+  float *s_gb = reinterpret_cast<float *>(hp + AV_BYTES + APHI_BYTES + AINJ_BYTES + SV_BYTES + MFRM_BYTES);   // [SCOLS][SPITCH] (phase R)
+  unsigned char *tail = hp + AV_BYTES + APHI_BYTES + AINJ_BYTES + SV_BYTES + MFRM_BYTES + MGB_BYTES;
+  TileDesc *sdesc = reinterpret_cast<TileDesc *>(tail);                          // [MNS + 1]
+  uint64_t *full = reinterpret_cast<uint64_t *>(tail + (MNS + 1) * sizeof(TileDesc));   // [MNS]
+
+  const Grid &g = a.g;
+  const int tid = threadIdx.x;
+  const int ntiles = g.tiles_z * g.tiles_x;
+  const int nitems = a.batch * ntiles;
+  const int stride = gridDim.x;   // round-robin item order (see fwd_step_kernel)
+  const int it_a = a.it + 1;      // time index of the adjoint step in phase A; phase R rewinds it_a -> a.it
+  const int ain = a.cur_a ? S_AB : S_AA, aout = a.cur_a ? S_AA : S_AB;
+  const int psi_i = a.cur_a ? S_PSI_B : S_PSI_A, psi_o = a.cur_a ? S_PSI_A : S_PSI_B;
+  const int phi_i = a.cur_a ? S_PHI_B : S_PHI_A, phi_o = a.cur_a ? S_PHI_A : S_PHI_B;
+  const int fin = a.cur_f ? S_FB : S_FA, fout = a.cur_f ? S_FA : S_FB;
+  const int P = g.P;
+  const long long pl = g.plane;
+  const int nxp = a.pr.nxp;
+  const int zp_hi = g.nz - g.nPml - g.nPad - 1;
+  const int zq_lo = g.nPml + 2, zq_hi = g.nz - g.nPad - g.nPml - 3;   // psi arrays matter within 2 cells of the layers (Q5)
+  const int xq_lo = g.nPml + 2, xq_hi = g.nx - g.nPml - 3;
+
+  pdl_launch_dependents();
+  if (tid == 0) {
+    for (int s = 0; s < MNS; s++) mbar_init(&full[s], 1);
+    fence_barrier_init();
+  }
+  for (int i = tid; i < AINJ_BYTES / 16; i += NCOMPUTE) reinterpret_cast<float4 *>(s_inj)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncthreads();
+
+  // ---- producer: the sub-item sequence A(item), [R(item)], A(item + stride), ... two sub-items ahead ----
+  int p_item = blockIdx.x, p_kind = 0;   // only the producer lane's copies are used
+  auto produce_next = [&](int stage, int ds, bool first) {
+    if (p_item >= nitems) return;
+    const int io = a.order ? nitems - 1 - p_item : p_item;
+    const int tile = io / a.batch, shot = io - tile * a.batch;   // shot fastest
+    const int z0 = (tile % g.tiles_z) * TILE_Z + g.z_off, x0 = (tile / g.tiles_z) * TILE_X;
+    const int sz = a.st.src_z[shot], sx = a.st.src_x[shot];
+    const bool has_rev = !(z0 > g.zhi + 2 || z0 + TILE_Z - 1 < g.zlo - 2 || x0 > g.xhi + 2 || x0 + TILE_X - 1 < g.xlo - 2);
+    TileDesc d;
+    d.soff = (long long)shot * S_COUNT * pl + (long long)x0 * P + z0;
+    d.moff = x0 * P + z0;
+    d.z0 = z0; d.x0 = x0; d.shot = shot; d.tile = tile; d.sz = sz; d.sx = sx;
+    d.pad[0] = d.pad[1] = d.pad[2] = d.pad[3] = 0;
+    unsigned char *sb = base + stage * MSTAGE_BYTES;
+    int fl = 0;
+    if (sz >= z0 && sz < z0 + TILE_Z && sx >= x0 && sx < x0 + TILE_X) fl |= TF_SRC;
+    if (p_kind == 0) {   // ---- phase A boxes: adjoint stress triple (halo 8 / 3) + adjoint velocity pair (halo 4 / 2) ----
+      d.r0 = a.st.rec_ptr[shot * (ntiles + 1) + tile];
+      d.r1 = a.st.rec_ptr[shot * (ntiles + 1) + tile + 1];
+      if ((z0 - 4 < zq_lo) || (z0 + TILE_Z + 3 > zq_hi) || (x0 - 2 < xq_lo) || (x0 + TILE_X + 1 > xq_hi)) fl |= TF_PML;
+      if (has_rev) fl |= TF_REV;
+      d.flags = fl;
+      sdesc[ds] = d;
+      const int p0 = shot * S_COUNT + ain;
+      if (first) pdl_wait();   // everything above reads static tables only
+      mbar_arrive_expect_tx(&full[stage], AS_BYTES + AV_BYTES);
+      tma_load_3d(sb, &a.tm.s3, z0 - 8, x0 - 3 + XM, p0 + F_SZZ, &full[stage]);
+      tma_load_3d(sb + AS_PAD, &a.tm.vn, z0 - 4, x0 - 2 + XM, p0 + F_VZ, &full[stage]);
+#if ADJ_PF_MODEL
+      if (ADJ_PF_MODEL == 1 || shot == 0) tma_prefetch_3d(&a.tm.m5, z0 - 4, x0 - 2 + XM, M_LDT);
+#endif
+#if FWI_L2PF
+      if (fl & TF_PML) {  // CPML memory of the layers this tile touches -> L2
+        const int ps = shot * S_COUNT;
+        if ((z0 - 4 < zq_lo) || (z0 + TILE_Z + 3 > zq_hi)) {
+          tma_prefetch_3d(&a.tm.r1, z0 - 4, x0 - 2 + XM, ps + psi_i + PSI_VX_Z);
+          tma_prefetch_3d(&a.tm.r1, z0 - 4, x0 - 2 + XM, ps + psi_i + PSI_VZ_Z);
+          tma_prefetch_3d(&a.tm.r1, z0 - 4, x0 - 2 + XM, ps + phi_i + PHI_SXZ_Z);
+          tma_prefetch_3d(&a.tm.r1, z0 - 4, x0 - 2 + XM, ps + phi_i + PHI_SZZ_Z);
+        }
+        if ((x0 - 2 < xq_lo) || (x0 + TILE_X + 1 > xq_hi)) {
+          tma_prefetch_3d(&a.tm.r1, z0 - 4, x0 - 2 + XM, ps + psi_i + PSI_VX_X);
+          tma_prefetch_3d(&a.tm.r1, z0 - 4, x0 - 2 + XM, ps + psi_i + PSI_VZ_X);
+          tma_prefetch_3d(&a.tm.r1, z0 - 4, x0 - 2 + XM, ps + phi_i + PHI_SXX_X);
+          tma_prefetch_3d(&a.tm.r1, z0 - 4, x0 - 2 + XM, ps + phi_i + PHI_SXZ_X);
+        }
+      }
+#endif
+      if (has_rev) p_kind = 1; else p_item += stride;
+    } else {   // ---- phase R boxes: forward stress triple of time it+1 (halo 8 / 4) + forward velocity pair (halo 4 / 2) ----
+      d.r0 = d.r1 = 0;
+      if (!(z0 - 4 > g.zlo + 2 && z0 + TILE_Z + 3 < g.zhi - 2 && x0 - 2 > g.xlo + 2 && x0 + TILE_X + 1 < g.xhi - 2)) fl |= TF_FRAME;
+      d.flags = fl;
+      sdesc[ds] = d;
+      const int p0 = shot * S_COUNT + fin;
+      mbar_arrive_expect_tx(&full[stage], RSTAGE_BYTES);
+      tma_load_3d(sb, &a.tm.sw, z0 - 8, x0 - 4 + XM, p0 + F_SZZ, &full[stage]);
+      tma_load_3d(sb + RW_BYTES, &a.tm.vn, z0 - 4, x0 - 2 + XM, p0 + F_VZ, &full[stage]);
+#if FWI_L2PF
+      tma_prefetch_3d(&a.tm.g4, z0, x0 + XM, shot * G_COUNT);   // the four accumulator planes of the owner tile -> L2
+#endif
+      p_kind = 0;
+      p_item += stride;
+    }
+  };
+  if (tid == PRODUCER_TID)
+    for (int s = 0; s < MNS; s++) produce_next(s, s, s == 0);
+  __syncthreads();   // the first descriptors are visible
+  pdl_wait();
+
+  const float dt = g.dt;
+  // adjoint-kernel spelling of the differences: (-c1 (..) + c2 (..)) / h  (el_stress_adj.cu:54-61)
+  const float akz1 = -C1 * g.rdz, akz2 = -C2 * g.rdz, akx1 = -C1 * g.rdx, akx2 = -C2 * g.rdx;
+  const float half_rdt = 0.5f / dt;            // 0.5 byc^2 dt      = (0.5 / dt) (byc dt)^2
+  const float q_rdt = 250000.0f / dt;          // 1e6 mu_bar^2 dt/4 = (250000 / dt) (mu_bar dt)^2
+  const float dt6 = dt * 1e6f;
+  const int q = tid & 15, c = tid >> 4;
+  const bool inner = q >= 1 && q <= TILE_Z / 4 && c >= 2 && c < TILE_X + 2;
+  const int sj = c * SPITCH + 4 * q;
+  const int gx_max = g.nx + XM - 1;
+  const int cm2 = (c > 0 ? 2 : 1) * VPITCH, cp2 = (c < SCOLS - 1 ? 2 : 1) * VPITCH;   // keep halo-column reads in the tile
+  const float *zprof = a.pr.z;
+  float *my_frm = s_frm + 4 * ((q - 1) + (TILE_Z / 4) * (c - 2));   // owner quads only (nobody else uses theirs)
+
+  int stage = 0, phase = 0, ds = 0;
+  auto advance = [&]() {
+    if (++ds == MNS + 1) ds = 0;
+    if (++stage == MNS) { stage = 0; phase ^= 1; }
+  };
+  for (int item = blockIdx.x; item < nitems; item += stride) {
+    // =============================== phase A: adjoint step of time index it_a ===============================
+    const TileDesc d = sdesc[ds];   // written by the producer >= 1 block barrier ago
+    const int gz = d.z0 - 4 + 4 * q, gx = d.x0 - 2 + c;
+    const bool inb = (unsigned)gx < (unsigned)g.nx && (unsigned)gz < (unsigned)g.zlive;
+    const bool owner = inner && inb;
+    float *sq = a.state + g.origin + d.soff + ((long long)(c - 2) * P + 4 * q - 4);   // + slot * pl
+    const float *mq = a.m.ldt + ((long long)min(gx, gx_max) * P + gz);
+    const bool pml_tile = d.flags & TF_PML;
+    const bool has_rev = d.flags & TF_REV;
+    // quad with at least one active cell (2 <= z <= nz-nPad-3, 2 <= x <= nx-3): the only ones that touch CPML memory
+    const bool actq = gx >= 2 && gx <= g.ax_hi && gz + 3 >= 2 && gz <= g.az_hi;
+    const F4 ldt = ld4(mq), l2mdt = ld4(mq + pl), amudt = ld4(mq + 2 * pl);
+    const F4 byadt = ld4(mq + 3 * pl), bybdt = ld4(mq + 4 * pl);
+    const bool near_src = FWI_F64_UPDATE > 1 && abs(gx - d.sx) <= FWI_F64_UPDATE && gz + 3 >= d.sz - FWI_F64_UPDATE &&
+                          gz <= d.sz + FWI_F64_UPDATE;   // see fwd_step_kernel
+    mbar_wait(&full[stage], phase);
+
+    F4 vz, vx;          // adjoint velocities of the quad: pre-update, then new
+    F4 szz, sxx, sxz;   // adjoint stresses of the quad (owner threads): pre-update, then new
+    {
+      const unsigned char *sb = base + stage * MSTAGE_BYTES;
+      const float *sa = reinterpret_cast<const float *>(sb);              // [3][VCOLS][VPITCH]: adjoint szz sxx sxz
+      const float *sva = reinterpret_cast<const float *>(sb + AS_PAD);    // [2][SCOLS][SPITCH]: adjoint vz vx
+
+      // ---- adjoint velocity on 16 quads x 32 columns (el_velocity_adj.cu:56-100) ----
+      const float *zz = sa + (c + 1) * VPITCH + 4 * (q + 1);
+      const float *xx = zz + VCOLS * VPITCH;
+      const float *xz = xx + VCOLS * VPITCH;
+      const F4 zzB = ld4(zz), xxB = ld4(xx), xzB = ld4(xz);
+      float dszz_dx[4], dsxx_dx[4], dsxz_dz[4], dszz_dz[4], dsxx_dz[4], dsxz_dx[4];
+      dx4(ld4(zz - VPITCH), zzB, ld4(zz + VPITCH), ld4(zz + cp2), akx1, akx2, dszz_dx);   // ad_plus_x
+      dx4(ld4(xx - VPITCH), xxB, ld4(xx + VPITCH), ld4(xx + cp2), akx1, akx2, dsxx_dx);
+      dx4(ld4(xz - cm2), ld4(xz - VPITCH), xzB, ld4(xz + VPITCH), akx1, akx2, dsxz_dx);   // ad_minus_x
+      dz_plus4(ld4(zz - 4), zzB, ld4(zz + 4), akz1, akz2, dszz_dz);
+      dz_plus4(ld4(xx - 4), xxB, ld4(xx + 4), akz1, akz2, dsxx_dz);
+      dz_minus4(ld4(xz - 4), xzB, ld4(xz + 4), akz1, akz2, dsxz_dz);
+      vz = ld4(sva + sj);
+      vx = ld4(sva + SCOLS * SPITCH + sj);
+      szz = zzB; sxx = xxB; sxz = xzB;
+
+      // source_grad (utilities.cu:582-593): adjoint stress at the source BEFORE this step's injection and update
+      if ((d.flags & TF_SRC) && owner && gx == d.sx && (unsigned)(d.sz - gz) < 4u) {
+        const int ks = d.sz - gz;
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < 4; kk++)
+          if (kk == ks) { s1 = zzB.v[kk]; s2 = xxB.v[kk]; }
+        a.stf_grad[d.shot * g.nSteps + it_a] = (float)(-((double)s1 + 3.0 * (double)s2) * (double)dt);
+      }
+      // residual injection at time index it_a (utilities.cu:569-580): receivers of this tile add into the table
+      for (int r = d.r0 + tid; r < d.r1; r += NCOMPUTE) {
+        const int loc = a.st.rec_loc[d.shot * a.st.nrp + r];
+        const int lz = loc & 0xffff, lx = loc >> 16;
+        atomicAdd(&s_inj[(lx + 2) * SPITCH + lz + 4],
+                  a.res[((long long)d.shot * g.nSteps + it_a) * a.st.nrp + a.st.rec_id[d.shot * a.st.nrp + r]]);
+      }
+
+      float rKx = 1.0f, rKxh = 1.0f, ax = 0.0f, axh = 0.0f;
+      F4 rKz{{1.f, 1.f, 1.f, 1.f}}, rKzh{{1.f, 1.f, 1.f, 1.f}}, az = zero4(), azh = zero4();
+      bool zq_pml = false, xp = false;
+      if (!pml_tile) {
+#pragma unroll
+        for (int kk = 0; kk < 4; kk++) {  // coefficients carry dt and are 0 on inactive cells
+          // el_velocity_adj.cu:69-71,90-92: the (lambda + 2.0 mu) term promotes the sum to double
+          if (FWI_F64_UPDATE == 1 || (FWI_F64_UPDATE > 1 && near_src)) {
+            vx.v[kk] = (float)((double)vx.v[kk] + ((double)ldt.v[kk] * (double)dszz_dx[kk] + (double)l2mdt.v[kk] * (double)dsxx_dx[kk] +
+                                                   (double)amudt.v[kk] * (double)dsxz_dz[kk]));
+            vz.v[kk] = (float)((double)vz.v[kk] + ((double)l2mdt.v[kk] * (double)dszz_dz[kk] + (double)ldt.v[kk] * (double)dsxx_dz[kk] +
+                                                   (double)amudt.v[kk] * (double)dsxz_dx[kk]));
+          } else {
+            vx.v[kk] += fmaf(ldt.v[kk], dszz_dx[kk], fmaf(l2mdt.v[kk], dsxx_dx[kk], amudt.v[kk] * dsxz_dz[kk]));
+            vz.v[kk] += fmaf(l2mdt.v[kk], dszz_dz[kk], fmaf(ldt.v[kk], dsxx_dz[kk], amudt.v[kk] * dsxz_dx[kk]));
+          }
+        }
+      } else {
+        F4 f_szz_z = zero4(), f_sxz_x = zero4(), f_sxz_z = zero4(), f_sxx_x = zero4();   // new phi of the quad
+        if (actq) {
+          float tpx1[4] = {0, 0, 0, 0}, tpx2[4] = {0, 0, 0, 0}, tpz1[4] = {0, 0, 0, 0}, tpz2[4] = {0, 0, 0, 0};
+          const float *xpf = a.pr.x + gx + XM;
+          rKx = xpf[PR_RK * nxp];
+          rKxh = xpf[PR_RKH * nxp];
+          ax = xpf[PR_A * nxp];
+          axh = xpf[PR_AH * nxp];
+          xp = gx < g.nPml || gx > g.nx - g.nPml - 1;
+          zq_pml = gz < g.nPml || gz + 3 > zp_hi;
+          if (ax != 0.0f) {  // a_x * D+x(psi_xx)
+            const float *p = sq + (psi_i + PSI_VX_X) * pl;
+            float dd[4];
+            dx4(ld4(p - P), ld4(p), ld4(p + P), ld4(p + 2 * P), akx1, akx2, dd);
+#pragma unroll
+            for (int kk = 0; kk < 4; kk++) tpx1[kk] = ax * dd[kk];
+          }
+          if (axh != 0.0f) {  // a_x_half * D-x(psi_zx)
+            const float *p = sq + (psi_i + PSI_VZ_X) * pl;
+            float dd[4];
+            dx4(ld4(p - 2 * P), ld4(p - P), ld4(p), ld4(p + P), akx1, akx2, dd);
+#pragma unroll
+            for (int kk = 0; kk < 4; kk++) tpz2[kk] = axh * dd[kk];
+          }
+          if (zq_pml) {
+            rKz = ld4(zprof + PR_RK * P + gz);
+            rKzh = ld4(zprof + PR_RKH * P + gz);
+            az = ld4(zprof + PR_A * P + gz);
+            azh = ld4(zprof + PR_AH * P + gz);
+            const float *p1 = sq + (psi_i + PSI_VX_Z) * pl;  // a_z_half * D-z(psi_xz)
+            const float *p2 = sq + (psi_i + PSI_VZ_Z) * pl;  // a_z * D+z(psi_zz)
+            float dd[4];
+            dz_minus4(ld4(p1 - 4), ld4(p1), ld4(p1 + 4), akz1, akz2, dd);
+#pragma unroll
+            for (int kk = 0; kk < 4; kk++) tpx2[kk] = azh.v[kk] * dd[kk];
+            dz_plus4(ld4(p2 - 4), ld4(p2), ld4(p2 + 4), akz1, akz2, dd);
+#pragma unroll
+            for (int kk = 0; kk < 4; kk++) tpz1[kk] = az.v[kk] * dd[kk];
+          }
+#pragma unroll
+          for (int kk = 0; kk < 4; kk++) {
+            const int z = gz + kk;
+            if (z >= 2 && z <= g.az_hi) {
+              if (FWI_F64_UPDATE == 1 || (FWI_F64_UPDATE > 1 && near_src)) {
+                vx.v[kk] = (float)((double)vx.v[kk] + ((double)tpx1[kk] + (double)(ldt.v[kk] * dszz_dx[kk] * rKx) +
+                                                       (double)l2mdt.v[kk] * (double)(dsxx_dx[kk] * rKx) + (double)tpx2[kk] +
+                                                       (double)(amudt.v[kk] * rKzh.v[kk] * dsxz_dz[kk])));
+                vz.v[kk] = (float)((double)vz.v[kk] + ((double)tpz1[kk] + (double)l2mdt.v[kk] * (double)(dszz_dz[kk] * rKz.v[kk]) +
+                                                       (double)(ldt.v[kk] * dsxx_dz[kk] * rKz.v[kk]) + (double)tpz2[kk] +
+                                                       (double)(amudt.v[kk] * rKxh * dsxz_dx[kk])));
+              } else {
+                vx.v[kk] += tpx1[kk] + ldt.v[kk] * dszz_dx[kk] * rKx + l2mdt.v[kk] * dsxx_dx[kk] * rKx + tpx2[kk] +
+                            amudt.v[kk] * rKzh.v[kk] * dsxz_dz[kk];
+                vz.v[kk] += tpz1[kk] + l2mdt.v[kk] * dszz_dz[kk] * rKz.v[kk] + ldt.v[kk] * dsxx_dz[kk] * rKz.v[kk] + tpz2[kk] +
+                            amudt.v[kk] * rKxh * dsxz_dx[kk];
+              }
+            }
+          }
+          // phi memory of the quad, CPML cells only (el_velocity_adj.cu:74-79,95-100); buoyancies are 0 on inactive cells
+          if (xp) {
+            const float bx = xpf[PR_B * nxp], bxh = xpf[PR_BH * nxp];
+            f_sxx_x = ld4s(sq + (phi_i + PHI_SXX_X) * pl);
+            f_sxz_x = ld4s(sq + (phi_i + PHI_SXZ_X) * pl);
+#pragma unroll
+            for (int kk = 0; kk < 4; kk++) {
+              f_sxx_x.v[kk] = fmaf(bxh, f_sxx_x.v[kk], bybdt.v[kk] * vx.v[kk]);
+              f_sxz_x.v[kk] = fmaf(bx, f_sxz_x.v[kk], byadt.v[kk] * vz.v[kk]);
+            }
+            if (owner) {
+              st4(sq + (phi_o + PHI_SXX_X) * pl, f_sxx_x);
+              st4(sq + (phi_o + PHI_SXZ_X) * pl, f_sxz_x);
+            }
+          }
+          if (zq_pml) {
+            const F4 bz = ld4(zprof + PR_B * P + gz), bzh = ld4(zprof + PR_BH * P + gz);
+            f_sxz_z = ld4s(sq + (phi_i + PHI_SXZ_Z) * pl);
+            f_szz_z = ld4s(sq + (phi_i + PHI_SZZ_Z) * pl);
+#pragma unroll
+            for (int kk = 0; kk < 4; kk++) {
+              const int z = gz + kk;
+              if (z < g.nPml || z > zp_hi) {
+                f_sxz_z.v[kk] = fmaf(bz.v[kk], f_sxz_z.v[kk], bybdt.v[kk] * vx.v[kk]);
+                f_szz_z.v[kk] = fmaf(bzh.v[kk], f_szz_z.v[kk], byadt.v[kk] * vz.v[kk]);
+              }
+            }
+            if (owner) {
+              st4(sq + (phi_o + PHI_SXZ_Z) * pl, f_sxz_z);
+              st4(sq + (phi_o + PHI_SZZ_Z) * pl, f_szz_z);
+            }
+          }
+        }
+        st4(s_phi + PHI_SZZ_Z * SCOLS * SPITCH + sj, f_szz_z);
+        st4(s_phi + PHI_SXZ_X * SCOLS * SPITCH + sj, f_sxz_x);
+        st4(s_phi + PHI_SXZ_Z * SCOLS * SPITCH + sj, f_sxz_z);
+        st4(s_phi + PHI_SXX_X * SCOLS * SPITCH + sj, f_sxx_x);
+      }
+      st4(s_va + sj, vz);
+      st4(s_va + SCOLS * SPITCH + sj, vx);
+      float *ao = sq + aout * pl;
+      if (owner) {
+        st4(ao + F_VZ * pl, vz);
+        st4(ao + F_VX * pl, vx);
+      }
+      __syncthreads();  // s_va / s_phi / s_inj are complete; nobody reads ring slot `stage` any more
+      if (tid == PRODUCER_TID) produce_next(stage, ds == 0 ? MNS : ds - 1, false);
+
+      // ---- adjoint stress of the same quad, owner threads (el_stress_adj.cu:52-95) ----
+      if (owner) {
+        if (d.r1 > d.r0) {  // res_injection: szz += res, sxx += 3 res
+          const F4 r = ld4(s_inj + sj);
+          st4(s_inj + sj, zero4());
+#pragma unroll
+          for (int kk = 0; kk < 4; kk++) {   // utilities.cu:575-579: RSXXZZ is the double literal 3.0 -> one rounding
+            szz.v[kk] += r.v[kk];
+            sxx.v[kk] = (float)((double)sxx.v[kk] + 3.0 * (double)r.v[kk]);
+          }
+        }
+        const float *pz = s_va + sj;
+        const float *px = pz + SCOLS * SPITCH;
+        float dvz_dx[4], dvx_dz[4], dvx_dx[4], dvz_dz[4];
+        dx4(ld4(pz - SPITCH), vz, ld4(pz + SPITCH), ld4(pz + 2 * SPITCH), akx1, akx2, dvz_dx);   // ad_plus_x(vz)
+        dz_plus4(ld4(px - 4), vx, ld4(px + 4), akz1, akz2, dvx_dz);                              // ad_plus_z(vx)
+        dx4(ld4(px - 2 * SPITCH), ld4(px - SPITCH), vx, ld4(px + SPITCH), akx1, akx2, dvx_dx);   // ad_minus_x(vx)
+        dz_minus4(ld4(pz - 4), vz, ld4(pz + 4), akz1, akz2, dvz_dz);                             // ad_minus_z(vz)
+        if (!pml_tile) {
+#pragma unroll
+          for (int kk = 0; kk < 4; kk++) {
+            sxz.v[kk] += fmaf(dvz_dx[kk], byadt.v[kk], dvx_dz[kk] * bybdt.v[kk]);
+            sxx.v[kk] = fmaf(bybdt.v[kk], dvx_dx[kk], sxx.v[kk]);
+            szz.v[kk] = fmaf(byadt.v[kk], dvz_dz[kk], szz.v[kk]);
+          }
+        } else {
+          float t_xz_x[4] = {0, 0, 0, 0}, t_xz_z[4] = {0, 0, 0, 0}, t_xx[4] = {0, 0, 0, 0}, t_zz[4] = {0, 0, 0, 0};
+          if (actq) {
+            float dd[4];
+            if (ax != 0.0f) {  // a_x * D+x(phi_xz_x)
+              const float *p = s_phi + PHI_SXZ_X * SCOLS * SPITCH + sj;
+              dx4(ld4(p - SPITCH), ld4(p), ld4(p + SPITCH), ld4(p + 2 * SPITCH), akx1, akx2, dd);
+#pragma unroll
+              for (int kk = 0; kk < 4; kk++) t_xz_x[kk] = ax * dd[kk];
+            }
+            if (axh != 0.0f) {  // a_x_half * D-x(phi_xx_x)
+              const float *p = s_phi + PHI_SXX_X * SCOLS * SPITCH + sj;
+              dx4(ld4(p - 2 * SPITCH), ld4(p - SPITCH), ld4(p), ld4(p + SPITCH), akx1, akx2, dd);
+#pragma unroll
+              for (int kk = 0; kk < 4; kk++) t_xx[kk] = axh * dd[kk];
+            }
+            if (zq_pml) {
+              const float *p1 = s_phi + PHI_SXZ_Z * SCOLS * SPITCH + sj;   // a_z * D+z(phi_xz_z)
+              dz_plus4(ld4(p1 - 4), ld4(p1), ld4(p1 + 4), akz1, akz2, dd);
+#pragma unroll
+              for (int kk = 0; kk < 4; kk++) t_xz_z[kk] = az.v[kk] * dd[kk];
+              const float *p2 = s_phi + PHI_SZZ_Z * SCOLS * SPITCH + sj;   // a_z_half * D-z(phi_zz_z)
+              dz_minus4(ld4(p2 - 4), ld4(p2), ld4(p2 + 4), akz1, akz2, dd);
+#pragma unroll
+              for (int kk = 0; kk < 4; kk++) t_zz[kk] = azh.v[kk] * dd[kk];
+            }
+          }
+#pragma unroll
+          for (int kk = 0; kk < 4; kk++) {
+            const int z = gz + kk;
+            if (actq && z >= 2 && z <= g.az_hi) {
+              sxz.v[kk] += t_xz_x[kk] + dvz_dx[kk] * rKx * byadt.v[kk] + t_xz_z[kk] + dvx_dz[kk] * rKz.v[kk] * bybdt.v[kk];
+              sxx.v[kk] += t_xx[kk] + bybdt.v[kk] * dvx_dx[kk] * rKxh;
+              szz.v[kk] += t_zz[kk] + byadt.v[kk] * dvz_dz[kk] * rKzh.v[kk];
+            }
+          }
+          // psi memory within 2 cells of the layers (el_stress_adj.cu:68,71,89-94)
+          if (actq && (gx < xq_lo || gx > xq_hi)) {
+            const float *xpf = a.pr.x + gx + XM;
+            const float bx = xpf[PR_B * nxp], bxh = xpf[PR_BH * nxp];
+            F4 p1 = ld4(sq + (psi_i + PSI_VZ_X) * pl), p2 = ld4(sq + (psi_i + PSI_VX_X) * pl);
+#pragma unroll
+            for (int kk = 0; kk < 4; kk++) {
+              p1.v[kk] = fmaf(bxh, p1.v[kk], sxz.v[kk] * amudt.v[kk]);
+              p2.v[kk] = fmaf(bx, p2.v[kk], fmaf(ldt.v[kk], szz.v[kk], l2mdt.v[kk] * sxx.v[kk]));
+            }
+            st4(sq + (psi_o + PSI_VZ_X) * pl, p1);
+            st4(sq + (psi_o + PSI_VX_X) * pl, p2);
+          }
+          if (actq && (gz < zq_lo || gz + 3 > zq_hi)) {
+            const F4 bz = ld4(zprof + PR_B * P + gz), bzh = ld4(zprof + PR_BH * P + gz);
+            F4 p1 = ld4(sq + (psi_i + PSI_VX_Z) * pl), p2 = ld4(sq + (psi_i + PSI_VZ_Z) * pl);
+#pragma unroll
+            for (int kk = 0; kk < 4; kk++) {
+              const int z = gz + kk;
+              if (z < zq_lo || z > zq_hi) {
+                p1.v[kk] = fmaf(bzh.v[kk], p1.v[kk], sxz.v[kk] * amudt.v[kk]);
+                p2.v[kk] = fmaf(bz.v[kk], p2.v[kk], fmaf(l2mdt.v[kk], szz.v[kk], ldt.v[kk] * sxx.v[kk]));
+              }
+            }
+            st4(sq + (psi_o + PSI_VX_Z) * pl, p1);
+            st4(sq + (psi_o + PSI_VZ_Z) * pl, p2);
+          }
+        }
+        st4(ao + F_SZZ * pl, szz);
+        st4(ao + F_SXX * pl, sxx);
+        st4(ao + F_SXZ * pl, sxz);
+      }
+    }
+    advance();
+    if (!has_rev) {
+      __syncthreads();   // no phase R (and its barrier) between this item's reads of the phase-A tiles and the next item's writes
+      continue;
+    }
+
+    // ========== phase R: forward state it+1 -> it inside the inner box, frame restore, imaging with the NEW adjoint quads ==========
+    {
+      const TileDesc dr = sdesc[ds];   // same tile / shot; carries the frame flag
+      float *acc = a.gacc + g.origin + (long long)d.shot * (G_COUNT - S_COUNT) * pl + d.soff +
+                   ((long long)(c - 2) * P + 4 * q - 4);   // shot * G_COUNT * pl + cell
+      const bool colbox = gx >= g.xlo && gx <= g.xhi;
+      bool bx[4];   // cell inside the inner box (reconstruction / imaging region)
+#pragma unroll
+      for (int kk = 0; kk < 4; kk++) bx[kk] = colbox && (unsigned)(gz + kk - g.zlo) <= (unsigned)(g.zhi - g.zlo);
+      const bool in_rect = gx >= g.xlo - 2 && gx <= g.xhi + 2 && gz + 3 >= g.zlo - 2 && gz <= g.zhi + 2;
+      // saved frame values of the quad (to_bnd, libCUFD.cu:388,403), copied asynchronously (LDGSTS, no registers): the
+      // velocities straight into the quad's place in the rewound-velocity tile, the stresses into the owner's landing zone
+      int fq = -1;
+      if ((dr.flags & TF_FRAME) && in_rect) fq = frame_quad(g, gz, gx);
+      if (fq >= 0) {
+        const float *frm = a.frames + ((long long)d.shot * g.nSteps + a.it) * 5 * g.f_len + 4 * fq;
+        cp_async16(s_vr + sj, frm + F_VZ * g.f_len);
+        cp_async16(s_vr + SCOLS * SPITCH + sj, frm + F_VX * g.f_len);
+        if (inner) {
+#pragma unroll
+          for (int f = 0; f < 3; f++) cp_async16(my_frm + f * 4 * NOWN, frm + (F_SZZ + f) * g.f_len);
+        }
+      }
+      mbar_wait(&full[stage], phase);
+
+      const unsigned char *sb = base + stage * MSTAGE_BYTES;
+      const float *sw = reinterpret_cast<const float *>(sb);              // [3][WCOLS][VPITCH]: szz sxx sxz of time it+1
+      const float *sv = reinterpret_cast<const float *>(sb + RW_BYTES);   // [2][SCOLS][SPITCH]: vz vx of time it+1
+      const float kz1 = -akz1, kz2 = -akz2, kx1 = -akx1, kx2 = -akx2;
+
+      // ---- v^{it} = v^{it+1} - velocity(sigma^{it+1}) on 16 quads x 32 columns; rho imaging terms (el_velocity.cu:84-110) ----
+      const float *zz = sw + (c + 2) * VPITCH + 4 * (q + 1);
+      const float *xx = zz + WCOLS * VPITCH;
+      const float *xz = xx + WCOLS * VPITCH;
+      float ea[4], eb[4];
+      const F4 szzB = ld4(zz), sxxB = ld4(xx), sxzB = ld4(xz);
+      {
+        float d1[4], d2[4];
+        dz_plus4(ld4(zz - 4), szzB, ld4(zz + 4), kz1, kz2, d1);                       // dszz_dz
+        dx4(ld4(xz - 2 * VPITCH), ld4(xz - VPITCH), sxzB, ld4(xz + VPITCH), kx1, kx2, d2);   // dsxz_dx
+#pragma unroll
+        for (int kk = 0; kk < 4; kk++) ea[kk] = d1[kk] + d2[kk];
+        dz_minus4(ld4(xz - 4), sxzB, ld4(xz + 4), kz1, kz2, d1);                      // dsxz_dz
+        dx4(ld4(xx - VPITCH), sxxB, ld4(xx + VPITCH), ld4(xx + 2 * VPITCH), kx1, kx2, d2);   // dsxx_dx
+#pragma unroll
+        for (int kk = 0; kk < 4; kk++) eb[kk] = d1[kk] + d2[kk];
+      }
+      F4 fvz = ld4(sv + sj), fvx = ld4(sv + SCOLS * SPITCH + sj);
+      F4 ga = zero4(), gb = zero4();
+#pragma unroll
+      for (int kk = 0; kk < 4; kk++) {
+        if (bx[kk]) {
+          fvz.v[kk] = fmaf(-ea[kk], byadt.v[kk], fvz.v[kk]);
+          fvx.v[kk] = fmaf(-eb[kk], bybdt.v[kk], fvx.v[kk]);
+          // g = -v_adj (d sigma) dt * (-byc^2 / 2)     (el_velocity.cu:101-104); vz / vx = the new adjoint velocities
+          ga.v[kk] = (vz.v[kk] * ea[kk]) * (half_rdt * byadt.v[kk] * byadt.v[kk]);
+          gb.v[kk] = (vx.v[kk] * eb[kk]) * (half_rdt * bybdt.v[kk] * bybdt.v[kk]);
+        }
+      }
+      // the spray of el_velocity.cu:105-110 as a gather: cell (z, x) receives g_a(z, x) + g_b(z, x) + g_a(z-1, x) +
+      // g_b(z, x-1).  g_a of the cell above the quad comes from the thread above (same half-warp), g_b of the column
+      // to the left through shared memory after the barrier.
+      const float ga_up = __shfl_up_sync(0xffffffffu, ga.v[3], 1, 16);
+      st4(s_gb + sj, gb);
+      if (fq >= 0) {  // exact values of time `it` on the ring: already in the shared tile
+        cp_async_wait_all();
+        fvz = ld4(s_vr + sj);
+        fvx = ld4(s_vr + SCOLS * SPITCH + sj);
+      } else {
+        st4(s_vr + sj, fvz);
+        st4(s_vr + SCOLS * SPITCH + sj, fvx);
+      }
+      float *fo = sq + fout * pl;
+      const bool wr = owner && in_rect;
+      if (wr) {
+        st4(fo + F_VZ * pl, fvz);
+        st4(fo + F_VX * pl, fvx);
+      }
+      // accumulators of the stress half, requested before the barrier
+      F4 gl, gm, gs, gd;
+      const bool colrho = gx >= g.xlo && gx <= g.xhi + 1;   // the x+1 spray also lands in column xhi + 1 (Q2)
+      const bool rowbox = gz + 3 >= g.zlo && gz <= g.zhi;
+      if (wr && rowbox) {
+        if (colbox) { gl = ld4s(acc + G_LAM * pl); gm = ld4s(acc + G_MU * pl); gs = ld4s(acc + G_MUS * pl); }
+        if (colrho) gd = ld4s(acc + G_RHO_A * pl);
+      }
+      __syncthreads();  // s_vr / s_gb are complete; nobody reads ring slot `stage` any more
+      if (tid == PRODUCER_TID) produce_next(stage, ds == 0 ? MNS : ds - 1, false);
+
+      // ---- sigma^{it} = sigma^{it+1} - source - stress(v^{it}) on the owner quads; lambda / mu imaging (el_stress.cu:90-124) ----
+      if (wr) {
+        F4 fzz = szzB, fxx = sxxB, fxz = sxzB;
+        if (rowbox && colrho) {
+          const F4 gbl = ld4(s_gb + sj - SPITCH);
+#pragma unroll
+          for (int kk = 0; kk < 4; kk++) {
+            const float up = kk == 0 ? ga_up : ga.v[kk - 1];
+            // rows outside the box receive nothing: g_a / g_b are zero there, and the z+1 spray stops at zhi (el_velocity.cu:107)
+            const bool rowin = (unsigned)(gz + kk - g.zlo) <= (unsigned)(g.zhi - g.zlo);
+            gd.v[kk] += rowin ? (ga.v[kk] + gb.v[kk]) + (up + gbl.v[kk]) : 0.0f;
+          }
+          st4(acc + G_RHO_A * pl, gd);
+        }
+        if (rowbox && colbox) {
+          const float *pz = s_vr + sj;
+          const float *px = pz + SCOLS * SPITCH;
+          float dvz_dz[4], dvx_dz[4], dvx_dx[4], dvz_dx[4];
+          dz_minus4(ld4(pz - 4), fvz, ld4(pz + 4), kz1, kz2, dvz_dz);
+          dz_plus4(ld4(px - 4), fvx, ld4(px + 4), kz1, kz2, dvx_dz);
+          dx4(ld4(px - 2 * SPITCH), ld4(px - SPITCH), fvx, ld4(px + SPITCH), kx1, kx2, dvx_dx);
+          dx4(ld4(pz - SPITCH), fvz, ld4(pz + SPITCH), ld4(pz + 2 * SPITCH), kx1, kx2, dvz_dx);
+          if ((dr.flags & TF_SRC) && gx == d.sx && (unsigned)(d.sz - gz) < 4u) {  // add_source(isFor=false): utilities.cu:538-551
+            const float amp = a.st.stf[d.shot * g.nSteps + a.it];
+            const float azz = SRC_SCALE * amp * dt;
+            const double axx = 3.0 * (double)SRC_SCALE * (double)amp * (double)dt;
+            const int ks = d.sz - gz;
+#pragma unroll
+            for (int kk = 0; kk < 4; kk++) {
+              fzz.v[kk] -= (kk == ks) ? azz : 0.0f;
+              fxx.v[kk] = (kk == ks) ? (float)((double)fxx.v[kk] - axx) : fxx.v[kk];
+            }
+          }
+#pragma unroll
+          for (int kk = 0; kk < 4; kk++) {
+            if (bx[kk]) {
+#if FWI_F64_UPDATE == 1
+              fzz.v[kk] = (float)((double)fzz.v[kk] - ((double)l2mdt.v[kk] * (double)dvz_dz[kk] + (double)ldt.v[kk] * (double)dvx_dx[kk]));
+              fxx.v[kk] = (float)((double)fxx.v[kk] - ((double)ldt.v[kk] * (double)dvz_dz[kk] + (double)l2mdt.v[kk] * (double)dvx_dx[kk]));
+#else
+              fzz.v[kk] = fmaf(-l2mdt.v[kk], dvz_dz[kk], fmaf(-ldt.v[kk], dvx_dx[kk], fzz.v[kk]));
+              fxx.v[kk] = fmaf(-l2mdt.v[kk], dvx_dx[kk], fmaf(-ldt.v[kk], dvz_dz[kk], fxx.v[kk]));
+#endif
+              const float e = dvx_dz[kk] + dvz_dx[kk];
+              fxz.v[kk] = fmaf(-amudt.v[kk], e, fxz.v[kk]);
+              // el_stress.cu:109-116; szz / sxx / sxz = the new adjoint stresses of the quad
+              gl.v[kk] += -(szz.v[kk] + sxx.v[kk]) * (dvz_dz[kk] + dvx_dx[kk]) * dt6;
+              gm.v[kk] += (-2.0f * szz.v[kk] * dvz_dz[kk] - 2.0f * sxx.v[kk] * dvx_dx[kk]) * dt6;
+              //  s = -sxz_adj (exz + ezx) dt mu_bar / sum(1/mu) 1e6, mu_bar / sum(1/mu) == mu_bar^2 / 4; zero where mu_bar == 0
+              gs.v[kk] += -sxz.v[kk] * e * (q_rdt * amudt.v[kk] * amudt.v[kk]);
+            }
+          }
+          st4(acc + G_LAM * pl, gl);
+          st4(acc + G_MU * pl, gm);
+          st4(acc + G_MUS * pl, gs);
+        }
+        if (fq >= 0) {  // to_bnd(sigma) (libCUFD.cu:403)
+          fzz = ld4(my_frm);
+          fxx = ld4(my_frm + 4 * NOWN);
+          fxz = ld4(my_frm + 8 * NOWN);
+        }
+        st4(fo + F_SZZ * pl, fzz);
+        st4(fo + F_SXX * pl, fxx);
+        st4(fo + F_SXZ * pl, fxz);
+      }
+    }
+    advance();
+  }
+}
+
 }  // namespace
 
 // -1: pick the reverse kernel build by working-set size; 0 / 1: force the double-buffered / LEAN build
@@ -751,7 +1347,19 @@ size_t reverse_smem_bytes() { return REV_SMEM; }
 
 size_t adjoint_smem_bytes() { return ADJ_SMEM; }
 
+size_t merged_smem_bytes() { return MRG_SMEM; }
+
+// backward loop of one time index in ONE launch: adjoint step it+1, reverse step it+1 -> it + imaging (see bwd_step_kernel)
+void launch_backward_merged(const BwdArgs &a_in, cudaStream_t s) {
+  BwdArgs a = a_in;
+  a.order = FWI_ZIGZAG ? (a.it & 1) : 0;
+  const int nitems = a.batch * a.g.tiles_z * a.g.tiles_x;
+  const int blocks = nitems < sm_count() ? nitems : sm_count();
+  launch_step(bwd_step_kernel, blocks, NCOMPUTE, MRG_SMEM, s, a);
+}
+
 void configure_backward_kernels() {
+  cudaFuncSetAttribute(bwd_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MRG_SMEM);
   cudaFuncSetAttribute(rev_image_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rev_smem<false>());
   cudaFuncSetAttribute(rev_image_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rev_smem<true>());
   cudaFuncSetAttribute(adj_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ADJ_SMEM);

@@ -17,7 +17,8 @@
 #endif
 
 #ifndef FWI_F64_UPDATE
-#define FWI_F64_UPDATE 0   // 1: stress / adjoint-velocity increments summed in double like the reference (one rounding per update)
+#define FWI_F64_UPDATE 8   // 0: float increments everywhere; 1: stress / adjoint-velocity increments summed in double everywhere (one rounding per
+                           // update, like the reference's (lambda + 2.0 mu) expressions); R > 1: only for quads within R cells of the shot's source
 #endif
 
 namespace fwi {

@@ -87,6 +87,7 @@ struct alignas(64) TmaMaps {
   CUtensorMap o5;   // state planes, box (TILE_Z, TILE_X, 5): the five adjoint fields of the owner tile (reverse step)
   CUtensorMap r1;   // state planes, box (TILE_Z+8, TILE_X+4, 1): one CPML memory plane of the tile region
   CUtensorMap g5;   // imaging accumulators [batch][G_COUNT][plane], box (TILE_Z, TILE_X, 5)
+  CUtensorMap g4;   // the same, box (TILE_Z, TILE_X, 4): the merged backward kernel gathers the density spray itself
   CUtensorMap m5;   // model planes, box (TILE_Z+8, TILE_X+4, 5): the five dt-scaled coefficient planes of the tile region
 };
 
@@ -146,6 +147,9 @@ void launch_forward_step(const FwdArgs &a, bool save_frames, cudaStream_t s);
 void launch_reverse_imaging(const BwdArgs &a, cudaStream_t s);
 // adjoint step: source_grad, adjoint velocity, residual injection, adjoint stress
 void launch_adjoint_step(const BwdArgs &a, cudaStream_t s);
+// merged backward launch: adjoint step of time index a.it + 1 (adjoint buffer cur_a -> the other), then reverse step
+// a.it + 1 -> a.it with imaging (forward buffer cur_f -> the other); the density accumulator G_RHO_A is final (gathered)
+void launch_backward_merged(const BwdArgs &a, cudaStream_t s);
 
 // model preparation: double row-major MPa -> float planes (Pa), derived coefficients, max cp
 // `model` = base of the M_COUNT model planes
@@ -174,8 +178,9 @@ void launch_misfit(const float *j_shot, int n, float *misfit_half, cudaStream_t 
 void launch_traces_to_rt(const float *tr, float *rt, int nrec, int nrp, int nSteps, cudaStream_t s);
 
 // result = [gl|gm|gd|misfit] row-major [z][x] float: sums the per-slot accumulators
+// rho_gathered: G_RHO_A already holds the gathered density gradient (merged backward kernel)
 void launch_finalize(const Grid &g, const float *gacc, int nslots, const float *mu, const float *misfit_half,
-                     float *result, cudaStream_t s);
+                     float *result, bool rho_gathered, cudaStream_t s);
 
 // host: encode the TMA descriptors for a state buffer of `nplanes` planes and the model buffer
 // `gacc` may be null (no gradient): its descriptor is then left untouched
@@ -184,6 +189,7 @@ void encode_tma_maps(const Grid &g, float *state, long long nplanes, float *gacc
 size_t forward_smem_bytes();
 size_t reverse_smem_bytes();
 size_t adjoint_smem_bytes();
+size_t merged_smem_bytes();
 void configure_kernels();  // cudaFuncSetAttribute for dynamic smem
 void set_rev_lean(int v);   // A/B switch of the reverse kernel build: -1 auto, 0 double-buffered, 1 LEAN
 

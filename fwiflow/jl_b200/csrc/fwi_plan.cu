@@ -10,6 +10,7 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -83,6 +84,7 @@ struct fwi_b200_plan {
   std::vector<char> obs_set;
   int last_calc = -1;
   int cur_f_last = 0;  // forward-field buffer holding the newest state of the last batch
+  bool rho_gathered = false;  // the last backward loop ran the merged kernel: G_RHO_A holds the gathered density gradient
 
   // device memory
   DevBuf<float> model;        // lam mu den amu bya byb planes
@@ -143,8 +145,14 @@ struct fwi_b200_plan {
 #ifndef FWI_ADJ_INDEP
 #define FWI_ADJ_INDEP 1
 #endif
+#ifndef FWI_MERGED_BWD
+#define FWI_MERGED_BWD 1
+#endif
 
 namespace {
+
+// 1: backward loop = one merged launch per time index (bwd_step_kernel); 0: reverse + adjoint launches (A/B, set_option)
+std::atomic<int> g_merged_bwd{FWI_MERGED_BWD};
 
 int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
@@ -532,30 +540,48 @@ void run_locked(fwi_b200_plan &pl, int calc_id, cudaStream_t s) {
     ba.st = st; ba.state = pl.state.p; ba.res = pl.res_tr.p; ba.frames = pl.frames.p; ba.gacc = pl.gacc.p;
     ba.stf_grad = pl.stf_grad.p + (size_t)first * N; ba.batch = nb;
     int cur_a = 0;
-    ba.it = N - 1; ba.cur_f = cur_f; ba.cur_a = cur_a;   // priming: libCUFD.cu:353-373
-    launch_adjoint_step(ba, s);
-    pl.launches++;
-    cur_a ^= 1;
-    for (int it = N - 2; it >= 0; it--) {  // libCUFD.cu:374-445
-      ba.it = it; ba.cur_f = cur_f; ba.cur_a = cur_a;
-      launch_reverse_imaging(ba, s);
-      pl.launches++;
-      // (at it == 0 only the source_grad part of this launch is observable; kept for grad_stf[0])
-      ba.indep = FWI_ADJ_INDEP;   // follows the reverse step of the same time index: independent of it
+    if (g_merged_bwd.load(std::memory_order_relaxed)) {
+      // ONE launch per time index: the adjoint step of index it+1 (libCUFD.cu:353-373 for the first one, :405-427
+      // after) and the reverse step it+1 -> it with imaging (:380-403), which needs exactly the adjoint state that
+      // step has just produced -- handed over in registers (bwd_step_kernel)
+      for (int it = N - 2; it >= 0; it--) {
+        ba.it = it; ba.cur_f = cur_f; ba.cur_a = cur_a;
+        launch_backward_merged(ba, s);
+        pl.launches++;
+        cur_f ^= 1;
+        cur_a ^= 1;
+      }
+      // (the adjoint step of index 0: only its source_grad part is observable; kept for grad_stf[0])
+      ba.it = 0; ba.cur_f = cur_f; ba.cur_a = cur_a;
       launch_adjoint_step(ba, s);
-      ba.indep = 0;
       pl.launches++;
-      cur_f ^= 1;
+    } else {
+      ba.it = N - 1; ba.cur_f = cur_f; ba.cur_a = cur_a;   // priming: libCUFD.cu:353-373
+      launch_adjoint_step(ba, s);
+      pl.launches++;
       cur_a ^= 1;
+      for (int it = N - 2; it >= 0; it--) {  // libCUFD.cu:374-445
+        ba.it = it; ba.cur_f = cur_f; ba.cur_a = cur_a;
+        launch_reverse_imaging(ba, s);
+        pl.launches++;
+        // (at it == 0 only the source_grad part of this launch is observable; kept for grad_stf[0])
+        ba.indep = FWI_ADJ_INDEP;   // follows the reverse step of the same time index: independent of it
+        launch_adjoint_step(ba, s);
+        ba.indep = 0;
+        pl.launches++;
+        cur_f ^= 1;
+        cur_a ^= 1;
+      }
     }
     pl.cur_f_last = cur_f;
+    pl.rho_gathered = g_merged_bwd.load(std::memory_order_relaxed) != 0;
   }
   if (if_res) {
     launch_misfit(pl.j_shot.p, pl.group, pl.misfit_half.p, s);
     pl.launches++;
   }
   if (with_adj) {
-    launch_finalize(g, pl.gacc.p, std::min(pl.batch, pl.group), m.mu, pl.misfit_half.p, pl.result.p, s);
+    launch_finalize(g, pl.gacc.p, std::min(pl.batch, pl.group), m.mu, pl.misfit_half.p, pl.result.p, pl.rho_gathered, s);
     pl.launches++;
   } else if (if_res) {
     CUDA_OK(cudaMemcpyAsync(pl.result.p + 3LL * g.nz * g.nx, pl.misfit_half.p, sizeof(float), cudaMemcpyDeviceToDevice, s));
@@ -836,7 +862,7 @@ extern "C" int fwi_b200_plan_get_field(fwi_b200_plan *pl, int ishot, int field, 
 extern "C" int fwi_b200_plan_time_kernel(fwi_b200_plan *pl, int which, int iters, void *stream, float *ms_per_launch,
                                          double *alg_bytes) {
   return guarded([&] {
-    if (!pl || iters <= 0 || which < 0 || which > 3) throw Error(FWI_B200_ERR_ARG, "time_kernel: bad arguments");
+    if (!pl || iters <= 0 || which < 0 || which > 4) throw Error(FWI_B200_ERR_ARG, "time_kernel: bad arguments");
     std::lock_guard<std::mutex> lk(pl->mu);
     use_device(pl->gpu);
     const Grid &g = pl->g;
@@ -859,7 +885,8 @@ extern "C" int fwi_b200_plan_time_kernel(fwi_b200_plan *pl, int which, int iters
       const int it = 1 + (k % std::max(1, g.nSteps - 3));
       if (which <= 1) { fa.it = it; fa.cur = k & 1; launch_forward_step(fa, which == 1, s); }
       else if (which == 2) { ba.it = it; ba.cur_f = k & 1; ba.cur_a = 0; launch_reverse_imaging(ba, s); }
-      else { ba.it = it; ba.cur_f = 0; ba.cur_a = k & 1; launch_adjoint_step(ba, s); }
+      else if (which == 3) { ba.it = it; ba.cur_f = 0; ba.cur_a = k & 1; launch_adjoint_step(ba, s); }
+      else { ba.it = it; ba.cur_f = k & 1; ba.cur_a = k & 1; launch_backward_merged(ba, s); }
     };
     for (int k = 0; k < 3; k++) one(k);
     CUDA_OK(cudaEventRecord(e0, s));
@@ -881,7 +908,8 @@ extern "C" int fwi_b200_plan_time_kernel(fwi_b200_plan *pl, int which, int iters
       // 60 B forward, 124 B backward = 64 (reverse + imaging) + 60 (adjoint)
       if (which <= 1) b = cells * (60.0 + 32.0 * (fz + fx));
       else if (which == 2) b = box * 64.0;         // forward state R+W (40) + three gradient accumulators R+W (24)
-      else b = cells * (60.0 + 64.0 * (fz + fx));  // adjoint state R+W, 5 coefficients, psi/phi in the strips
+      else if (which == 3) b = cells * (60.0 + 64.0 * (fz + fx));  // adjoint state R+W, 5 coefficients, psi/phi in the strips
+      else b = cells * (60.0 + 64.0 * (fz + fx)) + box * 64.0;     // merged backward launch: both of the above = 124 B
       if (which == 1) b += (double)nb * 5 * g.f_len * 4.0;
       *alg_bytes = b;
     }
@@ -1278,6 +1306,7 @@ extern "C" int fwi_b200_set_option(const char *name, int value) {
     if (!name) throw Error(FWI_B200_ERR_ARG, "set_option: null name");
     const std::string k(name);
     if (k == "rev_lean") set_rev_lean(value);
+    else if (k == "merged_bwd") g_merged_bwd.store(value != 0, std::memory_order_relaxed);
     else throw Error(FWI_B200_ERR_ARG, "set_option: unknown option '" + k + "'");
   });
 }

@@ -111,7 +111,8 @@ int fwi_b200_timelapse(int nsurveys, const char *const *para_fnames, const doubl
 int fwi_b200_para_info(const char *para_fname, int *out);
 
 /* Developer A/B switches (not part of the reference's surface).  "rev_lean": -1 pick the build of the reverse-time
- * kernel by working-set size (default), 0 / 1 force the double-buffered / LEAN build. */
+ * kernel by working-set size (default), 0 / 1 force the double-buffered / LEAN build.  "merged_bwd": 1 (default) the
+ * backward loop is one launch per time index (adjoint step + reverse step / imaging), 0 two launches. */
 int fwi_b200_set_option(const char *name, int value);
 
 /* Host-only: the device layout this library derives from a parameter file (no GPU needed).
@@ -180,7 +181,8 @@ int fwi_b200_plan_get_field(fwi_b200_plan *plan, int ishot, int field, float *ou
 
 /* Kernel timing for the roofline: runs `iters` launches of one hot kernel on the plan's
  * current state (which: 0 forward step, 1 forward step + frame save, 2 reverse+imaging,
- * 3 adjoint step) on `stream` between two CUDA events, returns the mean ms per launch
+ * 3 adjoint step, 4 merged backward launch = adjoint step + reverse/imaging) on `stream` between two CUDA events,
+ * returns the mean ms per launch
  * and the algorithmic bytes one launch moves. */
 int fwi_b200_plan_time_kernel(fwi_b200_plan *plan, int which, int iters, void *stream,
                               float *ms_per_launch, double *alg_bytes_per_launch);

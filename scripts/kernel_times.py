@@ -15,7 +15,7 @@ p = ops.Plan(para, ids)
 p.set_stf(c.stf); p.set_model(*c.moduli("true")); p.run(2); print('obs ok', flush=True); p.write_obs_files()
 p.set_model(*c.moduli("init")); p.load_obs_files(); p.run(1); print('grad ok', flush=True)
 peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
-names = {0: "fwd", 1: "fwd+save", 2: "rev_image", 3: "adj"}
+names = {0: "fwd", 1: "fwd+save", 2: "rev_image", 3: "adj", 4: "bwd_merged"}
 for w in names:
     try:
         ms, b = p.time_kernel(w, iters=iters)

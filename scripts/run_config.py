@@ -10,6 +10,8 @@ import torch
 from fwiflow.jl_b200 import ops, synthetic
 
 case, nshots, nsteps = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
+if "FWI_MERGED" in os.environ:      # A/B: backward loop as one merged launch per time index (1) or two launches (0)
+    ops.set_option("merged_bwd", int(os.environ["FWI_MERGED"]))
 mk = {"c2": synthetic.case_c2, "c3": synthetic.case_c3, "c5": synthetic.case_c5}[case]
 c = mk(nshots=nshots, nSteps=nsteps)
 para = c.write_files(tempfile.mkdtemp(prefix=f"cfg_{case}_"))
@@ -28,7 +30,7 @@ ms = e0.elapsed_time(e1)
 free1, _ = torch.cuda.mem_get_info()
 j, gl, gm, gd, gs = p.result()
 cells = c.nz_pad * c.nx_pad
-print(json.dumps({"config": case, "grid": [c.nz_pad, c.nx_pad], "shots": nshots, "nSteps": nsteps, "batch": p.batch,
+print(json.dumps({"merged_bwd": os.environ.get("FWI_MERGED", "default"), "config": case, "grid": [c.nz_pad, c.nx_pad], "shots": nshots, "nSteps": nsteps, "batch": p.batch,
                   "gradient_s": ms / 1e3, "forward_only_s": t_obs, "shot_gradients_per_s": nshots / (ms / 1e3),
                   "cell_updates_per_s": 2.0 * nshots * cells * (nsteps - 1) / (ms / 1e3),
                   "hbm_used_gb": (total - free1) / 1e9, "misfit": j,

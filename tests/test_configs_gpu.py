@@ -8,6 +8,7 @@ plus an oracle check of one survey on a grid the CPU finishes in seconds.  Every
 """
 from __future__ import annotations
 
+import os
 import tempfile
 
 import numpy as np
@@ -55,6 +56,79 @@ def test_c2_full_length_against_reference_op(ops):
     for k in ("grad_lambda", "grad_mu", "grad_den"):
         assert rel(g_b[k][inner], g_r[k][inner]) <= TOL_GRAD, k
         assert rel(g_b[k], g_r[k]) <= 5 * TOL_GRAD, k          # incl. the ill-conditioned cells at the sources
+    # grad_stf: every C2 source sits on a receiver, so the adjoint stress at the source cell is driven by the residual
+    # of that one receiver = difference of two direct-arrival samples; a trace deviation of 1e-6 shows up ~1e3 times
+    # larger (profiles/r2_parity.md: the CPU restatement of the reference, with ALL its FP64 promotions, is at
+    # 1.3e-3 .. 1.8e-3 on such geometries).  Gate: 3e-3 over the group.
+    assert np.abs(g_r["grad_stf"]).max() > 0 and rel(g_b["grad_stf"], g_r["grad_stf"]) <= 3e-3
+
+
+def test_marmousi_fixtures_against_reference_op(ops):
+    """The reference's own input fixtures (docs/data: Marmousi cp true / 1-D initial, recorded source wavelet; cs = 0,
+    rho = 2500 -- the acoustic branch mu_bar = 0 of the elastic kernels) with the geometry of test/TestFWI.jl:6-35
+    (sources x = 4:8:384 at z = 2, 379 receivers), 12 of the 48 shots, 2000 steps, against the reference's own op.
+    The inputs travel as tests/golden/marmousi_inputs.npz (tests/golden/make_marmousi_fixture.py)."""
+    import sys
+    from oracle import oracle_py as op
+    if not op.ref_available():
+        pytest.skip("oracle/_ref/libCUFD_ref.so not built")
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts"))
+    from parity_full_length import marmousi_case
+    c = marmousi_case(48)
+    assert (c.nz_pad, c.nx_pad, c.nPad, c.nShots, c.nrec) == (224, 448, 26, 48, 379)
+    ids = np.arange(0, 48, 4, dtype=np.int32)
+    lam, mu, rho = c.moduli("true")
+    lam0, mu0, rho0 = c.moduli("init")
+    assert np.all(mu == 0.0) and np.all(rho == 2500.0)
+    para_r = c.write_files(tempfile.mkdtemp(prefix="marm_ref_"))
+    para_b = c.write_files(tempfile.mkdtemp(prefix="marm_b200_"))
+    ref_obs = op.ref_cufd(2, lam, mu, rho, c.stf, ids, para_r)["syn"]
+    b_obs = b200_cufd(2, lam, mu, rho, c.stf, ids, para_b)["syn"]
+    for a, b in zip(b_obs, ref_obs):
+        assert a.shape == b.shape == (379, 2000) and np.abs(b).max() > 0 and rel(a[:, 1:], b[:, 1:]) <= TOL_TRACE
+    j_r = op.ref_cufd(0, lam0, mu0, rho0, c.stf, ids, para_r)["misfit"]
+    j_b = b200_cufd(0, lam0, mu0, rho0, c.stf, ids, para_b)["misfit"]
+    assert j_r > 0 and abs(j_b - j_r) <= 1e-4 * j_r
+    g_r = op.ref_cufd(1, lam0, mu0, rho0, c.stf, ids, para_r)
+    g_b = b200_cufd(1, lam0, mu0, rho0, c.stf, ids, para_b)
+    inner = interior_mask(c)
+    for k in ("grad_lambda", "grad_mu", "grad_den"):
+        assert rel(g_b[k][inner], g_r[k][inner]) <= TOL_GRAD, k
+        assert rel(g_b[k], g_r[k]) <= TOL_GRAD, k
+    # mu = 0: see test_c2_full_length_against_reference_op; the acoustic branch is the noisiest (oracle 1.8e-3)
+    assert rel(g_b["grad_stf"], g_r["grad_stf"]) <= 8e-3
+
+
+def test_long_records_against_the_noise_floor(ops):
+    """Record lengths beyond a few thousand steps: the reference's adjoint scheme amplifies rounding differences
+    exponentially in reverse time (its gradient norm grows from 2e2 at 600 steps to 9e11 at 6000 steps on this 128 x 144
+    grid, profiles/r2_parity.md), so ANY two float32 implementations drift apart -- the CPU restatement of the reference
+    as much as this library.  The honest gate at such lengths is therefore relative to that noise floor: three-way
+    comparison reference / oracle / b200 on one shot; b200 must be as close to the reference as the oracle is."""
+    from oracle import oracle_py as op
+    from fwiflow.jl_b200 import synthetic
+    if not op.ref_available():
+        pytest.skip("oracle/_ref/libCUFD_ref.so not built")
+    inner = None
+    for n, floor_expected in ((600, False), (4000, True)):
+        c = synthetic.case_small("long", nSteps=n)
+        ids = np.array([0], np.int32)
+        lam, mu, rho = c.moduli("true")
+        lam0, mu0, rho0 = 0.96 * lam, 0.97 * mu, rho
+        g = {}
+        for who, run in (("ref", op.ref_cufd), ("orc", op.oracle_cufd), ("b200", b200_cufd)):
+            para = c.write_files(tempfile.mkdtemp(prefix=f"long_{who}_"))
+            tr = run(2, lam, mu, rho, c.stf, ids, para)["syn"][0]
+            g[who] = run(1, lam0, mu0, rho0, c.stf, ids, para)
+            g[who]["tr"] = tr
+        inner = interior_mask(c)
+        assert rel(g["b200"]["tr"][:, 1:], g["ref"]["tr"][:, 1:]) <= TOL_TRACE          # the forward pass never drifts
+        for k in ("grad_lambda", "grad_mu", "grad_den"):
+            e_b = rel(g["b200"][k][inner], g["ref"][k][inner])
+            e_o = rel(g["orc"][k][inner], g["ref"][k][inner])
+            assert e_b <= max(TOL_GRAD, 3.0 * e_o), (n, k, e_b, e_o)
+            if not floor_expected:
+                assert e_b <= TOL_GRAD, (n, k, e_b)
 
 
 # ---- the large grids of configs[2] and configs[4], one shot, directly against the reference's own op ---------------
@@ -80,6 +154,8 @@ def test_large_grids_against_reference_op(ops, which, nsteps):
     far = interior_mask(c)
     for k in ("grad_lambda", "grad_mu", "grad_den"):
         assert np.abs(g_r[k]).max() > 0 and rel(g_b[k][far], g_r[k][far]) <= TOL_GRAD, k
+    # the source (x = 4, z = 2) sits on a receiver: see test_c2_full_length_against_reference_op
+    assert np.abs(g_r["grad_stf"]).max() > 0 and rel(g_b["grad_stf"], g_r["grad_stf"]) <= 3e-3
 
 
 # ---- configs[2]: 1000 x 3000 model, gradient with boundary-saving checkpoints -----------------------------------

@@ -54,10 +54,14 @@ def test_misfit_and_gradients_match_reference_golden(name, b200_runs):
     else:
         assert rel(m["grad_mu"], g["grad_mu"]) <= TOL_GRAD
     assert rel(m["grad_mu"][far & inner], g["grad_mu"][far & inner]) <= TOL_GRAD
-    # grad_stf = adjoint stress AT the source cell.  In the acoustic case a receiver sits on the source, its residual is
-    # the difference of two huge direct-arrival samples, and the trace error (<= 1e-5 here) is amplified ~1e3 times:
-    # the reference's own value is float32 noise at the 1e-2 level there (tests/test_oracle_golden.py).
-    assert rel(m["grad_stf"], g["grad_stf"]) <= (2e-2 if name == "small_acoustic" else 5e-3)
+    # grad_stf = adjoint stress AT the source cell (SURVEY.md 8d gate: 1e-3).  Held on every elastic golden -- the
+    # increments of quads within 8 cells of a source are summed in double like the reference's (lambda + 2.0 mu)
+    # expressions (FWI_F64_UPDATE), which is where this output is decided when a receiver shares the source cell.
+    # mu = 0 (small_acoustic): the elastic scheme carries undamped zero-energy shear modes, traces agree to 1e-5 instead
+    # of 3e-7, and the difference of two direct-arrival samples at the shared cell amplifies that ~1e3 times: the CPU
+    # restatement of the reference with ALL its promotions is at 1.8e-3 there, any non-literal arithmetic (reciprocal
+    # multiply instead of the division by dz, dt-prescaled coefficients) at 3.5e-3 .. 9e-3 (profiles/r2_parity.md).
+    assert rel(m["grad_stf"], g["grad_stf"]) <= (5e-3 if name == "small_acoustic" else TOL_GRAD)
     assert np.all(m["grad_stf"][:, -1] == 0.0)
     for k in ("grad_lambda", "grad_mu", "grad_den", "grad_stf"):
         assert np.isfinite(m[k]).all()
@@ -373,8 +377,9 @@ def test_kernel_timer_reports_bytes(ops):
 
 
 def test_gradient_multi_matches_single_device(ops):
-    """fwi_b200_gradient_multi: the group sharded over the devices of this process (round-robin) sums to the
-    single-device result; with one visible GPU the shards run on the same device through separate plans."""
+    """fwi_b200_gradient_multi: the group sharded over the devices of this process (round-robin), per-device results
+    summed with ONE ncclAllReduce on the devices, equals the single-device result (<= 1e-5: summation order only).
+    With one visible GPU only the degenerate single-shard path runs; the NCCL path needs `gpurun --gpus 2`."""
     import torch
     c = CASES["small_elastic"]
     para = c.write_files(tempfile.mkdtemp())
@@ -382,13 +387,79 @@ def test_gradient_multi_matches_single_device(ops):
     lam0, mu0, rho0 = c.moduli("init")
     ops.fwi_obs_op(lam, mu, rho, c.stf, 0, [0, 1], para)
     ref = ops.fwi_op_and_grad(lam0, mu0, rho0, c.stf, 0, [0, 1], para)
-    gpus = [0, 1] if torch.cuda.device_count() > 1 else [0, 0]
+    gpus = [0, 1] if torch.cuda.device_count() > 1 else [0]
     got = ops.fwi_op_and_grad_multi(lam0, mu0, rho0, c.stf, gpus, [1, 0], para)     # order of the group is free
-    assert got[0] == pytest.approx(ref[0], rel=1e-6)
+    assert got[0] == pytest.approx(ref[0], rel=1e-5)
     for k in range(1, 5):
-        assert rel(got[k], ref[k]) <= 1e-6, k
+        assert rel(got[k], ref[k]) <= 1e-5, k
+    again = ops.fwi_op_and_grad_multi(lam0, mu0, rho0, c.stf, gpus, [1, 0], para)   # cached plans + communicators
+    assert again[0] == got[0] and all(np.array_equal(again[k], got[k]) for k in range(1, 5))
     with pytest.raises(ops.FwiError):
         ops.fwi_op_and_grad_multi(lam0, mu0, rho0, c.stf, [0, 77], [0, 1], para)    # no such device
+    with pytest.raises(ops.FwiError, match="duplicate"):
+        ops.fwi_op_and_grad_multi(lam0, mu0, rho0, c.stf, [0, 0], [0, 1], para)     # one NCCL rank per device
+
+
+def test_plan_set_obs_in_memory_equals_files(ops):
+    """f2: observations handed over in memory (fwi_b200_plan_set_obs) give exactly the evaluation that reading
+    Data/Shot<id>.bin gives, and wrong shapes are refused by the binding."""
+    c, para = _ragged_case()
+    ids = np.array([0, 1], np.int32)
+    lam, mu, rho = c.moduli("true")
+    lam0, mu0, rho0 = c.moduli("init")
+    obs = b200_cufd(2, lam, mu, rho, c.stf, ids, para)["syn"]            # also writes Data/Shot<id>.bin
+    a = ops.Plan(para, ids)
+    a.set_model(lam0, mu0, rho0); a.set_stf(c.stf); a.load_obs_files(); a.run(1)
+    ra = a.result()
+    a.close()
+    b = ops.Plan(para, ids)
+    b.set_model(lam0, mu0, rho0); b.set_stf(c.stf)
+    with pytest.raises(ops.FwiError, match="not set"):
+        b.run(1)                                                         # observations are required for calc_id 0 / 1
+    for i in range(2):
+        with pytest.raises(ops.FwiError, match="shape"):
+            b.set_obs(i, obs[i][:, :-1])
+        b.set_obs(i, obs[i])
+    with pytest.raises(ops.FwiError):
+        b.set_obs(2, obs[0])
+    b.run(1)
+    rb = b.result()
+    assert ra[0] == rb[0] > 0 and all(np.array_equal(x, y) for x, y in zip(ra[1:], rb[1:]))
+    # a second set of observations replaces the first: zero data -> the residual is minus the synthetic
+    b.set_obs(1, np.zeros_like(obs[1]))
+    b.run(0)
+    assert b.result(with_grad=False) != ra[0]
+    b.close()
+
+
+def test_scratch_dir_dumps_match_reference(ops):
+    """para "scratch_dir_name" (libCUFD.cu:493-511): Residual_Shot / Syn_Shot / CondObs_Shot / src_updated files of a
+    gradient call, compared with the files the reference's own op writes for the same inputs."""
+    from oracle import oracle_py as op
+    if not op.ref_available():
+        pytest.skip("oracle/_ref/libCUFD_ref.so not built")
+    c = CASES["small_elastic"]
+    ids = np.arange(c.nShots, dtype=np.int32)
+    lam, mu, rho = c.moduli("true")
+    lam0, mu0, rho0 = c.moduli("init")
+    dirs = {}
+    for who, run in (("ref", op.ref_cufd), ("b200", b200_cufd)):
+        wd = tempfile.mkdtemp(prefix=f"scratch_{who}_")
+        para = c.write_files(wd, scratch=True)
+        run(2, lam, mu, rho, c.stf, ids, para)
+        run(1, lam0, mu0, rho0, c.stf, ids, para)
+        dirs[who] = os.path.join(wd, "Scratch")
+    for sid in ids:
+        for stem, n in (("Residual_Shot", c.nrec * c.nSteps), ("Syn_Shot", c.nrec * c.nSteps),
+                        ("CondObs_Shot", c.nrec * c.nSteps), ("src_updated", c.nSteps)):
+            r = np.fromfile(os.path.join(dirs["ref"], f"{stem}{sid}.bin"), np.float32)
+            m = np.fromfile(os.path.join(dirs["b200"], f"{stem}{sid}.bin"), np.float32)
+            assert r.size == m.size == n, stem
+            if stem == "src_updated":
+                assert rel(m, r) <= 1e-6                                  # the tapered source (Src_Rec.cu:140)
+            else:                                                         # sample 0 of a trace: SURVEY.md Q7
+                r, m = r.reshape(c.nrec, c.nSteps)[:, 1:], m.reshape(c.nrec, c.nSteps)[:, 1:]
+                assert np.abs(r).max() > 0 and rel(m, r) <= (TOL_TRACE if stem != "Residual_Shot" else 1e-3), stem
 
 
 def test_sources_and_receivers_in_the_nPad_rows_are_refused(ops):
@@ -410,3 +481,29 @@ def test_sources_and_receivers_in_the_nPad_rows_are_refused(ops):
         with pytest.raises(ops.FwiError) as ei:
             ops.fwi_obs_op(lam, mu, rho, c.stf, 0, [0], para)
         assert ei.value.code == -7 and "nPad" in str(ei.value), str(ei.value)
+
+
+def test_merged_backward_kernel_equals_separate_launches(ops):
+    """The backward loop as ONE launch per time index (bwd_step_kernel: adjoint step it+1, then reverse step + imaging
+    with the adjoint quads handed over in registers, density spray gathered in the kernel) against the two-launch form
+    (rev_image_kernel + adj_step_kernel, spray gathered by finalize): same gradients up to the summation order of the
+    density terms (<= 1e-5), same adjoint quantities (grad_stf)."""
+    from fwiflow.jl_b200 import synthetic
+    cases = [CASES["small_elastic"], CASES["aniso"], CASES["gradtest"], synthetic.case_c2(nshots=3, nSteps=500)]
+    try:
+        for c in cases:
+            para = c.write_files(tempfile.mkdtemp(prefix="merged_"))
+            ids = np.arange(c.nShots, dtype=np.int32)
+            lam, mu, rho = c.moduli("true")
+            lam0, mu0, rho0 = c.moduli("init")
+            ops.fwi_obs_op(lam, mu, rho, c.stf, 0, ids, para)
+            out = {}
+            for merged in (0, 1):
+                ops.set_option("merged_bwd", merged)
+                out[merged] = ops.fwi_op_and_grad(lam0, mu0, rho0, c.stf, 0, ids, para)
+            assert out[1][0] == out[0][0] > 0
+            for k in (1, 2, 3):
+                assert np.abs(out[0][k]).max() > 0 and rel(out[1][k], out[0][k]) <= 1e-5, (c.name, k)
+            assert rel(out[1][4], out[0][4]) <= 1e-5, c.name      # same adjoint arithmetic, separately compiled
+    finally:
+        ops.set_option("merged_bwd", 1)
