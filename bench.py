@@ -289,8 +289,16 @@ class Dist:
         self.world = int(os.environ.get("WORLD_SIZE", "1"))
         self.local = int(os.environ.get("LOCAL_RANK", "0"))
         torch.cuda.set_device(self.local)
+        self.cpu_group = None
         if self.world > 1:
             dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+            self.cpu_group = dist.new_group(backend="gloo")   # host-side barrier that leaves the GPUs idle
+
+    def host_barrier(self):
+        """Wait on the HOST only: a NCCL barrier is a kernel that spins on the waiting ranks' GPUs."""
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier(group=self.cpu_group)
 
     def barrier(self):
         if self.world > 1:
@@ -332,7 +340,8 @@ def timed_gradients(D, plan, steps, warmup, sampler_gpu=None):
     synchronize on both sides; returns (ms total = max over ranks, launches summed over ranks, clocks)."""
     torch, dist = D.torch, D.dist
     result = plan.result_tensor()
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.current_stream()   # the created stream run_ours() made current: kernels, all-reduce, events
+    assert stream.cuda_stream != 0
 
     def step():
         plan.run(1, stream=stream.cuda_stream, sync=False)
@@ -361,8 +370,8 @@ def kernel_table(plan, stream, nsteps, nbatches, step_ms, peak, traffic, iters):
     algorithmic bytes, and the ncu dram bytes of the committed capture."""
     spec = [  # (C-ABI selector, name, launches per gradient and batch, rule)
         (1, "fwd_step_kernel<save_frames>", nsteps - 1, "60 + 32 (fz + fx) B per cell + frame quads"),
-        (4, "bwd_step_kernel", nsteps - 1, "adjoint step 60 + 64 (fz + fx) B per cell + reverse/imaging 64 B per inner-box cell"),
-        (3, "adj_step_kernel", 1, "60 + 64 (fz + fx) B per cell"),
+        (2, "rev_image_kernel", nsteps - 1, "64 B per inner-box cell"),
+        (3, "adj_step_kernel", nsteps, "60 + 64 (fz + fx) B per cell"),
     ]
     rows = []
     for which, name, n_launch, rule in spec:
@@ -404,7 +413,11 @@ def run_ours(args):
     warmup = max(args.warmup, 3)
     peak, peak_src = measured_peak()
     traffic = ncu_traffic()
-    stream = torch.cuda.current_stream()
+    # ONE created stream carries everything that is timed: the plan's kernels, the NCCL all-reduce and the CUDA events.
+    # (torch's default stream is CUDA's legacy stream, handle 0 -- the C ABI reads a null handle as "the plan's own
+    # stream", and work there is not ordered with events or collectives on the default stream.)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
 
     # ================= headline: C2, 30 shots per GPU (weak) =================
     c = make_case(n_gpus)
@@ -459,6 +472,7 @@ def run_ours(args):
     # ---- N > 1: the whole node through ONE C-ABI call from rank 0 (NCCL inside the library) ----
     multi = None
     if world > 1 and not args.no_multi:
+        D.host_barrier()          # every rank idle, no collective kernel resident on any GPU
         if rank == 0:
             try:
                 wd = tempfile.mkdtemp(prefix="bench_multi_")
@@ -478,7 +492,7 @@ def run_ours(args):
                 ops.release()
             except Exception as e:
                 multi = {"error": str(e)[:300]}
-        D.barrier()
+        D.host_barrier()
 
     # ================= strong scaling (i): configs[1] literally -- 30 C2 shots over N ranks =================
     strong = {}

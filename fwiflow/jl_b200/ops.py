@@ -265,7 +265,15 @@ class Plan:
         check(self._L.fwi_b200_plan_load_obs_files(self._h))
 
     def run(self, calc_id, stream=None, sync=True):
-        check(self._L.fwi_b200_plan_run(self._h, int(calc_id), ctypes.c_void_p(stream) if stream else None,
+        """Enqueue one evaluation.  `stream`: a cudaStream_t handle (int) of a stream created by the caller, e.g.
+        `torch.cuda.Stream().cuda_stream`; None = the plan's own non-blocking stream.  The handle 0 (CUDA's legacy
+        default stream, what `torch.cuda.current_stream().cuda_stream` is unless a stream context is active) cannot be
+        told apart from "none" by the C ABI and is refused here: work enqueued on the plan's own stream would NOT be
+        ordered with anything the caller does on the default stream (events, collectives)."""
+        if stream is not None and int(stream) == 0:
+            raise FwiError(-1, "Plan.run: stream handle 0 (legacy default stream) -- pass a created stream's handle, or "
+                               "None for the plan's own stream (then synchronise with sync=True)")
+        check(self._L.fwi_b200_plan_run(self._h, int(calc_id), ctypes.c_void_p(int(stream)) if stream is not None else None,
                                         1 if sync else 0))
 
     def result(self, with_grad=True):
@@ -321,6 +329,6 @@ class Plan:
         ms = ctypes.c_float(0.0)
         nbytes = ctypes.c_double(0.0)
         check(self._L.fwi_b200_plan_time_kernel(self._h, int(which), int(iters),
-                                                ctypes.c_void_p(stream) if stream else None,
+                                                ctypes.c_void_p(int(stream)) if stream else None,
                                                 ctypes.byref(ms), ctypes.cast(ctypes.byref(nbytes), c_dp)))
         return float(ms.value), float(nbytes.value)

@@ -111,8 +111,9 @@ int fwi_b200_timelapse(int nsurveys, const char *const *para_fnames, const doubl
 int fwi_b200_para_info(const char *para_fname, int *out);
 
 /* Developer A/B switches (not part of the reference's surface).  "rev_lean": -1 pick the build of the reverse-time
- * kernel by working-set size (default), 0 / 1 force the double-buffered / LEAN build.  "merged_bwd": 1 (default) the
- * backward loop is one launch per time index (adjoint step + reverse step / imaging), 0 two launches. */
+ * kernel by working-set size (default), 0 / 1 force the double-buffered / LEAN build.  "merged_bwd": 0 (default) the
+ * backward loop is two launches per time index (reverse step / imaging, adjoint step), 1 one merged launch (moves fewer
+ * DRAM bytes but measured slower: latency-bound). */
 int fwi_b200_set_option(const char *name, int value);
 
 /* Host-only: the device layout this library derives from a parameter file (no GPU needed).

@@ -21,12 +21,15 @@ p.set_stf(c.stf); p.set_model(*c.moduli("true"))
 t0 = time.time(); p.run(2); t_obs = time.time() - t0
 p.write_obs_files(); p.set_model(*c.moduli("init")); p.load_obs_files()
 free0, total = torch.cuda.mem_get_info()
-s = torch.cuda.current_stream()
+s = torch.cuda.Stream()                    # a created stream: handle 0 (the legacy default stream) would mean "the plan's own"
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 p.run(1)                                   # warm-up (allocations)
 torch.cuda.synchronize()
+t0 = time.perf_counter()
 e0.record(s); p.run(1, stream=s.cuda_stream, sync=False); e1.record(s); torch.cuda.synchronize()
+wall = time.perf_counter() - t0
 ms = e0.elapsed_time(e1)
+assert abs(ms * 1e-3 - wall) < 0.05 * wall + 5e-3, (ms, wall)   # the events bracket the work
 free1, _ = torch.cuda.mem_get_info()
 j, gl, gm, gd, gs = p.result()
 cells = c.nz_pad * c.nx_pad

@@ -506,4 +506,4 @@ def test_merged_backward_kernel_equals_separate_launches(ops):
                 assert np.abs(out[0][k]).max() > 0 and rel(out[1][k], out[0][k]) <= 1e-5, (c.name, k)
             assert rel(out[1][4], out[0][4]) <= 1e-5, c.name      # same adjoint arithmetic, separately compiled
     finally:
-        ops.set_option("merged_bwd", 1)
+        ops.set_option("merged_bwd", 0)      # the default: two launches per time index (faster)
