@@ -395,6 +395,36 @@ def whole_gradient_alg_bytes(c, nshots, nsteps):
     return float(nshots) * per_index * (nsteps - 1)
 
 
+def timelapse_record(c, gpus, reps):
+    """BASELINE configs[3] (C4): 6 surveys (baseline + 5 monitors with a growing -5 % lambda / -1 % rho anomaly, each with
+    its own para file and Data directory, 30 shots x 2000 steps on the C2 grid) evaluated at the baseline model through
+    fwi_b200_timelapse with host buffers: survey i on gpus[i % len(gpus)], cached plans stay resident between calls."""
+    from fwiflow.jl_b200 import ops
+    lam, mu, rho = c.moduli("true")
+    z, x = np.mgrid[0:c.nz_pad, 0:c.nx_pad]
+    ids = np.arange(SHOTS_PER_GPU, dtype=np.int32)
+    stf = c.stf[:SHOTS_PER_GPU]
+    surveys = []
+    for k in range(6):
+        r = 6.0 + 3.0 * k
+        blob = np.exp(-(((z - (c.nPml + 0.55 * c.nz)) / r) ** 2 + ((x - (c.nPml + 0.5 * c.nx)) / (2.0 * r)) ** 2)) if k else 0.0
+        lam_k, rho_k = lam * (1.0 - 0.05 * blob), rho * (1.0 - 0.01 * blob)
+        ck = c2_case(SHOTS_PER_GPU)
+        para = ck.write_files(tempfile.mkdtemp(prefix=f"bench_c4_s{k}_"))
+        ops.fwi_obs_op(lam_k, mu, rho_k, stf, gpus[k % len(gpus)], ids, para)        # this survey's observations
+        surveys.append((para, lam, mu, rho))                                          # every survey evaluated at the baseline
+    out = ops.timelapse(surveys, stf, gpus, ids)                                     # plans + observations warm
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        out = ops.timelapse(surveys, stf, gpus, ids)
+    dt = (time.perf_counter() - t0) / reps
+    js = [o[0] for o in out]
+    return {"workload": "C4: time-lapse, 6 surveys x 30 shots x 2000 steps on the C2 grid, one fwi_b200_timelapse call "
+                        f"(host buffers) on {len(gpus)} GPU(s)", "surveys": 6, "shots_per_survey": SHOTS_PER_GPU,
+            "value": 6 * SHOTS_PER_GPU / dt, "unit": UNIT, "surveys_per_s": 6 / dt, "s_per_call": dt, "steps": reps,
+            "misfits": js, "monitor_misfits_grow": bool(js[0] == 0.0 and all(js[k + 1] > js[k] for k in range(5)))}
+
+
 def run_ours(args):
     import torch
     from fwiflow.jl_b200 import dist as fdist
@@ -494,6 +524,18 @@ def run_ours(args):
                 multi = {"error": str(e)[:300]}
         D.host_barrier()
 
+    # ================= C4: time-lapse, baseline + 5 monitor surveys in ONE C-ABI call (rank 0 drives every GPU) =================
+    c4 = None
+    if not args.no_c4:
+        D.host_barrier()
+        if rank == 0:
+            try:
+                c4 = timelapse_record(c, list(range(world)), e2e_steps)
+            except Exception as e:
+                c4 = {"error": str(e)[:300]}
+            ops.release()
+        D.host_barrier()
+
     # ================= strong scaling (i): configs[1] literally -- 30 C2 shots over N ranks =================
     strong = {}
     if world > 1:
@@ -543,14 +585,14 @@ def run_ours(args):
         c3s = c3_case(STRONG_C3_SHOTS, STRONG_C3_NSTEPS)
         ids3s = fdist.shard_shots(np.arange(c3s.nShots, dtype=np.int32), rank, world)
         p3s, _ = resident_plan(D, c3s, ids3s, tempfile.mkdtemp(prefix=f"bench_c3s_r{rank}_"))
-        ms3s, _, _ = timed_gradients(D, p3s, 1, 1 if world > 1 else 0)
+        ms3s, _, _ = timed_gradients(D, p3s, 1, 1)
         strong["c3_200_shots"] = {"workload": f"configs[2]: C3 grid, {STRONG_C3_SHOTS} shots in total split over the ranks, "
                                               f"{STRONG_C3_NSTEPS} of the 4000 steps (same per-step work; keeps the N = 1 point short)",
                                   "shots_total": STRONG_C3_SHOTS, "shots_per_rank": int(len(ids3s)), "batch": int(p3s.batch),
                                   "value": STRONG_C3_SHOTS / (ms3s * 1e-3), "unit": UNIT + f" ({STRONG_C3_NSTEPS}-step shots)",
                                   "ms_per_gradient": ms3s,
                                   "cell_updates_per_s": 2.0 * STRONG_C3_SHOTS * cells3 * (STRONG_C3_NSTEPS - 1) / (ms3s * 1e-3),
-                                  "steps": 1, "warmup": 1 if world > 1 else 0}
+                                  "steps": 1, "warmup": 1}
         p3s.close()
         D.barrier()
 
@@ -564,6 +606,8 @@ def run_ours(args):
                            "parallelism": f"shots sharded over {n_gpus} GPU(s), one all-reduce per gradient"},
                 "cell_updates_per_s": cell_updates, "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline,
                 "kernels": kernels, "clocks": clocks, "configs": configs, "strong": strong}
+        if c4:
+            line["configs"]["c4"] = c4
         if multi:
             line["multi_c_abi"] = multi
         if cb:
@@ -584,6 +628,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-c3", action="store_true", help="skip the C3 config record and the C3 strong-scaling record")
     ap.add_argument("--no-multi", action="store_true", help="skip the single-process multi-GPU C-ABI leg (N > 1)")
+    ap.add_argument("--no-c4", action="store_true", help="skip the time-lapse (C4) record")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -116,7 +116,9 @@ rev_image_kernel(const __grid_constant__ BwdArgs a, int tz_first, int tx_first, 
     d.z0 = z0; d.x0 = x0; d.shot = shot; d.tile = t; d.sz = sz; d.sx = sx; d.r0 = d.r1 = 0;
     int fl = 0;
     // every tile whose owner cells or their +-4 halo can touch the ring (the old launch's frame_tile test)
-    if (!(z0 - 4 > g.zlo + 2 && z0 + TILE_Z + 3 < g.zhi - 2 && x0 - 2 > g.xlo + 2 && x0 + TILE_X + 1 < g.xhi - 2)) fl |= TF_FRAME;
+    if (!(z0 - 4 > g.zlo - 1 + g.f_in && z0 + TILE_Z + 3 < g.zhi + 1 - g.f_in && x0 - 2 > g.xlo - 1 + g.f_in &&
+          x0 + TILE_X + 1 < g.xhi + 1 - g.f_in))
+      fl |= TF_FRAME;
     if (sz >= z0 && sz < z0 + TILE_Z && sx >= x0 && sx < x0 + TILE_X) fl |= TF_SRC;
     d.flags = fl;
     d.pad[0] = d.pad[1] = d.pad[2] = d.pad[3] = 0;
@@ -858,7 +860,9 @@ __global__ void __launch_bounds__(NCOMPUTE, 1) bwd_step_kernel(const __grid_cons
       if (has_rev) p_kind = 1; else p_item += stride;
     } else {   // ---- phase R boxes: forward stress triple of time it+1 (halo 8 / 4) + forward velocity pair (halo 4 / 2) ----
       d.r0 = d.r1 = 0;
-      if (!(z0 - 4 > g.zlo + 2 && z0 + TILE_Z + 3 < g.zhi - 2 && x0 - 2 > g.xlo + 2 && x0 + TILE_X + 1 < g.xhi - 2)) fl |= TF_FRAME;
+      if (!(z0 - 4 > g.zlo - 1 + g.f_in && z0 + TILE_Z + 3 < g.zhi + 1 - g.f_in && x0 - 2 > g.xlo - 1 + g.f_in &&
+          x0 + TILE_X + 1 < g.xhi + 1 - g.f_in))
+      fl |= TF_FRAME;
       d.flags = fl;
       sdesc[ds] = d;
       const int p0 = shot * S_COUNT + fin;

@@ -159,17 +159,19 @@ struct __align__(16) TileDesc {  // built by the producer lane, read (broadcast)
 static_assert(sizeof(TileDesc) == 64, "descriptor size");
 
 // Boundary frames (the reference's Bnd store, Boundary.cu:17-41, utilities.cu:361-424): per step and field the
-// float4 quads that intersect the 5-cell ring starting 2 cells outside the inner box, laid out as
-// [left 5 columns | right 5 columns | per middle column: 2 top quads, 2 bottom quads].  Returns the quad slot of
-// the quad starting at row gz (a multiple of 4) in column gx, or -1.  Restoring a whole quad also restores a few
-// cells next to the ring with their exact forward values, which is harmless.
+// float4 quads that intersect the ring around the inner box -- the two cells outside it on every side plus f_in cells
+// inside (f_in = 3: the reference's 5-deep ring; f_in = 0: only what the stencils of the box cells reach) -- laid out as
+// [left 2 + f_in columns | right 2 + f_in columns | per middle column: f_ntq top quads, f_nbq bottom quads].  Returns the
+// quad slot of the quad starting at row gz (a multiple of 4) in column gx, or -1.  Restoring a whole quad also restores
+// a few cells next to the ring with their exact forward values, which is harmless.
 __device__ __forceinline__ int frame_quad(const Grid &g, int gz, int gx) {
   if (gx < g.xlo - 2 || gx > g.xhi + 2 || gz < g.f_zq0 || gz > g.zhi + 2) return -1;
-  if (gx <= g.xlo + 2) return (gx - (g.xlo - 2)) * g.f_nqB + ((gz - g.f_zq0) >> 2);
-  if (gx >= g.xhi - 2) return (5 + gx - (g.xhi - 2)) * g.f_nqB + ((gz - g.f_zq0) >> 2);
-  const int t = gz >> 2, mid = 10 * g.f_nqB + (gx - (g.xlo + 3)) * 4;
-  if ((unsigned)(t - g.f_tq0) < 2u) return mid + (t - g.f_tq0);
-  if ((unsigned)(t - g.f_bq0) < 2u) return mid + 2 + (t - g.f_bq0);
+  const int nL = 2 + g.f_in;
+  if (gx <= g.xlo - 1 + g.f_in) return (gx - (g.xlo - 2)) * g.f_nqB + ((gz - g.f_zq0) >> 2);
+  if (gx >= g.xhi + 1 - g.f_in) return (nL + gx - (g.xhi + 1 - g.f_in)) * g.f_nqB + ((gz - g.f_zq0) >> 2);
+  const int t = gz >> 2, mid = 2 * nL * g.f_nqB + (gx - (g.xlo + g.f_in)) * (g.f_ntq + g.f_nbq);
+  if ((unsigned)(t - g.f_tq0) < (unsigned)g.f_ntq) return mid + (t - g.f_tq0);
+  if ((unsigned)(t - g.f_bq0) < (unsigned)g.f_nbq) return mid + g.f_ntq + (t - g.f_bq0);
   return -1;
 }
 // 16-byte asynchronous copy global -> shared (LDGSTS): no register staging; complete after cp_async_wait_all()
@@ -180,7 +182,8 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 __device__ __forceinline__ bool tile_touches_frame(const Grid &g, int z0, int x0) {
   return !(z0 > g.zhi + 2 || z0 + TILE_Z - 1 < g.zlo - 2 || x0 > g.xhi + 2 || x0 + TILE_X - 1 < g.xlo - 2) &&
-         !(z0 > g.zlo + 2 && z0 + TILE_Z - 1 < g.zhi - 2 && x0 > g.xlo + 2 && x0 + TILE_X - 1 < g.xhi - 2);
+         !(z0 > g.zlo - 1 + g.f_in && z0 + TILE_Z - 1 < g.zhi + 1 - g.f_in && x0 > g.xlo - 1 + g.f_in &&
+           x0 + TILE_X - 1 < g.xhi + 1 - g.f_in);
 }
 
 }  // namespace dev

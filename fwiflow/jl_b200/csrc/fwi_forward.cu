@@ -110,6 +110,12 @@ __global__ void __launch_bounds__(NTHREADS_FWD, 1) fwd_step_kernel(const __grid_
     if (sz >= z0 - 4 && sz < z0 + TILE_Z + 4 && sx >= x0 - 2 && sx < x0 + TILE_X + 2) fl |= TF_SRC;
     d.flags = fl;
     d.pad[0] = d.pad[1] = d.pad[2] = d.pad[3] = 0;
+    if (item + stride < nitems) {   // tile origin of this CTA's NEXT item: its coefficient quads are fetched one item ahead,
+      const int ion = a.order ? nitems - 1 - (item + stride) : item + stride;   // and 512 threads need not divide for it
+      const int tn = ion / a.batch;
+      d.pad[0] = (tn % g.tiles_z) * TILE_Z + g.z_off;
+      d.pad[1] = (tn / g.tiles_z) * TILE_X;
+    }
     sdesc[ds] = d;
     unsigned char *sb = base + stage * STAGE_BYTES;
     const int p0 = shot * S_COUNT + fin;
@@ -297,14 +303,13 @@ __global__ void __launch_bounds__(NTHREADS_FWD, 1) fwd_step_kernel(const __grid_
       fx1 = ld4s(sq + (S_PHI_A + PHI_SXZ_X) * pl);
       fx2 = ld4s(sq + (S_PHI_A + PHI_SXX_X) * pl);
     }
-    // the next item's stress coefficients: requested now, used after the barrier.  Its tile origin is recomputed here
-    // rather than read from the producer's descriptor, which is written after the previous block barrier and is
-    // therefore only safe to read on the far side of this one.
+    // the next item's stress coefficients: requested now, used after the barrier.  Its tile origin travels in THIS
+    // item's descriptor (the next item's own descriptor is written after the previous block barrier and is therefore
+    // only safe to read on the far side of this one).
     const bool more = item + stride < nitems;
     const float *mq_next = a.m.ldt;
     if (more) {
-      const int tn = (a.order ? nitems - 1 - (item + stride) : item + stride) / a.batch;
-      const int gzn = (tn % g.tiles_z) * TILE_Z + g.z_off - 4 + 4 * q, gxn = min((tn / g.tiles_z) * TILE_X - 2 + c, gx_max);
+      const int gzn = d.pad[0] - 4 + 4 * q, gxn = min(d.pad[1] - 2 + c, gx_max);
       mq_next = a.m.ldt + ((long long)gxn * P + gzn);
       ldt = ld4(mq_next); l2mdt = ld4(mq_next + pl); amudt = ld4(mq_next + 2 * pl);
     }

@@ -59,9 +59,12 @@ struct Grid {
   float dt, rdz, rdx;      // 1/dz, 1/dx
   // boundary frames
   // boundary frames, stored at float4-quad granularity (every quad that intersects the 5-cell ring)
+  int f_in;            // ring cells kept INSIDE the box on each side: 3 = the reference's 5-deep ring (Boundary.cu:17-27),
+                       // 0 = only the two cells outside the box that the 4th-order stencils of the box cells reach
   int f_zq0;           // first row of the first ring quad: (zlo-2) & ~3
-  int f_nqB;           // quads per column of the left / right bands
-  int f_tq0, f_bq0;    // z >> 2 of the first quad of the top / bottom bands (two quads each)
+  int f_nqB;           // quads per column of the left / right bands (2 + f_in columns each)
+  int f_tq0, f_bq0;    // z >> 2 of the first quad of the top / bottom bands
+  int f_ntq, f_nbq;    // quads per column of the top / bottom bands (1 or 2)
   int f_len;           // floats per field per step
 };
 

@@ -145,6 +145,9 @@ struct fwi_b200_plan {
 #ifndef FWI_ADJ_INDEP
 #define FWI_ADJ_INDEP 1
 #endif
+#ifndef FWI_FRAME_RING
+#define FWI_FRAME_RING 2   // saved boundary ring: 2 = the two cells outside the box (default), 5 = the reference's ring (set_option)
+#endif
 #ifndef FWI_MERGED_BWD
 #define FWI_MERGED_BWD 0   // measured: the merged backward launch moves 12 % fewer DRAM bytes but is latency-bound (196 KB of shared
                            // memory leave 60 KB of L1, 59 spilled registers): C2 322 vs 280 ms, C3 15.0 vs 13.3 s per gradient
@@ -152,6 +155,8 @@ struct fwi_b200_plan {
 
 namespace {
 
+// depth of the saved boundary ring: 5 = the reference's (2 cells outside + 3 inside the box), 2 = the two outside cells
+std::atomic<int> g_frame_ring{FWI_FRAME_RING};
 // 1: backward loop = one merged launch per time index (bwd_step_kernel); 0: reverse + adjoint launches (A/B, set_option)
 std::atomic<int> g_merged_bwd{FWI_MERGED_BWD};
 
@@ -206,13 +211,21 @@ void build_grid(const Para &p, Grid &g) {
   g.rdx = (float)(1.0 / (double)p.dx);
   // frames: left/right bands = 10 columns x the quads covering rows zlo-2 .. zhi+2; top/bottom bands = 2 quads each
   // for the columns in between (5 consecutive rows always span exactly two aligned quads)
+  if (g.zhi - g.zlo + 1 < 8 || g.xhi - g.xlo + 1 < 8)
+    throw Error(FWI_B200_ERR_GEOM, "grid too small: fewer than 8 cells between the PML layers");
+  // Ring depth: the reverse-time update of a box cell reads two cells beyond the box (4th-order staggered stencils),
+  // so those two are all that MUST be replayed from the forward pass; the reference also overwrites the three box cells
+  // next to them with their forward values (5-deep ring, Boundary.cu:17-27).  frame_ring = 5 keeps that, 2 stores
+  // 2.1x fewer bytes per step (C5: 12.8 instead of 27 GB per shot) and lets the box cells be reconstructed like every
+  // other box cell; the gradients agree to rounding (tests/test_parity_gpu.py::test_thin_boundary_frames).
+  g.f_in = g_frame_ring.load(std::memory_order_relaxed) >= 5 ? 3 : 0;
   g.f_zq0 = (g.zlo - 2) & ~3;
   g.f_nqB = ((g.zhi + 2) >> 2) - (g.f_zq0 >> 2) + 1;
   g.f_tq0 = (g.zlo - 2) >> 2;
-  g.f_bq0 = (g.zhi - 2) >> 2;
-  g.f_len = 4 * (10 * g.f_nqB + 4 * std::max(0, g.xhi - g.xlo + 1 - 6));
-  if (g.zhi - g.zlo + 1 < 8 || g.xhi - g.xlo + 1 < 8)
-    throw Error(FWI_B200_ERR_GEOM, "grid too small: fewer than 8 cells between the PML layers");
+  g.f_ntq = ((g.zlo - 1 + g.f_in) >> 2) - g.f_tq0 + 1;
+  g.f_bq0 = (g.zhi + 1 - g.f_in) >> 2;
+  g.f_nbq = ((g.zhi + 2) >> 2) - g.f_bq0 + 1;
+  g.f_len = 4 * (2 * (2 + g.f_in) * g.f_nqB + (g.f_ntq + g.f_nbq) * std::max(0, g.xhi - g.xlo + 1 - 2 * g.f_in));
 }
 
 void upload_profiles(fwi_b200_plan &pl) {
@@ -950,7 +963,8 @@ std::list<CacheEntry> g_cache;           // most recently used first
 constexpr size_t kCachePerGpu = 8;       // per device: baseline + 5 monitor surveys of a time-lapse inversion stay resident (C4)
 
 std::string cache_key(const char *para_fname, const Para &p, const std::string &survey_text, int group, const int *ids) {
-  std::string k = std::string(para_fname) + "\n" + p.text + "\n" + survey_text + "\n";
+  std::string k = std::string(para_fname) + "\n" + p.text + "\n" + survey_text + "\n" +
+                  std::to_string(g_frame_ring.load(std::memory_order_relaxed)) + "\n";
   for (int i = 0; i < group; i++) k += std::to_string(ids[i]) + ",";
   return k;
 }
@@ -1308,6 +1322,10 @@ extern "C" int fwi_b200_set_option(const char *name, int value) {
     const std::string k(name);
     if (k == "rev_lean") set_rev_lean(value);
     else if (k == "merged_bwd") g_merged_bwd.store(value != 0, std::memory_order_relaxed);
+    else if (k == "frame_ring") {   // takes effect for plans created afterwards
+      if (value != 2 && value != 5) throw Error(FWI_B200_ERR_ARG, "set_option: frame_ring must be 2 or 5");
+      g_frame_ring.store(value, std::memory_order_relaxed);
+    }
     else throw Error(FWI_B200_ERR_ARG, "set_option: unknown option '" + k + "'");
   });
 }

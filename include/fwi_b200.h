@@ -113,7 +113,10 @@ int fwi_b200_para_info(const char *para_fname, int *out);
 /* Developer A/B switches (not part of the reference's surface).  "rev_lean": -1 pick the build of the reverse-time
  * kernel by working-set size (default), 0 / 1 force the double-buffered / LEAN build.  "merged_bwd": 0 (default) the
  * backward loop is two launches per time index (reverse step / imaging, adjoint step), 1 one merged launch (moves fewer
- * DRAM bytes but measured slower: latency-bound). */
+ * DRAM bytes but measured slower: latency-bound).  "frame_ring": depth of the boundary ring saved per
+ * time step for the reverse-time reconstruction, for plans created afterwards: 2 (default) the two cells outside the
+ * inner box that the stencils of the box cells read, 5 the reference's ring (Boundary.cu:17-27: those two plus three
+ * box cells); same gradients to 2e-5, 2.1x the frame bytes. */
 int fwi_b200_set_option(const char *name, int value);
 
 /* Host-only: the device layout this library derives from a parameter file (no GPU needed).

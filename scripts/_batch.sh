@@ -1,8 +1,9 @@
 set -x
-mkdir -p gpurun_out/r2h
-nvidia-smi -L
-timeout 600 python -m pytest tests/test_parity_gpu.py -x -q -k "multi or merged or sharded" > gpurun_out/r2h/multi_test.log 2>&1; tail -15 gpurun_out/r2h/multi_test.log
-( time timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 3 --warmup 3 ) > gpurun_out/r2h/bench2.json 2> gpurun_out/r2h/bench2.err
-tail -12 gpurun_out/r2h/bench2.err; cut -c1-300 gpurun_out/r2h/bench2.json
-( time timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 2 --warmup 1 ) > gpurun_out/r2h/ref2.json 2> gpurun_out/r2h/ref2.err
-tail -6 gpurun_out/r2h/ref2.err; cut -c1-300 gpurun_out/r2h/ref2.json
+mkdir -p gpurun_out/r2i
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r2i/tests.log 2>&1; tail -8 gpurun_out/r2i/tests.log
+timeout 300 python scripts/kernel_times.py c2 30 200 > gpurun_out/r2i/kt_c2.log 2>&1; grep -v "^obs\|^grad" gpurun_out/r2i/kt_c2.log
+timeout 300 python scripts/kernel_times.py c3 8 50 > gpurun_out/r2i/kt_c3.log 2>&1; grep -v "^obs\|^grad" gpurun_out/r2i/kt_c3.log
+for r in 5 2; do FWI_RING=$r timeout 300 python scripts/run_config.py c2 30 2000 >> gpurun_out/r2i/cfg.json 2>> gpurun_out/r2i/cfg.err; done
+FWI_RING=2 timeout 600 python scripts/run_config.py c3 25 4000 >> gpurun_out/r2i/cfg.json 2>> gpurun_out/r2i/cfg.err
+FWI_RING=2 timeout 900 python scripts/run_config.py c5 8 8000 >> gpurun_out/r2i/cfg.json 2>> gpurun_out/r2i/cfg.err
+cat gpurun_out/r2i/cfg.json; tail -5 gpurun_out/r2i/cfg.err

@@ -243,7 +243,11 @@ def test_device_layout_invariants(lib_built):
         wd = tempfile.mkdtemp()
         para = os.path.join(wd, "p.json")
         paraGen(nz, nx, 10.0, 10.0, 100, 0.001, 5.0, nPml, nPad, para, os.path.join(wd, "s.json"), os.path.join(wd, "D"))
-        g = ops.grid_info(para)
+        ops.set_option("frame_ring", 5)          # the reference's ring depth; the default is the thin ring, below
+        try:
+            g = ops.grid_info(para)
+        finally:
+            ops.set_option("frame_ring", 2)
         assert (g["nz"], g["nx"]) == (nz, nx) and g["pitch"] % 32 == 0 and g["pitch"] >= nz
         az_hi = nz - nPad - 3
         assert g["zlive"] % 4 == 0 and az_hi < g["zlive"] <= min(nz, az_hi + 4)
@@ -253,6 +257,10 @@ def test_device_layout_invariants(lib_built):
         assert (g["zlo"], g["zhi"], g["xlo"], g["xhi"]) == (nPml, nz - nPad - 1 - nPml, nPml, nx - 1 - nPml)
         len_bnd = 10 * ((nz - 2 * nPml - nPad + 4) + (nx - 2 * nPml + 4))          # Boundary.cu:19-23
         assert len_bnd <= g["frame_len"] <= 1.6 * len_bnd + 64, (nz0, nx0, nPml, len_bnd, g["frame_len"])
+        # the thin ring (the two cells outside the box only; still whole quads) is at most 0.8x the 5-deep one -- half of
+        # it where the two ring rows fall into one quad (C2 / C3 / C5: 0.49x)
+        thin = ops.grid_info(para)["frame_len"]
+        assert 0.2 * len_bnd <= thin <= 0.8 * g["frame_len"], (nz0, nx0, nPml, len_bnd, thin)
     c2 = ops.grid_info(os.path.join(_case_c2_para()))
     assert (c2["tiles_z"], c2["tiles_x"], c2["zlive"]) == (4, 16, 196)
 

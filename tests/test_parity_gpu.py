@@ -507,3 +507,31 @@ def test_merged_backward_kernel_equals_separate_launches(ops):
             assert rel(out[1][4], out[0][4]) <= 1e-5, c.name      # same adjoint arithmetic, separately compiled
     finally:
         ops.set_option("merged_bwd", 0)      # the default: two launches per time index (faster)
+
+
+def test_thin_boundary_frames(ops):
+    """frame_ring = 2: only the two cells outside the inner box are saved per step (what the 4th-order stencils of the
+    box cells read) instead of the reference's 5-deep ring; the three box cells next to them are then reconstructed
+    like every other box cell.  Same gradients up to the rounding of the reconstruction (<= 2e-5), less than half the
+    frame bytes -- on grids with nPml = 32 / 20, nPad = 0, ring rows that do and do not fill a quad."""
+    from fwiflow.jl_b200 import synthetic
+    cases = [CASES["small_elastic"], CASES["aniso"], CASES["gradtest"], synthetic.case_c2(nshots=2, nSteps=800)]
+    try:
+        for c in cases:
+            para = c.write_files(tempfile.mkdtemp(prefix="ring_"))
+            ids = np.arange(c.nShots, dtype=np.int32)
+            lam, mu, rho = c.moduli("true")
+            lam0, mu0, rho0 = c.moduli("init")
+            ops.fwi_obs_op(lam, mu, rho, c.stf, 0, ids, para)
+            out, flen = {}, {}
+            for ring in (5, 2):
+                ops.set_option("frame_ring", ring)
+                flen[ring] = ops.grid_info(para)["frame_len"]
+                out[ring] = ops.fwi_op_and_grad(lam0, mu0, rho0, c.stf, 0, ids, para)
+            assert flen[2] < 0.6 * flen[5]
+            assert out[2][0] == out[5][0] > 0                                  # the misfit comes from the forward pass
+            for k in (1, 2, 3):
+                assert np.abs(out[5][k]).max() > 0 and rel(out[2][k], out[5][k]) <= 2e-5, (c.name, k)
+            assert np.array_equal(out[2][4], out[5][4]), c.name               # the adjoint field never sees the frames
+    finally:
+        ops.set_option("frame_ring", 2)      # the default
