@@ -7,6 +7,9 @@
 #include <cstdint>
 #include <utility>
 
+#include <string>
+
+#include "fwi_host.hpp"
 #include "fwi_kernels.cuh"
 
 #ifndef FWI_PDL
@@ -203,7 +206,9 @@ inline void launch_step(void (*kernel)(KArgs...), int blocks, int threads, size_
   attr[0].val.programmaticStreamSerializationAllowed = FWI_PDL;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+  if (e != cudaSuccess)   // surfaces at the launch that failed, not at the end of the run
+    throw Error(FWI_B200_ERR_CUDA, std::string("CUDA: kernel launch failed: ") + cudaGetErrorString(e));
 }
 
 }  // namespace fwi

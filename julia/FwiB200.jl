@@ -11,8 +11,28 @@ rowmajor(a::AbstractMatrix{Float64}) = permutedims(a)      # (nz,nx) col-major -
 fwi_error(rc) = rc == 0 ? nothing :
     error("fwi_b200 ($rc): " * unsafe_string(ccall((:fwi_b200_last_error, LIBFWI), Cstring, ())))
 
+"what the parameter file says: [nz, nx, nSteps, nPoints_pml, nPad, if_win, scratch, 0] (host-only, fwi_b200_para_info)"
+function para_info_b200(para::String)
+    out = zeros(Int32, 8)
+    rc = ccall((:fwi_b200_para_info, LIBFWI), Cint, (Cstring, Ptr{Cint}), para, out)
+    fwi_error(rc); out
+end
+
+"the C ABI carries no sizes (like the reference's cufd): refuse arrays that do not match the parameter file"
+function check_shapes_b200(λ, μ, ρ, stf, shot_ids, para::String)
+    info = para_info_b200(para); nz, nx, nsteps = info[1], info[2], info[3]
+    for (name, a) in (("lambda", λ), ("mu", μ), ("den", ρ))
+        size(a) == (nz, nx) || error("fwi_b200: $name has size $(size(a)); the parameter file says ($nz, $nx)")
+    end
+    size(stf, 2) == nsteps || error("fwi_b200: stf has $(size(stf, 2)) samples per row; the parameter file says $nsteps")
+    (isempty(shot_ids) || minimum(shot_ids) < 0 || maximum(shot_ids) >= size(stf, 1)) &&
+        error("fwi_b200: shot ids do not index the $(size(stf, 1)) rows of stf (row = global shot id)")
+    nothing
+end
+
 "loss = fwi_op_b200(λ, μ, ρ, stf, gpu_id, shot_ids0, para)   (calc_id 0; FwiOp.cpp:47-103)"
 function fwi_op_b200(λ, μ, ρ, stf, gpu_id::Integer, shot_ids::Vector{Int32}, para::String)
+    check_shapes_b200(λ, μ, ρ, stf, shot_ids, para)
     misfit = Ref{Cdouble}(0.0)
     rc = ccall((:fwi_b200_forward, LIBFWI), Cint,
                (Ref{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Cint, Cint, Ptr{Cint}, Cstring),
@@ -22,6 +42,7 @@ end
 
 "(gλ, gμ, gρ, g_stf) = fwi_op_grad_b200(...)                  (calc_id 1; FwiOp.cpp:130-223)"
 function fwi_op_grad_b200(λ, μ, ρ, stf, gpu_id::Integer, shot_ids::Vector{Int32}, para::String)
+    check_shapes_b200(λ, μ, ρ, stf, shot_ids, para)
     nz, nx = size(λ); nsteps = size(stf, 2)
     gλ = zeros(nx, nz); gμ = zeros(nx, nz); gρ = zeros(nx, nz)          # row-major (nz,nx) buffers
     gs = zeros(nsteps, length(shot_ids))                                # row-major (group, nSteps)
@@ -36,6 +57,7 @@ end
 
 "writes <data_dir>/Shot<id>.bin                               (calc_id 2; FwiOp.cpp:260-317)"
 function fwi_obs_op_b200(λ, μ, ρ, stf, gpu_id::Integer, shot_ids::Vector{Int32}, para::String)
+    check_shapes_b200(λ, μ, ρ, stf, shot_ids, para)
     misfit = Ref{Cdouble}(0.0)
     rc = ccall((:fwi_b200_obscalc, LIBFWI), Cint,
                (Ref{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Cint, Cint, Ptr{Cint}, Cstring),
@@ -45,6 +67,7 @@ end
 
 "(loss, gλ, gμ, gρ, g_stf) on several GPUs of this process"
 function fwi_op_and_grad_multi_b200(λ, μ, ρ, stf, gpu_ids::Vector{Int32}, shot_ids::Vector{Int32}, para::String)
+    check_shapes_b200(λ, μ, ρ, stf, shot_ids, para)
     nz, nx = size(λ); nsteps = size(stf, 2)
     misfit = Ref{Cdouble}(0.0)
     gλ = zeros(nx, nz); gμ = zeros(nx, nz); gρ = zeros(nx, nz); gs = zeros(nsteps, length(shot_ids))
@@ -70,6 +93,7 @@ fwi_obs_op(λ::Array{Float64}, μ::Array{Float64}, ρ::Array{Float64}, stf::Arra
 
 "(misfit, gλ, gμ, gρ, g_stf) from ONE forward propagation (fwi_b200_misfit_and_gradient)"
 function fwi_op_and_grad_b200(λ, μ, ρ, stf, gpu_id::Integer, shot_ids::Vector{Int32}, para::String)
+    check_shapes_b200(λ, μ, ρ, stf, shot_ids, para)
     nz, nx = size(λ); nsteps = size(stf, 2)
     misfit = Ref{Cdouble}(0.0)
     gλ = zeros(nx, nz); gμ = zeros(nx, nz); gρ = zeros(nx, nz); gs = zeros(nsteps, length(shot_ids))
