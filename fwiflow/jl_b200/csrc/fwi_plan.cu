@@ -1237,18 +1237,20 @@ extern "C" int fwi_b200_gradient_multi(double *misfit, double *gl, double *gm, d
     }
     const bool reduce = shards.size() > 1;
     if (reduce) nccl_api();   // fail before any work if NCCL cannot be loaded
-    // one host thread per device: cached plan, inputs H2D, observations, forward + backward enqueued on the plan's
-    // stream.  Nothing synchronises: the gradient of the shard stays in the plan's packed result buffer.
-    std::vector<std::thread> workers;
+    // the cached plan of every shard, and its call lock (taken and released by THIS thread, in device order)
     for (size_t r = 0; r < shards.size(); r++) {
       Shard &sh = shards[r];
       sh.gpu = gpu_ids[r];
-      workers.emplace_back([&sh, Lambda, Mu, Den, stf, para_fname] {
-        sh.rc = guarded([&] {
-          sh.plan = cached_plan(para_fname, sh.gpu, (int)sh.ids.size(), sh.ids.data());
-          sh.call = std::unique_lock<std::mutex>(sh.plan->call_mu);
-          host_eval(sh.plan.get(), Lambda, Mu, Den, stf, 1, false);
-        });
+      sh.plan = cached_plan(para_fname, sh.gpu, (int)sh.ids.size(), sh.ids.data());
+      sh.call = std::unique_lock<std::mutex>(sh.plan->call_mu);
+    }
+    // one host thread per device: inputs H2D, observations, forward + backward enqueued on the plan's stream.
+    // Nothing synchronises: the gradient of the shard stays in the plan's packed result buffer.
+    std::vector<std::thread> workers;
+    for (size_t r = 0; r < shards.size(); r++) {
+      Shard &sh = shards[r];
+      workers.emplace_back([&sh, Lambda, Mu, Den, stf] {
+        sh.rc = guarded([&] { host_eval(sh.plan.get(), Lambda, Mu, Den, stf, 1, false); });
         if (sh.rc != FWI_B200_OK) sh.err = last_error_cstr();   // the error text is thread-local
       });
     }

@@ -1,5 +1,8 @@
 set -x
-mkdir -p gpurun_out/r2l
-nvidia-smi -L | wc -l
-( time timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29531 bench.py --gpus 8 --steps 5 --warmup 3 ) > gpurun_out/r2l/bench8.json 2> gpurun_out/r2l/bench8.err
-tail -8 gpurun_out/r2l/bench8.err; cut -c1-300 gpurun_out/r2l/bench8.json
+mkdir -p gpurun_out/r2m
+( time python -c "import __graft_entry__ as g; g.build(); g.smoke()" ) > gpurun_out/r2m/smoke.log 2>&1; tail -4 gpurun_out/r2m/smoke.log
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r2m/tests.log 2>&1; tail -4 gpurun_out/r2m/tests.log
+python scripts/c1_times.py > gpurun_out/r2m/c1.json 2> gpurun_out/r2m/c1.err; cat gpurun_out/r2m/c1.json
+( time python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 ) > gpurun_out/r2m/bench_ref.json 2> gpurun_out/r2m/bench_ref.err
+( time python bench.py --gpus 1 --steps 20 --warmup 5 ) > gpurun_out/r2m/bench.json 2> gpurun_out/r2m/bench.err
+grep real gpurun_out/r2m/*.err; cut -c1-260 gpurun_out/r2m/bench.json gpurun_out/r2m/bench_ref.json
