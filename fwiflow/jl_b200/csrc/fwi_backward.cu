@@ -135,7 +135,7 @@ rev_image_kernel(const __grid_constant__ BwdArgs a, int tz_first, int tx_first, 
 #if FWI_L2PF
     // operands of the owner quads that are fetched with direct loads: adjoint fields and imaging accumulators -> L2
     tma_prefetch_3d(&a.tm.o5, z0, x0 + XM, shot * S_COUNT + ain);
-    tma_prefetch_3d(&a.tm.g5, z0, x0 + XM, shot * G_COUNT);
+    tma_prefetch_3d(&a.tm.g4, z0, x0 + XM, shot * G_COUNT);
 #endif
   };
   if (tid == PRODUCER_TID)
@@ -189,12 +189,19 @@ rev_image_kernel(const __grid_constant__ BwdArgs a, int tz_first, int tx_first, 
       }
     }
 
-    // global operands of the velocity half, requested before waiting for the ring: buoyancies, adjoint velocities
+    // global operands of the velocity half, requested before waiting for the ring: buoyancies, adjoint velocities.
+    // The density spray (el_velocity.cu:105-110) is applied here as a gather -- cell (z, x) receives g_a(z, x) +
+    // g_b(z, x) + g_a(z-1, x) + g_b(z, x-1) -- so the quad row above the owner rows needs its adjoint vz as well (its
+    // g_a comes down by shuffle), and every owner thread evaluates g_b of the column to its left itself (one more
+    // adjoint quad and buoyancy quad, both L2 hits: the neighbour thread loads the same lines).
     const F4 byadt = ld4(mq + 3 * pl), bybdt = ld4(mq + 4 * pl);
-    F4 vza = zero4(), vxa = zero4();
+    F4 vza = zero4(), vxa = zero4(), vxaL = zero4(), bybL = zero4();
+    const bool above = q == 0 && c >= 2 && c < TILE_X + 2 && inb;   // halo quad right above an owner quad
+    if (owner || above) vza = ld4s(sq + (ain + F_VZ) * pl);
     if (owner) {
-      vza = ld4s(sq + (ain + F_VZ) * pl);
       vxa = ld4s(sq + (ain + F_VX) * pl);
+      vxaL = ld4s(sq + (ain + F_VX) * pl - P);
+      bybL = ld4(mq + 4 * pl - P);
     }
     mbar_wait(&full[stage], phase);
 
@@ -231,6 +238,32 @@ rev_image_kernel(const __grid_constant__ BwdArgs a, int tz_first, int tx_first, 
         gb.v[kk] = (vxa.v[kk] * eb[kk]) * (half_rdt * bybdt.v[kk] * bybdt.v[kk]);
       }
     }
+    // g_a of the cell right above the quad: from the thread above in the same half-warp (all 32 lanes take part)
+    const float ga_up = __shfl_up_sync(0xffffffffu, ga.v[3], 1, 16);
+    const bool wr = owner && in_rect;
+    const bool colrho = gx >= g.xlo && gx <= g.xhi + 1;   // the x+1 spray also lands in column xhi + 1
+    const bool rowbox = gz + 3 >= g.zlo && gz <= g.zhi;
+    F4 grho = zero4();   // this step's density term of the quad, gathered
+    if (wr && rowbox && colrho) {
+      // g_b of column x-1 (zero outside the box): D-z(sxz) + D+x(sxx) one column to the left
+      float ebL[4] = {0.f, 0.f, 0.f, 0.f};
+      if (gx - 1 >= g.xlo && gx - 1 <= g.xhi) {
+        float d1[4], d2[4];
+        const float *xzL = xz - VPITCH;
+        dz_minus4(ld4(xzL - 4), ld4(xzL), ld4(xzL + 4), kz1, kz2, d1);
+        dx4(ld4(xx - 2 * VPITCH), ld4(xx - VPITCH), sxxB, ld4(xx + VPITCH), kx1, kx2, d2);
+#pragma unroll
+        for (int kk = 0; kk < 4; kk++) ebL[kk] = d1[kk] + d2[kk];
+      }
+#pragma unroll
+      for (int kk = 0; kk < 4; kk++) {
+        const bool rowin = (unsigned)(gz + kk - g.zlo) <= (unsigned)(g.zhi - g.zlo);
+        const float gbl = (vxaL.v[kk] * ebL[kk]) * (half_rdt * bybL.v[kk] * bybL.v[kk]);
+        const float up = kk == 0 ? ga_up : ga.v[kk - 1];
+        // rows outside the box receive nothing; g_a / g_b are zero outside it, and the z+1 spray stops at zhi (el_velocity.cu:107)
+        grho.v[kk] = rowin ? (ga.v[kk] + gb.v[kk]) + (up + gbl) : 0.0f;
+      }
+    }
     if (fq >= 0) {  // exact values of time `it` on the ring: already in the shared tile
       cp_async_wait_all();
       vz = ld4(s_v + sj);
@@ -240,18 +273,17 @@ rev_image_kernel(const __grid_constant__ BwdArgs a, int tz_first, int tx_first, 
       st4(s_v + SCOLS * SPITCH + sj, vx);
     }
     float *fo = sq + fout * pl;
-    const bool wr = owner && in_rect;
     if (wr) {
       st4(fo + F_VZ * pl, vz);
       st4(fo + F_VX * pl, vx);
     }
     // global operands of the stress half, requested before the barrier
-    F4 ldt, l2mdt, amudt, za, xa, xza, gl, gm, gs, accA, accB;
+    F4 ldt, l2mdt, amudt, za, xa, xza, gl, gm, gs, gd;
     if (wr) {
       ldt = ld4(mq); l2mdt = ld4(mq + pl); amudt = ld4(mq + 2 * pl);
       za = ld4s(sq + (ain + F_SZZ) * pl); xa = ld4s(sq + (ain + F_SXX) * pl); xza = ld4s(sq + (ain + F_SXZ) * pl);
       gl = ld4s(acc + G_LAM * pl); gm = ld4s(acc + G_MU * pl); gs = ld4s(acc + G_MUS * pl);
-      accA = ld4s(acc + G_RHO_A * pl); accB = ld4s(acc + G_RHO_B * pl);
+      if (rowbox && colrho) gd = ld4s(acc + G_RHO * pl);
     }
     __syncthreads();  // s_v is complete; nobody reads ring slot `stage` any more
     if (tid == PRODUCER_TID && item + NS * stride < nitems) produce(item + NS * stride, stage, ds == 0 ? NS : ds - 1);
@@ -297,16 +329,14 @@ rev_image_kernel(const __grid_constant__ BwdArgs a, int tz_first, int tx_first, 
             gs.v[kk] += -xza.v[kk] * e * (q_rdt * amudt.v[kk] * amudt.v[kk]);
           }
         }
-#pragma unroll
-        for (int kk = 0; kk < 4; kk++) {
-          accA.v[kk] += ga.v[kk];
-          accB.v[kk] += gb.v[kk];
-        }
         st4(acc + G_LAM * pl, gl);
         st4(acc + G_MU * pl, gm);
         st4(acc + G_MUS * pl, gs);
-        st4(acc + G_RHO_A * pl, accA);
-        st4(acc + G_RHO_B * pl, accB);
+      }
+      if (rowbox && colrho) {
+#pragma unroll
+        for (int kk = 0; kk < 4; kk++) gd.v[kk] += grho.v[kk];
+        st4(acc + G_RHO * pl, gd);
       }
       if (fq >= 0) {  // to_bnd(sigma) (libCUFD.cu:403)
         szz = ld4(my_frm);
@@ -1266,7 +1296,7 @@ __global__ void __launch_bounds__(NCOMPUTE, 1) bwd_step_kernel(const __grid_cons
       const bool rowbox = gz + 3 >= g.zlo && gz <= g.zhi;
       if (wr && rowbox) {
         if (colbox) { gl = ld4s(acc + G_LAM * pl); gm = ld4s(acc + G_MU * pl); gs = ld4s(acc + G_MUS * pl); }
-        if (colrho) gd = ld4s(acc + G_RHO_A * pl);
+        if (colrho) gd = ld4s(acc + G_RHO * pl);
       }
       __syncthreads();  // s_vr / s_gb are complete; nobody reads ring slot `stage` any more
       if (tid == PRODUCER_TID) produce_next(stage, ds == 0 ? MNS : ds - 1, false);
@@ -1283,7 +1313,7 @@ __global__ void __launch_bounds__(NCOMPUTE, 1) bwd_step_kernel(const __grid_cons
             const bool rowin = (unsigned)(gz + kk - g.zlo) <= (unsigned)(g.zhi - g.zlo);
             gd.v[kk] += rowin ? (ga.v[kk] + gb.v[kk]) + (up + gbl.v[kk]) : 0.0f;
           }
-          st4(acc + G_RHO_A * pl, gd);
+          st4(acc + G_RHO * pl, gd);
         }
         if (rowbox && colbox) {
           const float *pz = s_vr + sj;

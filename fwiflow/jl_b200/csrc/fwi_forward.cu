@@ -443,7 +443,6 @@ void encode_tma_maps(const Grid &g, float *state, long long nplanes, float *gacc
   encode_one(&out->s3, g, state, nplanes, TILE_Z + 16, TILE_X + 6, 3);
   encode_one(&out->o5, g, state, nplanes, TILE_Z, TILE_X, 5);
   encode_one(&out->r1, g, state, nplanes, SPITCH, SCOLS, 1);
-  if (gacc) encode_one(&out->g5, g, gacc, gacc_planes, TILE_Z, TILE_X, 5);
   if (gacc) encode_one(&out->g4, g, gacc, gacc_planes, TILE_Z, TILE_X, 4);
   encode_one(&out->m5, g, model, M_COUNT, SPITCH, SCOLS, 5);
 }

@@ -201,10 +201,10 @@ __global__ void traces_to_rt_kernel(const float *tr, float *rt, int nrec, int nr
 }
 
 // result planes are row-major [z][x] (libCUFD.cu:480-486).  Sums the per-slot accumulators in slot order and
-// applies the reference's 4-point spray of the mu / rho imaging terms as a gather (el_stress.cu:113-124,
-// el_velocity.cu:105-110, incl. the always-true x+1 guard that lands in column xhi+1).
+// applies the reference's 4-point spray of the mu imaging term as a gather (el_stress.cu:113-124, incl. the always-true
+// x+1 guard that lands in column xhi+1); the density spray (el_velocity.cu:105-110) is gathered by the reverse kernel.
 __global__ void finalize_kernel(Grid g, const float *gacc, int nslots, const float *mu, const float *misfit_half,
-                                float *result, bool rho_gathered) {
+                                float *result) {
   __shared__ float t[3][32][33];
   const int zb = blockIdx.x * 32, xb = blockIdx.y * 32;
   auto S = [&](int which, int z, int x) -> float {
@@ -225,8 +225,7 @@ __global__ void finalize_kernel(Grid g, const float *gacc, int nslots, const flo
         const float m = mu[(long long)x * g.P + z];
         gm += G / (m * m);
       }
-      gd = rho_gathered ? S(G_RHO_A, z, x)
-                        : S(G_RHO_A, z, x) + S(G_RHO_B, z, x) + S(G_RHO_A, z - 1, x) + S(G_RHO_B, z, x - 1);
+      gd = S(G_RHO, z, x);   // the density spray is gathered per time step by the reverse kernel
     }
     t[0][r][threadIdx.x] = gl;
     t[1][r][threadIdx.x] = gm;
@@ -297,10 +296,10 @@ void launch_traces_to_rt(const float *tr, float *rt, int nrec, int nrp, int nSte
 }
 
 void launch_finalize(const Grid &g, const float *gacc, int nslots, const float *mu, const float *misfit_half,
-                     float *result, bool rho_gathered, cudaStream_t s) {
+                     float *result, cudaStream_t s) {
   dim3 tb(32, 8);
   dim3 tg((g.nz + 31) / 32, (g.nx + 31) / 32);
-  finalize_kernel<<<tg, tb, 0, s>>>(g, gacc, nslots, mu, misfit_half, result, rho_gathered);
+  finalize_kernel<<<tg, tb, 0, s>>>(g, gacc, nslots, mu, misfit_half, result);
 }
 
 }  // namespace fwi

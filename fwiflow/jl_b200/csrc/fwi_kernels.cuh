@@ -34,8 +34,9 @@ enum Slot : int {
   S_PHI_B = 32,
   S_COUNT = 36
 };
-// gradient accumulator planes (per concurrent shot)
-enum Grad : int { G_LAM = 0, G_MU = 1, G_MUS = 2, G_RHO_A = 3, G_RHO_B = 4, G_COUNT = 5 };
+// gradient accumulator planes (per concurrent shot): lambda, mu (direct term), mu (spray amplitude, gathered by
+// finalize_kernel), rho (spray gathered in the reverse kernel)
+enum Grad : int { G_LAM = 0, G_MU = 1, G_MUS = 2, G_RHO = 3, G_COUNT = 4 };
 enum Field : int { F_VZ = 0, F_VX = 1, F_SZZ = 2, F_SXX = 3, F_SXZ = 4 };
 enum Psi : int { PSI_VZ_Z = 0, PSI_VX_X = 1, PSI_VX_Z = 2, PSI_VZ_X = 3 };
 enum Phi : int { PHI_SZZ_Z = 0, PHI_SXZ_X = 1, PHI_SXZ_Z = 2, PHI_SXX_X = 3 };
@@ -89,8 +90,7 @@ struct alignas(64) TmaMaps {
   // L2 prefetch boxes (cp.async.bulk.prefetch.tensor): operands the threads read with direct loads
   CUtensorMap o5;   // state planes, box (TILE_Z, TILE_X, 5): the five adjoint fields of the owner tile (reverse step)
   CUtensorMap r1;   // state planes, box (TILE_Z+8, TILE_X+4, 1): one CPML memory plane of the tile region
-  CUtensorMap g5;   // imaging accumulators [batch][G_COUNT][plane], box (TILE_Z, TILE_X, 5)
-  CUtensorMap g4;   // the same, box (TILE_Z, TILE_X, 4): the merged backward kernel gathers the density spray itself
+  CUtensorMap g4;   // imaging accumulators [batch][G_COUNT][plane], box (TILE_Z, TILE_X, 4)
   CUtensorMap m5;   // model planes, box (TILE_Z+8, TILE_X+4, 5): the five dt-scaled coefficient planes of the tile region
 };
 
@@ -151,7 +151,7 @@ void launch_reverse_imaging(const BwdArgs &a, cudaStream_t s);
 // adjoint step: source_grad, adjoint velocity, residual injection, adjoint stress
 void launch_adjoint_step(const BwdArgs &a, cudaStream_t s);
 // merged backward launch: adjoint step of time index a.it + 1 (adjoint buffer cur_a -> the other), then reverse step
-// a.it + 1 -> a.it with imaging (forward buffer cur_f -> the other); the density accumulator G_RHO_A is final (gathered)
+// a.it + 1 -> a.it with imaging (forward buffer cur_f -> the other); same accumulators as the two-launch form
 void launch_backward_merged(const BwdArgs &a, cudaStream_t s);
 
 // model preparation: double row-major MPa -> float planes (Pa), derived coefficients, max cp
@@ -181,9 +181,8 @@ void launch_misfit(const float *j_shot, int n, float *misfit_half, cudaStream_t 
 void launch_traces_to_rt(const float *tr, float *rt, int nrec, int nrp, int nSteps, cudaStream_t s);
 
 // result = [gl|gm|gd|misfit] row-major [z][x] float: sums the per-slot accumulators
-// rho_gathered: G_RHO_A already holds the gathered density gradient (merged backward kernel)
 void launch_finalize(const Grid &g, const float *gacc, int nslots, const float *mu, const float *misfit_half,
-                     float *result, bool rho_gathered, cudaStream_t s);
+                     float *result, cudaStream_t s);
 
 // host: encode the TMA descriptors for a state buffer of `nplanes` planes and the model buffer
 // `gacc` may be null (no gradient): its descriptor is then left untouched

@@ -84,7 +84,6 @@ struct fwi_b200_plan {
   std::vector<char> obs_set;
   int last_calc = -1;
   int cur_f_last = 0;  // forward-field buffer holding the newest state of the last batch
-  bool rho_gathered = false;  // the last backward loop ran the merged kernel: G_RHO_A holds the gathered density gradient
 
   // device memory
   DevBuf<float> model;        // lam mu den amu bya byb planes
@@ -592,14 +591,13 @@ void run_locked(fwi_b200_plan &pl, int calc_id, cudaStream_t s) {
       }
     }
     pl.cur_f_last = cur_f;
-    pl.rho_gathered = g_merged_bwd.load(std::memory_order_relaxed) != 0;
   }
   if (if_res) {
     launch_misfit(pl.j_shot.p, pl.group, pl.misfit_half.p, s);
     pl.launches++;
   }
   if (with_adj) {
-    launch_finalize(g, pl.gacc.p, std::min(pl.batch, pl.group), m.mu, pl.misfit_half.p, pl.result.p, pl.rho_gathered, s);
+    launch_finalize(g, pl.gacc.p, std::min(pl.batch, pl.group), m.mu, pl.misfit_half.p, pl.result.p, s);
     pl.launches++;
   } else if (if_res) {
     CUDA_OK(cudaMemcpyAsync(pl.result.p + 3LL * g.nz * g.nx, pl.misfit_half.p, sizeof(float), cudaMemcpyDeviceToDevice, s));

@@ -1,8 +1,8 @@
 set -x
-mkdir -p gpurun_out/r2m
-( time python -c "import __graft_entry__ as g; g.build(); g.smoke()" ) > gpurun_out/r2m/smoke.log 2>&1; tail -4 gpurun_out/r2m/smoke.log
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r2m/tests.log 2>&1; tail -4 gpurun_out/r2m/tests.log
-python scripts/c1_times.py > gpurun_out/r2m/c1.json 2> gpurun_out/r2m/c1.err; cat gpurun_out/r2m/c1.json
-( time python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 ) > gpurun_out/r2m/bench_ref.json 2> gpurun_out/r2m/bench_ref.err
-( time python bench.py --gpus 1 --steps 20 --warmup 5 ) > gpurun_out/r2m/bench.json 2> gpurun_out/r2m/bench.err
-grep real gpurun_out/r2m/*.err; cut -c1-260 gpurun_out/r2m/bench.json gpurun_out/r2m/bench_ref.json
+mkdir -p gpurun_out/r2n
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r2n/tests.log 2>&1; tail -6 gpurun_out/r2n/tests.log
+timeout 300 python scripts/kernel_times.py c2 30 200 > gpurun_out/r2n/kt_c2.log 2>&1; grep -v "^obs\|^grad" gpurun_out/r2n/kt_c2.log
+timeout 300 python scripts/kernel_times.py c3 8 50 > gpurun_out/r2n/kt_c3.log 2>&1; grep -v "^obs\|^grad" gpurun_out/r2n/kt_c3.log
+timeout 300 python scripts/run_config.py c2 30 2000 >> gpurun_out/r2n/cfg.json 2>> gpurun_out/r2n/cfg.err
+timeout 600 python scripts/run_config.py c3 25 4000 >> gpurun_out/r2n/cfg.json 2>> gpurun_out/r2n/cfg.err
+cat gpurun_out/r2n/cfg.json; tail -3 gpurun_out/r2n/cfg.err
