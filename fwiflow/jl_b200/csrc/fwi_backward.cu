@@ -4,9 +4,10 @@
 //   replaces el_velocity(isFor=false) / to_bnd x2 / add_source(isFor=false) / el_stress(isFor=false) / to_bnd x3
 //   (reference: deps/CustomOps/FWI/Src/libCUFD.cu:380-403, el_velocity.cu:84-117, el_stress.cu:90-131,
 //    utilities.cu:394-424,538-551)
-//   The imaging condition only ACCUMULATES per-cell source terms (5 planes per concurrent shot: lambda, mu-direct,
-//   mu-spray amplitude S, rho-a, rho-b); the reference's 4-point atomic "spray" (el_stress.cu:113-124,
-//   el_velocity.cu:101-110) is linear in those and is applied once, as a deterministic gather, by finalize_kernel.
+//   The imaging condition accumulates four per-cell planes per concurrent shot: lambda, mu-direct, mu-spray amplitude S
+//   and rho.  The reference's 4-point atomic "sprays" (el_stress.cu:113-124, el_velocity.cu:101-110) are linear in
+//   per-cell amplitudes and are applied as deterministic gathers: the density one here, per time step (shuffle for the
+//   row above, the left column evaluated in place), the mu one once per gradient by finalize_kernel.
 //
 // One CTA of 16 warps per SM loops over (shot, tile) items of the tile range that covers the inner box + frame ring.
 // The producer lane streams, two items ahead, the stress triple of time it+1 with halo 8 / 4 (72 x 36) and the
