@@ -21,7 +21,7 @@ from . import ops
 from .utils import (moduli_to_velocity_grads, paraGen, surveyGen, symmetric_pad, velocity_to_moduli)
 
 __all__ = ["FWI", "FWIExample", "compute_observation", "compute_misfit", "compute_misfit_and_gradient", "padding",
-           "try_pad", "timelapse_misfit_and_gradients"]
+           "try_pad", "timelapse_misfit_and_gradients", "timelapse_misfit_and_gradients_batched"]
 
 
 @dataclass
@@ -200,4 +200,31 @@ def timelapse_misfit_and_gradients(surveys, stf_array, shot_ids=None, gpu_ids=(0
         t.join()
     if errs:
         raise errs[0]
+    return float(sum(o[0] for o in out)), out
+
+
+def timelapse_misfit_and_gradients_batched(surveys, stf_array, shot_ids=None, gpu_ids=(0,), is_masked=False, cp_ref=None,
+                                           cs_ref=None, rho_ref=None):
+    """The same evaluation through ONE C-ABI call (fwi_b200_timelapse): the mask blend and the velocity -> moduli map
+    run here, all surveys go down together (survey i on gpu_ids[i % len(gpu_ids)], one host thread per device inside
+    the library, plans and observations resident between calls), and the chain rule back to (cp, cs, rho) is applied to
+    what comes back.  Same return value as timelapse_misfit_and_gradients."""
+    items, models = [], []
+    for fwi, cp, cs, rho in surveys:
+        cp_m, cs_m, rho_m = _masked_models(fwi, cp, cs, rho, is_masked, cp_ref, cs_ref, rho_ref)
+        lam, mu = velocity_to_moduli(cp_m, cs_m, rho_m)
+        items.append((fwi.para_path, lam, mu, rho_m))
+        models.append((fwi, cp_m, cs_m, rho_m))
+    fwi0 = surveys[0][0]
+    stf = _stf_rows(fwi0, stf_array)
+    if shot_ids is None:
+        shot_ids = np.arange(1, len(fwi0.ind_src_x) + 1)
+    ids0 = np.asarray(shot_ids, dtype=np.int32) - 1
+    res = ops.timelapse(items, stf, list(gpu_ids), ids0)
+    out = []
+    for (fwi, cp_m, cs_m, rho_m), (j, gl, gm, gd) in zip(models, res):
+        g_cp, g_cs, g_rho = moduli_to_velocity_grads(cp_m, cs_m, rho_m, gl, gm, gd)
+        if not is_masked:
+            g_cp, g_cs, g_rho = g_cp * fwi.mask, g_cs * fwi.mask, g_rho * fwi.mask
+        out.append((j, g_cp, g_cs, g_rho))
     return float(sum(o[0] for o in out)), out

@@ -245,6 +245,14 @@ def test_c4_timelapse_six_surveys(ops):
     for k in (1, 5):
         j, g_cp, g_cs, g_rho = compute_misfit_and_gradient(trial[k][0], cp0, cs0, rho0, stf, is_masked=True)
         assert j == pytest.approx(js[k], rel=1e-6) and rel(g_cp, per[k][1]) <= 1e-6 and rel(g_rho, per[k][3]) <= 1e-6
+    # ... and exactly what ONE C-ABI call for all six surveys returns (fwi_b200_timelapse)
+    from fwiflow.jl_b200.fwi import timelapse_misfit_and_gradients_batched
+    total_c, per_c = timelapse_misfit_and_gradients_batched(trial, stf, is_masked=True)
+    assert total_c == pytest.approx(total, rel=1e-9)
+    for k in range(6):
+        assert per_c[k][0] == pytest.approx(per[k][0], rel=1e-6, abs=0.0)
+        for i in (1, 2, 3):
+            assert rel(per_c[k][i], per[k][i]) <= 1e-6, (k, i)
     # zero residual -> zero gradient for the baseline; the monitors' gradients are finite and grow with the anomaly
     assert all(np.all(g == 0) for g in per[0][1:])
     e = [float(np.linalg.norm(per[k][1])) for k in range(6)]
