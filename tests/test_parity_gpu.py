@@ -515,7 +515,13 @@ def test_thin_boundary_frames(ops):
     like every other box cell.  Same gradients up to the rounding of the reconstruction (<= 2e-5), less than half the
     frame bytes -- on grids with nPml = 32 / 20, nPad = 0, ring rows that do and do not fill a quad."""
     from fwiflow.jl_b200 import synthetic
-    cases = [CASES["small_elastic"], CASES["aniso"], CASES["gradtest"], synthetic.case_c2(nshots=2, nSteps=800)]
+    # nPml = 30 / 13: the two ring rows straddle a quad boundary at the top (rows 28, 29 | 11, 12) and, with these
+    # heights, at the bottom as well -- the 1-or-2-quads-per-column bookkeeping of frame_quad()
+    odd = [synthetic.make_layered_case("odd30", 61, 83, 20.0, 0.002, 500, 6.0, nlayers=4, nshots=2, smooth_sigma=4.0,
+                                       nPml=30, vmax=3500.0),
+           synthetic.make_layered_case("odd13", 47, 58, 20.0, 0.002, 400, 6.0, nlayers=3, nshots=1, smooth_sigma=4.0,
+                                       nPml=13, vmax=3500.0)]
+    cases = [CASES["small_elastic"], CASES["aniso"], CASES["gradtest"], synthetic.case_c2(nshots=2, nSteps=800)] + odd
     try:
         for c in cases:
             para = c.write_files(tempfile.mkdtemp(prefix="ring_"))
@@ -528,10 +534,17 @@ def test_thin_boundary_frames(ops):
                 ops.set_option("frame_ring", ring)
                 flen[ring] = ops.grid_info(para)["frame_len"]
                 out[ring] = ops.fwi_op_and_grad(lam0, mu0, rho0, c.stf, 0, ids, para)
-            assert flen[2] < 0.6 * flen[5]
+            assert flen[2] <= 0.8 * flen[5]      # 0.49x where the two ring rows share a quad, up to 0.8x where they straddle
             assert out[2][0] == out[5][0] > 0                                  # the misfit comes from the forward pass
             for k in (1, 2, 3):
                 assert np.abs(out[5][k]).max() > 0 and rel(out[2][k], out[5][k]) <= 2e-5, (c.name, k)
             assert np.array_equal(out[2][4], out[5][4]), c.name               # the adjoint field never sees the frames
+            if c in odd:   # and both are right: against the CPU oracle
+                from oracle import oracle_py as op
+                op.oracle_cufd(2, lam, mu, rho, c.stf, ids, para)
+                g_o = op.oracle_cufd(1, lam0, mu0, rho0, c.stf, ids, para)
+                inner = interior_mask(c)
+                for k, name in ((1, "grad_lambda"), (2, "grad_mu"), (3, "grad_den")):
+                    assert rel(out[2][k][inner], g_o[name][inner]) <= TOL_GRAD, (c.name, name)
     finally:
         ops.set_option("frame_ring", 2)      # the default
