@@ -496,8 +496,10 @@ __global__ void __launch_bounds__(NCOMPUTE, 1) adj_step_kernel(const __grid_cons
     const bool actq = gx >= 2 && gx <= g.ax_hi && gz + 3 >= 2 && gz <= g.az_hi;
     const F4 ldt = ld4(mq), l2mdt = ld4(mq + pl), amudt = ld4(mq + 2 * pl);
     const F4 byadt = ld4(mq + 3 * pl), bybdt = ld4(mq + 4 * pl);
-    const bool near_src = FWI_F64_UPDATE > 1 && abs(gx - d.sx) <= FWI_F64_UPDATE && gz + 3 >= d.sz - FWI_F64_UPDATE &&
-                          gz <= d.sz + FWI_F64_UPDATE;   // see fwd_step_kernel
+    // double increments next to the source in the ADJOINT kernels too (FWI_F64_ADJ): off -- measured to make no
+    // difference to grad_stf, which is decided by the forward arithmetic (profiles/r2_parity.md)
+    const bool near_src = FWI_F64_ADJ && FWI_F64_UPDATE > 1 && abs(gx - d.sx) <= FWI_F64_UPDATE &&
+                          gz + 3 >= d.sz - FWI_F64_UPDATE && gz <= d.sz + FWI_F64_UPDATE;
     mbar_wait(&full[stage], phase);
 
     const unsigned char *sb = base + stage * ASTAGE_BYTES;
@@ -548,7 +550,7 @@ __global__ void __launch_bounds__(NCOMPUTE, 1) adj_step_kernel(const __grid_cons
 #pragma unroll
       for (int kk = 0; kk < 4; kk++) {  // coefficients carry dt and are 0 on inactive cells
         // el_velocity_adj.cu:69-71,90-92: the (lambda + 2.0 mu) term promotes the sum to double
-        if (FWI_F64_UPDATE == 1 || (FWI_F64_UPDATE > 1 && near_src)) {
+        if (FWI_F64_UPDATE == 1 || (FWI_F64_ADJ && FWI_F64_UPDATE > 1 && near_src)) {
           vx.v[kk] = (float)((double)vx.v[kk] + ((double)ldt.v[kk] * (double)dszz_dx[kk] + (double)l2mdt.v[kk] * (double)dsxx_dx[kk] +
                                                  (double)amudt.v[kk] * (double)dsxz_dz[kk]));
           vz.v[kk] = (float)((double)vz.v[kk] + ((double)l2mdt.v[kk] * (double)dszz_dz[kk] + (double)ldt.v[kk] * (double)dsxx_dz[kk] +
@@ -602,7 +604,7 @@ __global__ void __launch_bounds__(NCOMPUTE, 1) adj_step_kernel(const __grid_cons
         for (int kk = 0; kk < 4; kk++) {
           const int z = gz + kk;
           if (z >= 2 && z <= g.az_hi) {
-            if (FWI_F64_UPDATE == 1 || (FWI_F64_UPDATE > 1 && near_src)) {
+            if (FWI_F64_UPDATE == 1 || (FWI_F64_ADJ && FWI_F64_UPDATE > 1 && near_src)) {
             vx.v[kk] = (float)((double)vx.v[kk] + ((double)tpx1[kk] + (double)(ldt.v[kk] * dszz_dx[kk] * rKx) +
                                                    (double)l2mdt.v[kk] * (double)(dsxx_dx[kk] * rKx) + (double)tpx2[kk] +
                                                    (double)(amudt.v[kk] * rKzh.v[kk] * dsxz_dz[kk])));
@@ -945,8 +947,10 @@ __global__ void __launch_bounds__(NCOMPUTE, 1) bwd_step_kernel(const __grid_cons
     const bool actq = gx >= 2 && gx <= g.ax_hi && gz + 3 >= 2 && gz <= g.az_hi;
     const F4 ldt = ld4(mq), l2mdt = ld4(mq + pl), amudt = ld4(mq + 2 * pl);
     const F4 byadt = ld4(mq + 3 * pl), bybdt = ld4(mq + 4 * pl);
-    const bool near_src = FWI_F64_UPDATE > 1 && abs(gx - d.sx) <= FWI_F64_UPDATE && gz + 3 >= d.sz - FWI_F64_UPDATE &&
-                          gz <= d.sz + FWI_F64_UPDATE;   // see fwd_step_kernel
+    // double increments next to the source in the ADJOINT kernels too (FWI_F64_ADJ): off -- measured to make no
+    // difference to grad_stf, which is decided by the forward arithmetic (profiles/r2_parity.md)
+    const bool near_src = FWI_F64_ADJ && FWI_F64_UPDATE > 1 && abs(gx - d.sx) <= FWI_F64_UPDATE &&
+                          gz + 3 >= d.sz - FWI_F64_UPDATE && gz <= d.sz + FWI_F64_UPDATE;
     mbar_wait(&full[stage], phase);
 
     F4 vz, vx;          // adjoint velocities of the quad: pre-update, then new
@@ -996,7 +1000,7 @@ __global__ void __launch_bounds__(NCOMPUTE, 1) bwd_step_kernel(const __grid_cons
 #pragma unroll
         for (int kk = 0; kk < 4; kk++) {  // coefficients carry dt and are 0 on inactive cells
           // el_velocity_adj.cu:69-71,90-92: the (lambda + 2.0 mu) term promotes the sum to double
-          if (FWI_F64_UPDATE == 1 || (FWI_F64_UPDATE > 1 && near_src)) {
+          if (FWI_F64_UPDATE == 1 || (FWI_F64_ADJ && FWI_F64_UPDATE > 1 && near_src)) {
             vx.v[kk] = (float)((double)vx.v[kk] + ((double)ldt.v[kk] * (double)dszz_dx[kk] + (double)l2mdt.v[kk] * (double)dsxx_dx[kk] +
                                                    (double)amudt.v[kk] * (double)dsxz_dz[kk]));
             vz.v[kk] = (float)((double)vz.v[kk] + ((double)l2mdt.v[kk] * (double)dszz_dz[kk] + (double)ldt.v[kk] * (double)dsxx_dz[kk] +
@@ -1050,7 +1054,7 @@ __global__ void __launch_bounds__(NCOMPUTE, 1) bwd_step_kernel(const __grid_cons
           for (int kk = 0; kk < 4; kk++) {
             const int z = gz + kk;
             if (z >= 2 && z <= g.az_hi) {
-              if (FWI_F64_UPDATE == 1 || (FWI_F64_UPDATE > 1 && near_src)) {
+              if (FWI_F64_UPDATE == 1 || (FWI_F64_ADJ && FWI_F64_UPDATE > 1 && near_src)) {
                 vx.v[kk] = (float)((double)vx.v[kk] + ((double)tpx1[kk] + (double)(ldt.v[kk] * dszz_dx[kk] * rKx) +
                                                        (double)l2mdt.v[kk] * (double)(dsxx_dx[kk] * rKx) + (double)tpx2[kk] +
                                                        (double)(amudt.v[kk] * rKzh.v[kk] * dsxz_dz[kk])));

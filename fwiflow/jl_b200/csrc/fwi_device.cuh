@@ -20,8 +20,14 @@
 #endif
 
 #ifndef FWI_F64_UPDATE
-#define FWI_F64_UPDATE 8   // 0: float increments everywhere; 1: stress / adjoint-velocity increments summed in double everywhere (one rounding per
-                           // update, like the reference's (lambda + 2.0 mu) expressions); R > 1: only for quads within R cells of the shot's source
+#define FWI_F64_UPDATE 8   // 0: float increments everywhere; 1: stress / adjoint-velocity increments summed in double everywhere (one rounding
+                           // per update, like the reference's (lambda + 2.0 mu) expressions); R > 1: only in the forward kernel and only for
+                           // quads within R cells of the shot's source.  (Measured and dropped: the reference's arithmetic to the letter for
+                           // those quads -- IEEE division by dz, unscaled coefficients: C2 grad_stf 1.0e-3 -> 4.9e-4, forward kernel +34 %.)
+#endif
+
+#ifndef FWI_F64_ADJ
+#define FWI_F64_ADJ 0
 #endif
 
 namespace fwi {

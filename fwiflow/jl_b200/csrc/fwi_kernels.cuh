@@ -58,6 +58,7 @@ struct Grid {
                            // the top absorbing layer (+ its 2-cell fringe + the 4-row halo): the tile rows between the
                            // layers then carry no CPML code at all (C2: 2 of 4 tile rows instead of 1 of 4)
   float dt, rdz, rdx;      // 1/dz, 1/dx
+  float dz, dx;            // the spacings themselves
   // boundary frames
   // boundary frames, stored at float4-quad granularity (every quad that intersects the 5-cell ring)
   int f_in;            // ring cells kept INSIDE the box on each side: 3 = the reference's 5-deep ring (Boundary.cu:17-27),

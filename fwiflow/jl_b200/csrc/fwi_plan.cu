@@ -208,6 +208,8 @@ void build_grid(const Para &p, Grid &g) {
   g.dt = p.dt;
   g.rdz = (float)(1.0 / (double)p.dz);
   g.rdx = (float)(1.0 / (double)p.dx);
+  g.dz = p.dz;
+  g.dx = p.dx;
   // frames: left/right bands = 10 columns x the quads covering rows zlo-2 .. zhi+2; top/bottom bands = 2 quads each
   // for the columns in between (5 consecutive rows always span exactly two aligned quads)
   if (g.zhi - g.zlo + 1 < 8 || g.xhi - g.xlo + 1 < 8)
