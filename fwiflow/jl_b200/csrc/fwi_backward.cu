@@ -75,7 +75,7 @@ constexpr size_t REV_SMEM = rev_smem<false>();
 static_assert(RW_BYTES % 128 == 0 && RV_BYTES % 128 == 0, "TMA destination alignment");
 
 template <bool LEAN>
-__global__ void __launch_bounds__(NCOMPUTE, 1)
+__global__ void __launch_bounds__(NCOMPUTE, CTAS_PER_SM)
 rev_image_kernel(const __grid_constant__ BwdArgs a, int tz_first, int tx_first, int ntz, int ntiles) {
   constexpr int NSV = LEAN ? 1 : 2;
   constexpr int NFRM = LEAN ? NOWN : NCOMPUTE;
@@ -383,7 +383,7 @@ constexpr size_t ADJ_SMEM =
     (size_t)ANS * ASTAGE_BYTES + 2 * AV_BYTES + ANB * (APHI_BYTES + AINJ_BYTES) + (ANS + 1) * sizeof(TileDesc) + (ANS + 1) * 8 + 128;
 static_assert(AV_BYTES % 128 == 0, "TMA destination alignment");
 
-__global__ void __launch_bounds__(NCOMPUTE, 1) adj_step_kernel(const __grid_constant__ BwdArgs a) {
+__global__ void __launch_bounds__(NCOMPUTE, CTAS_PER_SM) adj_step_kernel(const __grid_constant__ BwdArgs a) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char *base = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
   float *s_v_base = reinterpret_cast<float *>(base + ANS * ASTAGE_BYTES);                         // [2][2][SCOLS][SPITCH]
@@ -802,7 +802,7 @@ constexpr size_t MRG_SMEM = (size_t)MNS * MSTAGE_BYTES + AV_BYTES + APHI_BYTES +
 static_assert(MSTAGE_BYTES % 128 == 0, "TMA destination alignment");
 enum : int { TF_REV = 8 };   // phase-A descriptor: the tile has a phase R
 
-__global__ void __launch_bounds__(NCOMPUTE, 1) bwd_step_kernel(const __grid_constant__ BwdArgs a) {
+__global__ void __launch_bounds__(NCOMPUTE, CTAS_PER_SM) bwd_step_kernel(const __grid_constant__ BwdArgs a) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char *base = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
   unsigned char *hp = base + MNS * MSTAGE_BYTES;
@@ -1393,7 +1393,7 @@ void launch_backward_merged(const BwdArgs &a_in, cudaStream_t s) {
   BwdArgs a = a_in;
   a.order = FWI_ZIGZAG ? (a.it & 1) : 0;
   const int nitems = a.batch * a.g.tiles_z * a.g.tiles_x;
-  const int blocks = nitems < sm_count() ? nitems : sm_count();
+  const int blocks = nitems < sm_count() * CTAS_PER_SM ? nitems : sm_count() * CTAS_PER_SM;
   launch_step(bwd_step_kernel, blocks, NCOMPUTE, MRG_SMEM, s, a);
 }
 
@@ -1410,7 +1410,7 @@ void launch_adjoint_step(const BwdArgs &a_in, cudaStream_t s) {
   BwdArgs a = a_in;
   a.order = 0;
   const int nitems = a.batch * a.g.tiles_z * a.g.tiles_x;
-  const int blocks = nitems < sm_count() ? nitems : sm_count();
+  const int blocks = nitems < sm_count() * CTAS_PER_SM ? nitems : sm_count() * CTAS_PER_SM;
   launch_step(adj_step_kernel, blocks, NCOMPUTE, ADJ_SMEM, s, a);
 }
 
@@ -1422,7 +1422,7 @@ void launch_reverse_imaging(const BwdArgs &a_in, cudaStream_t s) {
   const int tx0 = max(g.xlo - 2, 0) / TILE_X, tx1 = min(g.xhi + 2, g.nx - 1) / TILE_X;
   const int ntz = tz1 - tz0 + 1, ntx = tx1 - tx0 + 1;
   const int nitems = a.batch * ntz * ntx;
-  const int blocks = nitems < sm_count() ? nitems : sm_count();
+  const int blocks = nitems < sm_count() * CTAS_PER_SM ? nitems : sm_count() * CTAS_PER_SM;
   // working set of one launch = forward + adjoint fields and accumulators of every box cell of the batch; beyond a few
   // L2 capacities the kernel is bound by its streams and wants the larger L1 (see rev_smem)
   const double working_set = 100.0 * a.batch * (double)(g.zhi - g.zlo + 1) * (g.xhi - g.xlo + 1);

@@ -61,7 +61,7 @@ constexpr size_t FWD_SMEM = (size_t)NS * STAGE_BYTES + NSNEW * SNEW_BYTES + (NS 
 static_assert(V_BYTES % 128 == 0 && S_BYTES % 128 == 0, "TMA destination alignment");
 
 template <bool SAVE>
-__global__ void __launch_bounds__(NTHREADS_FWD, 1) fwd_step_kernel(const __grid_constant__ FwdArgs a) {
+__global__ void __launch_bounds__(NTHREADS_FWD, CTAS_PER_SM) fwd_step_kernel(const __grid_constant__ FwdArgs a) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char *base = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
   float *s_new_base = reinterpret_cast<float *>(base + NS * STAGE_BYTES);                     // [2][3][SCOLS][SPITCH]
@@ -460,7 +460,7 @@ void launch_forward_step(const FwdArgs &a_in, bool save_frames, cudaStream_t s) 
   FwdArgs a = a_in;
   a.order = FWI_ZIGZAG ? (a.it & 1) : 0;
   const int nitems = a.batch * a.g.tiles_z * a.g.tiles_x;
-  const int blocks = nitems < sm_count() ? nitems : sm_count();
+  const int blocks = nitems < sm_count() * CTAS_PER_SM ? nitems : sm_count() * CTAS_PER_SM;
   if (save_frames)
     launch_step(fwd_step_kernel<true>, blocks, NTHREADS_FWD, FWD_SMEM, s, a);
   else

@@ -19,8 +19,15 @@ namespace fwi {
 constexpr int XM = 4;        // margin columns in x
 constexpr int SLACK = 256;   // floats before / after each plane
 constexpr int TILE_Z = 56;   // owner tile (z fastest): 14 float4 quads, 7 sectors of 32 B
-constexpr int TILE_X = 28;   // owner tile columns: stress region 32 columns, velocity-input region 34
-constexpr int NT_STEP = 512;      // persistent TMA-fed step kernels: 16 quads x 32 columns, one quad per thread
+#ifndef FWI_TILE_X
+#define FWI_TILE_X 28        // owner tile columns.  28: one 512-thread CTA per SM; 12: 256-thread CTAs, two per SM (FWI_CTAS_PER_SM = 2)
+#endif
+#ifndef FWI_CTAS_PER_SM
+#define FWI_CTAS_PER_SM 1
+#endif
+constexpr int TILE_X = FWI_TILE_X;   // owner tile columns: stress region TILE_X + 4 columns, velocity-input region TILE_X + 6
+constexpr int NT_STEP = 16 * (TILE_X + 4);   // persistent TMA-fed step kernels: 16 quads x (TILE_X + 4) columns, one quad per thread
+constexpr int CTAS_PER_SM = FWI_CTAS_PER_SM;
 
 // state slots
 enum Slot : int {
