@@ -44,6 +44,18 @@ __global__ void model_transpose_kernel(Grid g, const double *__restrict__ lam_in
   }
 }
 
+// the same for a caller whose (nz, nx) arrays are COLUMN-major (Julia): element (z, x) at x * nz + z is already the
+// device order, so there is nothing to transpose (the optional layout flag)
+__global__ void model_convert_cm_kernel(Grid g, const double *__restrict__ lam_in, const double *__restrict__ mu_in,
+                                        const double *__restrict__ den_in, float *model) {
+  const int z = blockIdx.x * blockDim.x + threadIdx.x, x = blockIdx.y;
+  if (z >= g.nz) return;
+  const long long k = (long long)x * g.nz + z, o = g.origin + (long long)x * g.P + z;
+  model[M_LAM * g.plane + o] = (float)(lam_in[k] * 1e6);
+  model[M_MU * g.plane + o] = (float)(mu_in[k] * 1e6);
+  model[M_DEN * g.plane + o] = (float)den_in[k];
+}
+
 // mu_bar, averaged buoyancies (utilities.cu:125-152, Model.cu:67-73), max cp (utilities.cu:109-123), and the
 // dt-scaled coefficient planes the step kernels read: lambda dt, (lambda + 2 mu) dt, mu_bar dt, byc_a dt, byc_b dt
 __global__ void model_derive_kernel(Grid g, float *model, unsigned int *cpmax_bits) {
@@ -204,7 +216,7 @@ __global__ void traces_to_rt_kernel(const float *tr, float *rt, int nrec, int nr
 // applies the reference's 4-point spray of the mu imaging term as a gather (el_stress.cu:113-124, incl. the always-true
 // x+1 guard that lands in column xhi+1); the density spray (el_velocity.cu:105-110) is gathered by the reverse kernel.
 __global__ void finalize_kernel(Grid g, const float *gacc, int nslots, const float *mu, const float *misfit_half,
-                                float *result) {
+                                float *result, int column_major) {
   __shared__ float t[3][32][33];
   const int zb = blockIdx.x * 32, xb = blockIdx.y * 32;
   auto S = [&](int which, int z, int x) -> float {
@@ -230,9 +242,13 @@ __global__ void finalize_kernel(Grid g, const float *gacc, int nslots, const flo
     t[0][r][threadIdx.x] = gl;
     t[1][r][threadIdx.x] = gm;
     t[2][r][threadIdx.x] = gd;
+    if (column_major && z < g.nz && x < g.nx) {   // the caller's order is the device order: no transpose
+      const long long n = (long long)g.nz * g.nx, k = (long long)x * g.nz + z;
+      result[k] = gl; result[n + k] = gm; result[2 * n + k] = gd;
+    }
   }
   __syncthreads();
-  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+  for (int r = threadIdx.y; r < 32 && !column_major; r += blockDim.y) {
     const int z = zb + r, x = xb + threadIdx.x;
     if (z < g.nz && x < g.nx)
       for (int k = 0; k < 3; k++) result[((long long)k * g.nz + z) * g.nx + x] = t[k][threadIdx.x][r];
@@ -265,10 +281,15 @@ void configure_kernels() {
 }
 
 void launch_model_prep(const Grid &g, const double *d_lam, const double *d_mu, const double *d_den, float *model,
-                       unsigned int *cpmax_bits, cudaStream_t s) {
-  dim3 tb(32, 8);
-  dim3 tg((g.nx + 31) / 32, (g.nz + 31) / 32);
-  model_transpose_kernel<<<tg, tb, 0, s>>>(g, d_lam, d_mu, d_den, model);
+                       unsigned int *cpmax_bits, int column_major, cudaStream_t s) {
+  if (column_major) {
+    dim3 cg((g.nz + 127) / 128, g.nx);
+    model_convert_cm_kernel<<<cg, 128, 0, s>>>(g, d_lam, d_mu, d_den, model);
+  } else {
+    dim3 tb(32, 8);
+    dim3 tg((g.nx + 31) / 32, (g.nz + 31) / 32);
+    model_transpose_kernel<<<tg, tb, 0, s>>>(g, d_lam, d_mu, d_den, model);
+  }
   dim3 dg((g.nz + 127) / 128, g.nx);
   model_derive_kernel<<<dg, 128, 0, s>>>(g, model, cpmax_bits);
 }
@@ -296,10 +317,10 @@ void launch_traces_to_rt(const float *tr, float *rt, int nrec, int nrp, int nSte
 }
 
 void launch_finalize(const Grid &g, const float *gacc, int nslots, const float *mu, const float *misfit_half,
-                     float *result, cudaStream_t s) {
+                     float *result, int column_major, cudaStream_t s) {
   dim3 tb(32, 8);
   dim3 tg((g.nz + 31) / 32, (g.nx + 31) / 32);
-  finalize_kernel<<<tg, tb, 0, s>>>(g, gacc, nslots, mu, misfit_half, result);
+  finalize_kernel<<<tg, tb, 0, s>>>(g, gacc, nslots, mu, misfit_half, result, column_major);
 }
 
 }  // namespace fwi

@@ -164,8 +164,9 @@ void launch_backward_merged(const BwdArgs &a, cudaStream_t s);
 
 // model preparation: double row-major MPa -> float planes (Pa), derived coefficients, max cp
 // `model` = base of the M_COUNT model planes
+// column_major: the caller's (nz, nx) arrays are column-major (z fastest, Julia) instead of row-major [z][x] (TF)
 void launch_model_prep(const Grid &g, const double *d_lam, const double *d_mu, const double *d_den, float *model,
-                       unsigned int *cpmax_bits, cudaStream_t s);
+                       unsigned int *cpmax_bits, int column_major, cudaStream_t s);
 
 // residual: taper obs & syn, res = obs - syn (t=0 -> 0), partial sums of res^2, taper res
 struct ResidualArgs {
@@ -190,7 +191,7 @@ void launch_traces_to_rt(const float *tr, float *rt, int nrec, int nrp, int nSte
 
 // result = [gl|gm|gd|misfit] row-major [z][x] float: sums the per-slot accumulators
 void launch_finalize(const Grid &g, const float *gacc, int nslots, const float *mu, const float *misfit_half,
-                     float *result, cudaStream_t s);
+                     float *result, int column_major, cudaStream_t s);
 
 // host: encode the TMA descriptors for a state buffer of `nplanes` planes and the model buffer
 // `gacc` may be null (no gradient): its descriptor is then left untouched

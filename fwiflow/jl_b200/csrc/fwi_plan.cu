@@ -79,6 +79,7 @@ struct fwi_b200_plan {
   std::mutex mu;  // one evaluation at a time per plan
   std::mutex call_mu;  // held by a host-buffer entry point for its whole set_model .. get_result sequence on a cached plan
   int max_batch_req = 0;  // the caller's max_batch (0 = from free memory); kept for re-planning after an eviction
+  int layout = 0;         // 0: the caller's (nz, nx) grids are row-major [z][x] (TensorFlow, the reference); 1: column-major (Julia)
   long long launches = 0;
   bool model_set = false, stf_set = false;
   std::vector<char> obs_set;
@@ -599,13 +600,17 @@ void run_locked(fwi_b200_plan &pl, int calc_id, cudaStream_t s) {
     pl.launches++;
   }
   if (with_adj) {
-    launch_finalize(g, pl.gacc.p, std::min(pl.batch, pl.group), m.mu, pl.misfit_half.p, pl.result.p, s);
+    launch_finalize(g, pl.gacc.p, std::min(pl.batch, pl.group), m.mu, pl.misfit_half.p, pl.result.p, pl.layout, s);
     pl.launches++;
   } else if (if_res) {
     CUDA_OK(cudaMemcpyAsync(pl.result.p + 3LL * g.nz * g.nx, pl.misfit_half.p, sizeof(float), cudaMemcpyDeviceToDevice, s));
   }
   CUDA_OK(cudaGetLastError());
   pl.last_calc = calc_id;
+}
+
+void check(int rc) {
+  if (rc != FWI_B200_OK) throw Error(rc, last_error_cstr());
 }
 
 template <typename F>
@@ -679,7 +684,7 @@ static void plan_set_model_impl(fwi_b200_plan *pl, const double *Lambda, const d
   CUDA_OK(cudaMemcpyAsync(pl->model_in.p + n, Mu, n * sizeof(double), cudaMemcpyHostToDevice, s));
   CUDA_OK(cudaMemcpyAsync(pl->model_in.p + 2 * n, Den, n * sizeof(double), cudaMemcpyHostToDevice, s));
   CUDA_OK(cudaMemsetAsync(pl->cpmax.p, 0, sizeof(unsigned int), s));
-  launch_model_prep(g, pl->model_in.p, pl->model_in.p + n, pl->model_in.p + 2 * n, pl->model.p, pl->cpmax.p, s);
+  launch_model_prep(g, pl->model_in.p, pl->model_in.p + n, pl->model_in.p + 2 * n, pl->model.p, pl->cpmax.p, pl->layout, s);
   pl->launches += 2;
   unsigned int bits = 0;
   CUDA_OK(cudaMemcpyAsync(&bits, pl->cpmax.p, sizeof(bits), cudaMemcpyDeviceToHost, s));
@@ -717,6 +722,15 @@ static void plan_set_stf_impl(fwi_b200_plan *pl, const double *stf) {
   CUDA_OK(cudaMemcpyAsync(pl->stf.p, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice, pl->stream));
   CUDA_OK(cudaStreamSynchronize(pl->stream));
   pl->stf_set = true;
+}
+
+extern "C" int fwi_b200_plan_set_layout(fwi_b200_plan *pl, int layout) {
+  return guarded([&] {
+    if (!pl || (layout != 0 && layout != 1)) throw Error(FWI_B200_ERR_ARG, "set_layout: layout must be 0 (row-major) or 1 (column-major)");
+    std::lock_guard<std::mutex> lk(pl->mu);
+    if (pl->layout != layout) pl->model_set = false;   // the resident model was converted under the other convention
+    pl->layout = layout;
+  });
 }
 
 extern "C" int fwi_b200_plan_set_stf(fwi_b200_plan *pl, const double *stf) {
@@ -1073,8 +1087,9 @@ void write_scratch(fwi_b200_plan *pl) {   // libCUFD.cu:493-511
 
 int host_call(double *misfit, double *gl, double *gm, double *gd, double *gs, const double *Lambda, const double *Mu,
               const double *Den, const double *stf, int calc_id, bool also_misfit, int gpu_id, int group_size,
-              const int *shot_ids, const char *para_fname) {
+              const int *shot_ids, const char *para_fname, int layout = 0) {
   return guarded([&] {
+    if (layout != 0 && layout != 1) throw Error(FWI_B200_ERR_ARG, "layout must be 0 (row-major) or 1 (column-major)");
     if (calc_id < 0 || calc_id > 2) throw Error(FWI_B200_ERR_ARG, "Invalid calc_id " + std::to_string(calc_id));
     if (!Lambda || !Mu || !Den || !stf || !shot_ids || !para_fname || group_size <= 0)
       throw Error(FWI_B200_ERR_ARG, "cufd: null input");
@@ -1085,6 +1100,7 @@ int host_call(double *misfit, double *gl, double *gm, double *gd, double *gs, co
     // one caller at a time per cached plan, for the WHOLE sequence: two threads with the same (para, gpu, shot ids) but
     // different models must not interleave set_model / run / get_result
     std::lock_guard<std::mutex> call(pl->call_mu);
+    check(fwi_b200_plan_set_layout(pl, layout));
     host_eval(pl, Lambda, Mu, Den, stf, calc_id, true);
     if (calc_id == 2) {
       plan_write_obs_files_impl(pl);
@@ -1105,6 +1121,13 @@ extern "C" int fwi_b200_cufd(double *misfit, double *gl, double *gm, double *gd,
                              const double *Mu, const double *Den, const double *stf, int calc_id, int gpu_id,
                              int group_size, const int *shot_ids, const char *para_fname) {
   return host_call(misfit, gl, gm, gd, gs, Lambda, Mu, Den, stf, calc_id, false, gpu_id, group_size, shot_ids, para_fname);
+}
+
+extern "C" int fwi_b200_cufd_ex(double *misfit, double *gl, double *gm, double *gd, double *gs, const double *Lambda,
+                                const double *Mu, const double *Den, const double *stf, int calc_id, int gpu_id,
+                                int group_size, const int *shot_ids, const char *para_fname, int layout, int with_misfit) {
+  return host_call(misfit, gl, gm, gd, gs, Lambda, Mu, Den, stf, calc_id, with_misfit != 0, gpu_id, group_size, shot_ids,
+                   para_fname, layout);
 }
 
 extern "C" int fwi_b200_forward(double *misfit, const double *Lambda, const double *Mu, const double *Den, const double *stf,
@@ -1243,6 +1266,7 @@ extern "C" int fwi_b200_gradient_multi(double *misfit, double *gl, double *gm, d
       sh.gpu = gpu_ids[r];
       sh.plan = cached_plan(para_fname, sh.gpu, (int)sh.ids.size(), sh.ids.data());
       sh.call = std::unique_lock<std::mutex>(sh.plan->call_mu);
+      check(fwi_b200_plan_set_layout(sh.plan.get(), 0));
     }
     // one host thread per device: inputs H2D, observations, forward + backward enqueued on the plan's stream.
     // Nothing synchronises: the gradient of the shard stays in the plan's packed result buffer.

@@ -117,6 +117,25 @@ def fwi_op_and_grad(lam, mu, den, stf, gpu_id, shot_ids, para_fname):
     return float(misfit.value), gl, gm, gd, gs
 
 
+def fwi_cufd_column_major(calc_id, lam, mu, den, stf, gpu_id, shot_ids, para_fname, with_misfit=True):
+    """fwi_b200_cufd_ex with layout = 1: lam / mu / den are handed over as COLUMN-major (nz, nx) arrays (Fortran / Julia
+    order -- the order the device keeps) and the gradients come back the same way; no transpose on either side.
+    Returns (misfit, gl, gm, gd, gs) with Fortran-ordered (nz, nx) gradient arrays."""
+    lam, mu, den, stf, ids = _prep(lam, mu, den, stf, shot_ids, para_fname)
+    F = lambda a: np.asfortranarray(a)                      # element (z, x) at x * nz + z
+    lam, mu, den = F(lam), F(mu), F(den)
+    gl, gm, gd = (np.zeros(lam.shape, np.float64, order="F") for _ in range(3))
+    gs_group = np.zeros((len(ids), stf.shape[1]), np.float64)
+    misfit = ctypes.c_double(0.0)
+    fp = lambda a: a.ctypes.data_as(c_dp)
+    check(_lib.lib().fwi_b200_cufd_ex(ctypes.cast(ctypes.byref(misfit), c_dp), fp(gl), fp(gm), fp(gd), _dp(gs_group), fp(lam),
+                                      fp(mu), fp(den), _dp(stf), int(calc_id), int(gpu_id), len(ids),
+                                      ids.ctypes.data_as(c_ip), str(para_fname).encode(), 1, 1 if with_misfit else 0))
+    gs = np.zeros_like(stf)
+    gs[ids] = gs_group
+    return float(misfit.value), gl, gm, gd, gs
+
+
 def fwi_op_and_grad_multi(lam, mu, den, stf, gpu_ids, shot_ids, para_fname):
     """Loss and gradients with the shots of the group sharded over several GPUs of THIS process
     (fwi_b200_gradient_multi): shot k goes to gpu_ids[k % len(gpu_ids)], the devices run concurrently."""

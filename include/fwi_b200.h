@@ -72,6 +72,16 @@ int fwi_b200_obscalc(double *misfit, const double *Lambda, const double *Mu, con
                      const double *stf, int gpu_id, int group_size, const int *shot_ids,
                      const char *para_fname);
 
+/* fwi_b200_cufd with two more arguments.  layout: 0 = Lambda / Mu / Den and the three gradient grids are
+ * ROW-major [z][x] like the reference's TensorFlow tensors; 1 = COLUMN-major (nz, nx) arrays, element (z, x) at
+ * x * nz + z -- what a Julia Matrix is, and the order the device keeps, so neither side transposes (the reference makes
+ * Julia transpose into TensorFlow's layout and cufd transpose back, libCUFD.cu:68-78).  stf and grad_stf are unaffected
+ * (row = shot).  with_misfit != 0 with calc_id 1: also write *misfit (like fwi_b200_misfit_and_gradient). */
+int fwi_b200_cufd_ex(double *misfit, double *grad_Lambda, double *grad_Mu, double *grad_Den,
+                     double *grad_stf, const double *Lambda, const double *Mu, const double *Den,
+                     const double *stf, int calc_id, int gpu_id, int group_size, const int *shot_ids,
+                     const char *para_fname, int layout, int with_misfit);
+
 /* Fused loss + gradient from ONE forward propagation (the reference propagates twice
  * per L-BFGS evaluation: FwiOp.cpp:100 and :220).  Any output pointer may be NULL. */
 int fwi_b200_misfit_and_gradient(double *misfit, double *grad_Lambda, double *grad_Mu,
@@ -148,6 +158,9 @@ void fwi_b200_plan_destroy(fwi_b200_plan *plan);
 int fwi_b200_plan_set_model(fwi_b200_plan *plan, const double *Lambda, const double *Mu,
                             const double *Den);
 int fwi_b200_plan_set_stf(fwi_b200_plan *plan, const double *stf);
+/* layout of the (nz, nx) grids this plan takes (set_model) and returns (get_result, result_device): 0 row-major [z][x]
+ * (default), 1 column-major.  Changing it invalidates the resident model. */
+int fwi_b200_plan_set_layout(fwi_b200_plan *plan, int layout);
 /* observed data of the i-th shot of the group: (nrec, nSteps) float32, time fastest. */
 int fwi_b200_plan_set_obs(fwi_b200_plan *plan, int ishot, const float *obs);
 /* read data_dir_name/Shot<id>.bin for every shot of the group (libCUFD.cu:189-192). */

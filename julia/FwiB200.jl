@@ -108,3 +108,21 @@ end
 
 "free the device contexts cached behind the host-buffer entry points"
 fwi_release_b200() = ccall((:fwi_b200_release, LIBFWI), Cvoid, ())
+
+# ---- without any transpose: Julia matrices are column-major, which is the order the device keeps (layout = 1) ----------
+"(misfit, gλ, gμ, gρ, g_stf) = cufd_colmajor_b200(calc_id, λ, μ, ρ, stf, gpu_id, shot_ids0, para): the (nz, nx) arrays go
+down and come back as they are (fwi_b200_cufd_ex, layout = 1); the reference transposes twice per call
+(convert_to_tensor + libCUFD.cu:68-78)"
+function cufd_colmajor_b200(calc_id::Integer, λ::Matrix{Float64}, μ::Matrix{Float64}, ρ::Matrix{Float64}, stf,
+                            gpu_id::Integer, shot_ids::Vector{Int32}, para::String)
+    check_shapes_b200(λ, μ, ρ, stf, shot_ids, para)
+    nz, nx = size(λ); nsteps = size(stf, 2)
+    misfit = Ref{Cdouble}(0.0)
+    gλ = zeros(nz, nx); gμ = zeros(nz, nx); gρ = zeros(nz, nx); gs = zeros(nsteps, length(shot_ids))
+    rc = ccall((:fwi_b200_cufd_ex, LIBFWI), Cint,
+               (Ref{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble},
+                Ptr{Cdouble}, Ptr{Cdouble}, Cint, Cint, Cint, Ptr{Cint}, Cstring, Cint, Cint),
+               misfit, gλ, gμ, gρ, gs, λ, μ, ρ, rowmajor(stf), calc_id, gpu_id, length(shot_ids), shot_ids, para, 1, 1)
+    fwi_error(rc)
+    misfit[], gλ, gμ, gρ, permutedims(gs)
+end

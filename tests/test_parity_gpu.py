@@ -548,3 +548,27 @@ def test_thin_boundary_frames(ops):
                     assert rel(out[2][k][inner], g_o[name][inner]) <= TOL_GRAD, (c.name, name)
     finally:
         ops.set_option("frame_ring", 2)      # the default
+
+
+def test_column_major_layout_is_the_same_evaluation(ops):
+    """fwi_b200_cufd_ex(layout = 1): column-major (nz, nx) grids in, column-major gradients out -- the very
+    same numbers as the row-major call, bit for bit, for all three calc ids."""
+    c = CASES["aniso"]                                   # nz != nx, dz != dx: a transposition mistake cannot hide
+    para = c.write_files(tempfile.mkdtemp(prefix="cm_"))
+    ids = np.arange(c.nShots, dtype=np.int32)
+    lam, mu, rho = c.moduli("true")
+    lam0, mu0, rho0 = c.moduli("init")
+    ops.fwi_obs_op(lam, mu, rho, c.stf, 0, ids, para)
+    obs_rm = [np.fromfile(os.path.join(os.path.dirname(para), "Data", f"Shot{i}.bin"), np.float32) for i in ids]
+    ops.fwi_cufd_column_major(2, lam, mu, rho, c.stf, 0, ids, para)
+    obs_cm = [np.fromfile(os.path.join(os.path.dirname(para), "Data", f"Shot{i}.bin"), np.float32) for i in ids]
+    assert all(np.array_equal(a, b) and np.abs(a).max() > 0 for a, b in zip(obs_rm, obs_cm))
+    j, gl, gm, gd, gs = ops.fwi_op_and_grad(lam0, mu0, rho0, c.stf, 0, ids, para)
+    jc, glc, gmc, gdc, gsc = ops.fwi_cufd_column_major(1, lam0, mu0, rho0, c.stf, 0, ids, para)
+    assert glc.flags["F_CONTIGUOUS"] and glc.shape == gl.shape
+    assert jc == j > 0 and np.array_equal(gsc, gs)
+    for a, b in ((glc, gl), (gmc, gm), (gdc, gd)):
+        assert np.abs(b).max() > 0 and np.array_equal(np.ascontiguousarray(a), b)
+    assert ops.fwi_cufd_column_major(0, lam0, mu0, rho0, c.stf, 0, ids, para)[0] == ops.fwi_op(lam0, mu0, rho0, c.stf, 0, ids, para)
+    again = ops.fwi_op_and_grad(lam0, mu0, rho0, c.stf, 0, ids, para)      # the cached plan is back in row-major mode
+    assert again[0] == j and np.array_equal(again[1], gl)
