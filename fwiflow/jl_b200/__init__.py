@@ -14,4 +14,5 @@ from .utils import (paraGen, surveyGen, sourceGene, velocity_to_moduli, klauderW
 from .ops import (fwi_op, fwi_obs_op, fwi_op_grad, fwi_op_and_grad, fwi_op_and_grad_multi, Plan, FwiError,  # noqa: F401
                   release)
 from .fwi import (FWI, FWIExample, compute_observation, compute_misfit, compute_misfit_and_gradient,  # noqa: F401
+                  compute_misfit_and_gradient_resident,
                   timelapse_misfit_and_gradients, timelapse_misfit_and_gradients_batched)

@@ -29,6 +29,7 @@ SYMBOLS = [
     "fwi_b200_plan_shot_geometry", "fwi_b200_plan_launch_count", "fwi_b200_plan_get_field",
     "fwi_b200_plan_time_kernel", "fwi_b200_version", "fwi_b200_grid_info", "fwi_b200_para_info",
     "fwi_b200_timelapse", "fwi_b200_set_option", "fwi_b200_cufd_ex", "fwi_b200_plan_set_layout",
+    "fwi_b200_plan_set_velocities", "fwi_b200_plan_get_velocity_gradients",
 ]
 
 ERRORS = {-1: "ERR_ARG", -2: "ERR_IO", -3: "ERR_JSON", -4: "ERR_CFL", -5: "ERR_CUDA", -6: "ERR_UNSUPPORTED",
@@ -70,6 +71,8 @@ def lib():
     L.fwi_b200_cufd.argtypes = host_sig
     L.fwi_b200_cufd_ex.argtypes = host_sig + [ctypes.c_int, ctypes.c_int]
     L.fwi_b200_plan_set_layout.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    L.fwi_b200_plan_set_velocities.argtypes = [ctypes.c_void_p] + [c_dp] * 6 + [ctypes.c_int, ctypes.c_int]
+    L.fwi_b200_plan_get_velocity_gradients.argtypes = [ctypes.c_void_p] + [c_dp] * 4
     L.fwi_b200_misfit_and_gradient.argtypes = [c_dp] * 9 + [ctypes.c_int, ctypes.c_int, c_ip, ctypes.c_char_p]
     L.fwi_b200_gradient_multi.argtypes = [c_dp] * 9 + [ctypes.c_int, c_ip, ctypes.c_int, c_ip, ctypes.c_char_p]
     L.fwi_b200_grid_info.argtypes = [ctypes.c_char_p, c_ip]

@@ -56,6 +56,67 @@ __global__ void model_convert_cm_kernel(Grid g, const double *__restrict__ lam_i
   model[M_DEN * g.plane + o] = (float)den_in[k];
 }
 
+// =================================================================================================
+// velocity-space front end (src/FWI.jl:156-205, src/Utils.jl:221-227 on the device)
+// =================================================================================================
+// tf.pad(a, [nPml (nPml + nPad); nPml nPml], "SYMMETRIC"): padded index -> source index (edge repeated, reflecting on)
+__device__ __forceinline__ int sym_index(int i, int pad, int n) {
+  const int m = 2 * n;
+  int r = (i - pad) % m;
+  if (r < 0) r += m;
+  return r < n ? r : m - 1 - r;
+}
+// the reference's gradient mask (src/FWI.jl:45-49): 1 inside the absorbing layers, minus the 10 rows under the top one
+__device__ __forceinline__ bool fwi_mask(const Grid &g, int z, int x) {
+  const int nz0 = g.nz - 2 * g.nPml - g.nPad, nx0 = g.nx - 2 * g.nPml;
+  return z >= g.nPml + 10 && z < g.nPml + nz0 && x >= g.nPml && x < g.nPml + nx0;
+}
+
+// cp, cs, rho (unpadded (nz0, nx0) or padded (nz, nx), the caller's layout) -> padded, mask-blended with the reference
+// models unless is_masked (src/FWI.jl:174-176) -> vel [3][nz nx] (kept for the chain rule) and lambda, mu [MPa], rho
+// in model_in, all in the caller's layout and in double with NumPy's / Julia's operation order (no contraction), so that
+// the float planes derived from them are the ones the host path produces.
+__global__ void velocity_prep_kernel(Grid g, int column_major, int padded, int is_masked, const double *__restrict__ in,
+                                     long long n_in, double *__restrict__ vel, double *__restrict__ model_in) {
+  const long long n = (long long)g.nz * g.nx;
+  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int z = column_major ? (int)(k % g.nz) : (int)(k / g.nx), x = column_major ? (int)(k / g.nz) : (int)(k % g.nx);
+  const int nz0 = g.nz - 2 * g.nPml - g.nPad, nx0 = g.nx - 2 * g.nPml;
+  long long j = k;
+  if (!padded) {
+    const int zs = sym_index(z, g.nPml, nz0), xs = sym_index(x, g.nPml, nx0);
+    j = column_major ? (long long)xs * nz0 + zs : (long long)zs * nx0 + xs;
+  }
+  const bool use_ref = !is_masked && !fwi_mask(g, z, x);
+  const double *src = in + (use_ref ? 3 * n_in : 0);
+  const double cp = src[j], cs = src[n_in + j], den = src[2 * n_in + j];
+  vel[k] = cp; vel[n + k] = cs; vel[2 * n + k] = den;
+  const double cs2 = __dmul_rn(__dmul_rn(2.0, cs), cs);
+  model_in[k] = __ddiv_rn(__dmul_rn(__dsub_rn(__dmul_rn(cp, cp), cs2), den), 1e6);
+  model_in[n + k] = __ddiv_rn(__dmul_rn(__dmul_rn(cs, cs), den), 1e6);
+  model_in[2 * n + k] = den;
+}
+
+// chain rule of velocity_to_moduli (what TF autodiff applies in the reference): packed float gradients w.r.t.
+// (lambda, mu, rho) -> double gradients w.r.t. (cp, cs, rho) on the padded grid, times the mask unless is_masked
+__global__ void velocity_grad_kernel(Grid g, int column_major, int is_masked, const float *__restrict__ result,
+                                     const double *__restrict__ vel, double *__restrict__ out) {
+  const long long n = (long long)g.nz * g.nx;
+  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int z = column_major ? (int)(k % g.nz) : (int)(k / g.nx), x = column_major ? (int)(k / g.nz) : (int)(k % g.nx);
+  const double gl = result[k], gm = result[n + k], gd = result[2 * n + k];
+  const double cp = vel[k], cs = vel[n + k], den = vel[2 * n + k];
+  double g_cp = __dmul_rn(__ddiv_rn(__dmul_rn(__dmul_rn(2.0, cp), den), 1e6), gl);
+  double g_cs = __ddiv_rn(__dmul_rn(__dmul_rn(__dadd_rn(__dmul_rn(-4.0, gl), __dmul_rn(2.0, gm)), cs), den), 1e6);
+  const double a = __dmul_rn(__dsub_rn(__dmul_rn(cp, cp), __dmul_rn(__dmul_rn(2.0, cs), cs)), gl);
+  const double b = __dmul_rn(__dmul_rn(cs, cs), gm);
+  double g_rho = __dadd_rn(gd, __ddiv_rn(__dadd_rn(a, b), 1e6));
+  if (!is_masked && !fwi_mask(g, z, x)) g_cp = g_cs = g_rho = 0.0;
+  out[k] = g_cp; out[n + k] = g_cs; out[2 * n + k] = g_rho;
+}
+
 // mu_bar, averaged buoyancies (utilities.cu:125-152, Model.cu:67-73), max cp (utilities.cu:109-123), and the
 // dt-scaled coefficient planes the step kernels read: lambda dt, (lambda + 2 mu) dt, mu_bar dt, byc_a dt, byc_b dt
 __global__ void model_derive_kernel(Grid g, float *model, unsigned int *cpmax_bits) {
@@ -292,6 +353,18 @@ void launch_model_prep(const Grid &g, const double *d_lam, const double *d_mu, c
   }
   dim3 dg((g.nz + 127) / 128, g.nx);
   model_derive_kernel<<<dg, 128, 0, s>>>(g, model, cpmax_bits);
+}
+
+void launch_velocity_prep(const Grid &g, int column_major, int padded, int is_masked, const double *in, long long n_in,
+                          double *vel, double *model_in, cudaStream_t s) {
+  const long long n = (long long)g.nz * g.nx;
+  velocity_prep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(g, column_major, padded, is_masked, in, n_in, vel, model_in);
+}
+
+void launch_velocity_grad(const Grid &g, int column_major, int is_masked, const float *result, const double *vel, double *out,
+                          cudaStream_t s) {
+  const long long n = (long long)g.nz * g.nx;
+  velocity_grad_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(g, column_major, is_masked, result, vel, out);
 }
 
 void launch_residual(const ResidualArgs &a, int *nblocks_out, cudaStream_t s) {

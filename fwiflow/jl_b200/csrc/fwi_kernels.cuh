@@ -168,6 +168,14 @@ void launch_backward_merged(const BwdArgs &a, cudaStream_t s);
 void launch_model_prep(const Grid &g, const double *d_lam, const double *d_mu, const double *d_den, float *model,
                        unsigned int *cpmax_bits, int column_major, cudaStream_t s);
 
+// velocity-space front end: `in` = [cp | cs | rho | cp_ref | cs_ref | rho_ref] doubles of n_in elements each (unpadded
+// (nz0, nx0) or padded grids in the caller's layout; the refs only when !is_masked) -> vel [3][nz nx] + model_in [3][nz nx]
+void launch_velocity_prep(const Grid &g, int column_major, int padded, int is_masked, const double *in, long long n_in,
+                          double *vel, double *model_in, cudaStream_t s);
+// packed float result [gl | gm | gd] + vel -> out [g_cp | g_cs | g_rho] doubles on the padded grid, caller's layout
+void launch_velocity_grad(const Grid &g, int column_major, int is_masked, const float *result, const double *vel, double *out,
+                          cudaStream_t s);
+
 // residual: taper obs & syn, res = obs - syn (t=0 -> 0), partial sums of res^2, taper res
 struct ResidualArgs {
   const float *syn_tr;   // [nSteps][nrp]  raw synthetic (receiver fastest)

@@ -89,6 +89,8 @@ struct fwi_b200_plan {
   // device memory
   DevBuf<float> model;        // lam mu den amu bya byb planes
   DevBuf<double> model_in;    // 3 * nz*nx staging of the caller's doubles
+  DevBuf<double> vel_in, vel, vel_grad;   // velocity-space front end: staged inputs, masked padded (cp, cs, rho), chain-rule output
+  int vel_masked = -1;        // is_masked of the last set_velocities (-1: the model was not set through velocities)
   DevBuf<unsigned int> cpmax;
   DevBuf<float> zprof, xprof, w2;
   DevBuf<float> state, gacc, frames, syn_tr, res_tr;
@@ -126,7 +128,7 @@ struct fwi_b200_plan {
       if (pin[k]) cudaFreeHost(pin[k]);
     }
     if (stream) cudaStreamSynchronize(stream);
-    model.release(); model_in.release(); cpmax.release(); zprof.release(); xprof.release(); w2.release();
+    model.release(); model_in.release(); vel_in.release(); vel.release(); vel_grad.release(); cpmax.release(); zprof.release(); xprof.release(); w2.release();
     state.release(); gacc.release(); frames.release(); syn_tr.release(); res_tr.release();
     obs_rt.release(); syn_rt.release(); res_rt.release(); obs_cond_rt.release();
     src_z.release(); src_x.release(); rec_ptr.release(); rec_loc.release(); rec_id.release(); win.release();
@@ -673,6 +675,8 @@ extern "C" int fwi_b200_plan_create(fwi_b200_plan **out, const char *para_fname,
 
 extern "C" void fwi_b200_plan_destroy(fwi_b200_plan *plan) { delete plan; }
 
+static void finish_model_locked(fwi_b200_plan *pl);
+
 static void plan_set_model_impl(fwi_b200_plan *pl, const double *Lambda, const double *Mu, const double *Den) {
   if (!pl || !Lambda || !Mu || !Den) throw Error(FWI_B200_ERR_ARG, "set_model: null pointer");
   std::lock_guard<std::mutex> lk(pl->mu);
@@ -683,6 +687,15 @@ static void plan_set_model_impl(fwi_b200_plan *pl, const double *Lambda, const d
   CUDA_OK(cudaMemcpyAsync(pl->model_in.p, Lambda, n * sizeof(double), cudaMemcpyHostToDevice, s));
   CUDA_OK(cudaMemcpyAsync(pl->model_in.p + n, Mu, n * sizeof(double), cudaMemcpyHostToDevice, s));
   CUDA_OK(cudaMemcpyAsync(pl->model_in.p + 2 * n, Den, n * sizeof(double), cudaMemcpyHostToDevice, s));
+  pl->vel_masked = -1;
+  finish_model_locked(pl);
+}
+
+// model_in (lambda, mu [MPa], rho; caller's layout) -> float planes, derived coefficients, Courant check
+static void finish_model_locked(fwi_b200_plan *pl) {
+  const Grid &g = pl->g;
+  const size_t n = (size_t)g.nz * g.nx;
+  cudaStream_t s = pl->stream;
   CUDA_OK(cudaMemsetAsync(pl->cpmax.p, 0, sizeof(unsigned int), s));
   launch_model_prep(g, pl->model_in.p, pl->model_in.p + n, pl->model_in.p + 2 * n, pl->model.p, pl->cpmax.p, pl->layout, s);
   pl->launches += 2;
@@ -722,6 +735,56 @@ static void plan_set_stf_impl(fwi_b200_plan *pl, const double *stf) {
   CUDA_OK(cudaMemcpyAsync(pl->stf.p, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice, pl->stream));
   CUDA_OK(cudaStreamSynchronize(pl->stream));
   pl->stf_set = true;
+}
+
+extern "C" int fwi_b200_plan_set_velocities(fwi_b200_plan *pl, const double *cp, const double *cs, const double *rho,
+                                            const double *cp_ref, const double *cs_ref, const double *rho_ref, int is_masked,
+                                            int padded) {
+  return guarded([&] {
+    if (!pl || !cp || !cs || !rho) throw Error(FWI_B200_ERR_ARG, "set_velocities: null pointer");
+    if (!is_masked && !(cp_ref && cs_ref && rho_ref))
+      throw Error(FWI_B200_ERR_ARG, "set_velocities: cp_ref, cs_ref, rho_ref are required when is_masked is 0 (src/FWI.jl:174-176)");
+    std::lock_guard<std::mutex> lk(pl->mu);
+    use_device(pl->gpu);
+    const Grid &g = pl->g;
+    const long long nz0 = g.nz - 2 * g.nPml - g.nPad, nx0 = g.nx - 2 * g.nPml;
+    if (nz0 <= 0 || nx0 <= 0) throw Error(FWI_B200_ERR_GEOM, "set_velocities: no cells between the absorbing layers");
+    const long long n = (long long)g.nz * g.nx, n_in = padded ? n : nz0 * nx0;
+    pl->vel_in.alloc((size_t)6 * n_in);
+    pl->vel.alloc((size_t)3 * n);
+    cudaStream_t s = pl->stream;
+    const double *src[6] = {cp, cs, rho, cp_ref, cs_ref, rho_ref};
+    for (int k = 0; k < (is_masked ? 3 : 6); k++)
+      CUDA_OK(cudaMemcpyAsync(pl->vel_in.p + k * n_in, src[k], n_in * sizeof(double), cudaMemcpyHostToDevice, s));
+    launch_velocity_prep(g, pl->layout, padded ? 1 : 0, is_masked ? 1 : 0, pl->vel_in.p, n_in, pl->vel.p, pl->model_in.p, s);
+    pl->launches++;
+    pl->vel_masked = is_masked ? 1 : 0;
+    finish_model_locked(pl);
+  });
+}
+
+extern "C" int fwi_b200_plan_get_velocity_gradients(fwi_b200_plan *pl, double *misfit, double *g_cp, double *g_cs,
+                                                    double *g_rho) {
+  return guarded([&] {
+    if (!pl || !g_cp || !g_cs || !g_rho) throw Error(FWI_B200_ERR_ARG, "get_velocity_gradients: null pointer");
+    std::lock_guard<std::mutex> lk(pl->mu);
+    use_device(pl->gpu);
+    if (pl->vel_masked < 0 || pl->last_calc != 1)
+      throw Error(FWI_B200_ERR_ARG, "get_velocity_gradients: needs set_velocities followed by a calc_id 1 run");
+    CUDA_OK(cudaDeviceSynchronize());
+    const Grid &g = pl->g;
+    const size_t n = (size_t)g.nz * g.nx;
+    pl->vel_grad.alloc(3 * n);
+    launch_velocity_grad(g, pl->layout, pl->vel_masked, pl->result.p, pl->vel.p, pl->vel_grad.p, pl->stream);
+    pl->launches++;
+    CUDA_OK(cudaMemcpyAsync(g_cp, pl->vel_grad.p, n * sizeof(double), cudaMemcpyDeviceToHost, pl->stream));
+    CUDA_OK(cudaMemcpyAsync(g_cs, pl->vel_grad.p + n, n * sizeof(double), cudaMemcpyDeviceToHost, pl->stream));
+    CUDA_OK(cudaMemcpyAsync(g_rho, pl->vel_grad.p + 2 * n, n * sizeof(double), cudaMemcpyDeviceToHost, pl->stream));
+    float m = 0;
+    CUDA_OK(cudaMemcpyAsync(&m, pl->result.p + 3 * n, sizeof(float), cudaMemcpyDeviceToHost, pl->stream));
+    CUDA_OK(cudaStreamSynchronize(pl->stream));
+    if (misfit) *misfit = m;
+  });
 }
 
 extern "C" int fwi_b200_plan_set_layout(fwi_b200_plan *pl, int layout) {

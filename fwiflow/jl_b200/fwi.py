@@ -168,6 +168,44 @@ def compute_misfit_and_gradient(fwi: FWI, cp, cs, rho, stf_array, shot_ids=None,
     return misfit, g_cp, g_cs, g_rho
 
 
+def compute_misfit_and_gradient_resident(fwi: FWI, cp, cs, rho, stf_array, shot_ids=None, gpu_id=0, is_masked=False,
+                                         cp_ref=None, cs_ref=None, rho_ref=None, reload_obs=False):
+    """Same value as compute_misfit_and_gradient with everything between the caller's (cp, cs, rho) and the gradients
+    w.r.t. them on the device: a plan per (gpu, shot group) is kept on `fwi`, the observations
+    are read from WORKSPACE/Data once (`reload_obs=True` after they change), the source time functions are uploaded
+    when they change, and symmetric padding, mask blend, velocity_to_moduli and the chain rule back run as kernels
+    (fwi_b200_plan_set_velocities / _get_velocity_gradients).  Per evaluation the host moves 3 model grids down and 3
+    gradient grids up, nothing else."""
+    if shot_ids is None:
+        shot_ids = np.arange(1, len(fwi.ind_src_x) + 1)
+    ids0 = np.asarray(shot_ids, dtype=np.int32) - 1
+    cache = fwi.__dict__.setdefault("_resident_plans", {})
+    key = (int(gpu_id), tuple(int(i) for i in ids0))
+    ent = cache.get(key)
+    if ent is None:
+        ent = cache[key] = {"plan": ops.Plan(fwi.para_path, ids0, gpu_id=gpu_id), "stf": None, "obs": False}
+    plan = ent["plan"]
+    if reload_obs or not ent["obs"]:
+        plan.load_obs_files()
+        ent["obs"] = True
+    stf = _stf_rows(fwi, stf_array)                       # rows indexed by global shot id (Src_Rec.cu:135)
+    if ent["stf"] is None or ent["stf"].shape != stf.shape or not np.array_equal(ent["stf"], stf):
+        plan.set_stf(stf)
+        ent["stf"] = stf.copy()
+    models = [np.asarray(a, dtype=np.float64) for a in (cp, cs, rho)]
+    refs = None
+    if not is_masked:
+        if cp_ref is None or cs_ref is None or rho_ref is None:
+            raise ValueError("compute_misfit: cp_ref, cs_ref, rho_ref are required when is_masked is False")
+        refs = [np.asarray(a, dtype=np.float64) for a in (cp_ref, cs_ref, rho_ref)]
+    if len({a.shape for a in models + (refs or [])}) > 1:      # mixed padded / unpadded inputs: pad on the host
+        models = list(try_pad(fwi, *models))
+        refs = list(try_pad(fwi, *refs)) if refs else None
+    plan.set_velocities(*models, refs=refs, is_masked=is_masked)
+    plan.run(1)
+    return plan.velocity_gradients()
+
+
 def timelapse_misfit_and_gradients(surveys, stf_array, shot_ids=None, gpu_ids=(0,), **kw):
     """Time-lapse (flow-coupled) FWI: one misfit + gradient per survey, baseline and monitors, as the reference's
     coupled inversion evaluates them (docs/codes/src_fwi_coupled/main_two_phase_flow_inversion.jl:50-62,84-93: one

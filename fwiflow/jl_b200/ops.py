@@ -261,6 +261,34 @@ class Plan:
         _check_shapes(self.nz, self.nx, self.nSteps, lam, mu, den, None, self.shot_ids)
         check(self._L.fwi_b200_plan_set_model(self._h, _dp(lam), _dp(mu), _dp(den)))
 
+    def set_velocities(self, cp, cs, rho, refs=None, is_masked=False):
+        """cp, cs, rho -> symmetric padding, mask blend with `refs` = (cp_ref, cs_ref, rho_ref) unless is_masked,
+        velocity_to_moduli and the model planes, all on the device (src/FWI.jl:156-205).  The grids are either
+        unpadded (nz - 2 nPml - nPad, nx - 2 nPml) or padded (nz, nx), refs like the models."""
+        arrs = [_f64(a) for a in (cp, cs, rho)]
+        inner = (self.nz - 2 * self.nPml - self.nPad, self.nx - 2 * self.nPml)
+        if arrs[0].shape not in (inner, (self.nz, self.nx)):
+            raise FwiError(-1, f"set_velocities: cp has shape {arrs[0].shape}; the para file gives {inner} unpadded or "
+                               f"{(self.nz, self.nx)} padded")
+        if not is_masked:
+            if refs is None:
+                raise FwiError(-1, "set_velocities: refs=(cp_ref, cs_ref, rho_ref) is required unless is_masked")
+            arrs += [_f64(a) for a in refs]
+        for a in arrs:
+            if a.shape != arrs[0].shape:
+                raise FwiError(-1, f"set_velocities: shapes differ: {a.shape} vs {arrs[0].shape}")
+        ptrs = [_dp(a) for a in arrs] + [None] * (6 - len(arrs))
+        check(self._L.fwi_b200_plan_set_velocities(self._h, *ptrs, 1 if is_masked else 0,
+                                                   1 if arrs[0].shape == (self.nz, self.nx) else 0))
+
+    def velocity_gradients(self):
+        """(misfit, g_cp, g_cs, g_rho) on the padded grid after run(1) on a model given by set_velocities."""
+        misfit = ctypes.c_double(0.0)
+        g = [np.zeros((self.nz, self.nx)) for _ in range(3)]
+        check(self._L.fwi_b200_plan_get_velocity_gradients(self._h, ctypes.cast(ctypes.byref(misfit), c_dp),
+                                                           *[_dp(a) for a in g]))
+        return (float(misfit.value), *g)
+
     def set_stf(self, stf):
         stf = _f64(stf)
         if stf.ndim == 1:

@@ -161,6 +161,21 @@ int fwi_b200_plan_set_stf(fwi_b200_plan *plan, const double *stf);
 /* layout of the (nz, nx) grids this plan takes (set_model) and returns (get_result, result_device): 0 row-major [z][x]
  * (default), 1 column-major.  Changing it invalidates the resident model. */
 int fwi_b200_plan_set_layout(fwi_b200_plan *plan, int layout);
+/* Velocity-space front end: what FWI.jl does in TensorFlow around the op (src/FWI.jl:156-205, src/Utils.jl:221-227),
+ * done on the device.  cp, cs [m/s], rho [kg/m^3] in the plan's layout; padded = 0: (nz - 2 nPml - nPad, nx - 2 nPml)
+ * grids, extended like tf.pad(..., "SYMMETRIC") (FWI.jl:166-170); padded = 1: (nz, nx) grids.  is_masked = 0 blends
+ * with the padded reference models outside the reference's mask (FWI.jl:45-49, 174-176; *_ref required, same shape
+ * as cp), is_masked != 0 takes the models as they are (*_ref ignored).  Then lambda = (cp^2 - 2 cs^2) rho / 1e6,
+ * mu = cs^2 rho / 1e6 (Utils.jl:221-227) and the Courant check of set_model. */
+int fwi_b200_plan_set_velocities(fwi_b200_plan *plan, const double *cp, const double *cs, const double *rho,
+                                 const double *cp_ref, const double *cs_ref, const double *rho_ref,
+                                 int is_masked, int padded);
+/* After a calc_id 1 run on a model given by set_velocities: the misfit and d misfit / d (cp, cs, rho) on the PADDED
+ * (nz, nx) grid in the plan's layout -- the chain rule TensorFlow applies through velocity_to_moduli and the mask
+ * blend (zero outside the mask when is_masked was 0).  Gradients w.r.t. unpadded inputs are the fold of these over
+ * the symmetric padding (the adjoint of tf.pad), left to the caller. */
+int fwi_b200_plan_get_velocity_gradients(fwi_b200_plan *plan, double *misfit, double *g_cp, double *g_cs,
+                                         double *g_rho);
 /* observed data of the i-th shot of the group: (nrec, nSteps) float32, time fastest. */
 int fwi_b200_plan_set_obs(fwi_b200_plan *plan, int ishot, const float *obs);
 /* read data_dir_name/Shot<id>.bin for every shot of the group (libCUFD.cu:189-192). */

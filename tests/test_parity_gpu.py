@@ -338,6 +338,50 @@ def test_high_level_api(ops):
     assert fd == pytest.approx(an, rel=0.1)
 
 
+@pytest.mark.parametrize("is_masked", [False, True])
+def test_velocity_front_end_on_the_device(ops, is_masked):
+    """fwi_b200_plan_set_velocities / _get_velocity_gradients: symmetric padding, mask blend,
+    velocity_to_moduli and the chain rule as kernels give what the NumPy mirror of src/FWI.jl:156-205 gives around the
+    host-buffer op -- the same doubles go into the same float planes, so the comparison is to rounding of the double
+    chain rule, not to a float tolerance."""
+    from fwiflow.jl_b200 import (FWI, compute_misfit_and_gradient, compute_misfit_and_gradient_resident,
+                                 compute_observation, sourceGene)
+    from fwiflow.jl_b200.fwi import padding
+    rng = np.random.default_rng(11)
+    nz, nx = 37, 53                                   # odd sizes: padded grid 37 + 64 + nPad
+    fwi = FWI(nz=nz, nx=nx, dz=20.0, dx=20.0, nSteps=250, dt=0.002, f0=6.0, ind_src_x=[10, 30, 44], ind_src_z=[12, 12, 12],
+              ind_rec_x=np.arange(3, 50), ind_rec_z=np.full(47, 12))
+    cp = 2500.0 + 300.0 * (np.arange(nz)[:, None] / nz) * np.ones((1, nx))
+    cs = cp / np.sqrt(3.0); rho = 2200.0 + 50.0 * rng.random((nz, nx))
+    stf = sourceGene(6.0, 250, 0.002)
+    compute_observation(fwi, cp, cs, rho, stf)
+    cp2 = cp * (1.0 + 0.03 * rng.random(cp.shape)); cs2 = cs * (1.0 - 0.02 * rng.random(cp.shape))
+    kw = dict(is_masked=is_masked, cp_ref=cp, cs_ref=cs, rho_ref=rho)
+    ref = compute_misfit_and_gradient(fwi, cp2, cs2, rho, stf, shot_ids=[1, 3], **kw)
+    for models in ((cp2, cs2, rho), padding(fwi, cp2, cs2, rho)):          # unpadded (device pads) and padded inputs
+        got = compute_misfit_and_gradient_resident(fwi, *models, stf, shot_ids=[1, 3], **kw)
+        assert got[0] == pytest.approx(ref[0], rel=1e-6)
+        for a, b in zip(got[1:], ref[1:]):
+            assert a.shape == (fwi.nz_pad, fwi.nx_pad)
+            assert rel(a, b) <= 1e-6
+            if not is_masked:
+                assert np.all(a[fwi.mask == 0] == 0)
+    # the second evaluation reuses the plan, the observations and the source functions
+    assert len(fwi._resident_plans) == 1
+    again = compute_misfit_and_gradient_resident(fwi, cp2, cs2, rho, stf, shot_ids=[1, 3], **kw)
+    assert again[0] == got[0] and np.array_equal(again[1], got[1])
+    # error behaviour: refs missing, wrong shape, gradients before a run
+    plan = ops.Plan(fwi.para_path, [0])
+    with pytest.raises(ops.FwiError):
+        plan.set_velocities(cp2, cs2, rho)
+    with pytest.raises(ops.FwiError):
+        plan.set_velocities(cp2[:-1], cs2[:-1], rho[:-1], is_masked=True)
+    plan.set_velocities(cp2, cs2, rho, is_masked=True)
+    with pytest.raises(ops.FwiError):
+        plan.velocity_gradients()
+    plan.close()
+
+
 def test_sharded_gradient_single_rank_and_device_buffer(ops):
     import torch
     from fwiflow.jl_b200 import dist as fdist
