@@ -71,10 +71,15 @@ template <bool LEAN> constexpr int frm_bytes() { return (LEAN ? NOWN : NCOMPUTE)
 template <bool LEAN> constexpr size_t rev_smem() {
   return (size_t)NS * RSTAGE_BYTES + (LEAN ? 1 : 2) * SV_BYTES + frm_bytes<LEAN>() + (NS + 1) * sizeof(TileDesc) + (NS + 1) * 8 + 128;
 }
+// Shot groups (BwdArgs::acc_group > 1): the imaging accumulators of a tile stay in shared memory while the CTA takes
+// the shots of the group one after the other -- one accumulator slot per GROUP in HBM, read at the group's first shot
+// and written at its last, instead of 32 B per cell, shot and time index.
+constexpr int RACC_BYTES = G_COUNT * NOWN * 16 + 32;
+enum : int { TF_ACC_FIRST = 64, TF_ACC_LAST = 128 };
 constexpr size_t REV_SMEM = rev_smem<false>();
 static_assert(RW_BYTES % 128 == 0 && RV_BYTES % 128 == 0, "TMA destination alignment");
 
-template <bool LEAN>
+template <bool LEAN, bool GROUPED>
 __global__ void __launch_bounds__(NCOMPUTE, CTAS_PER_SM)
 rev_image_kernel(const __grid_constant__ BwdArgs a, int tz_first, int tx_first, int ntz, int ntiles) {
   constexpr int NSV = LEAN ? 1 : 2;
@@ -90,8 +95,22 @@ rev_image_kernel(const __grid_constant__ BwdArgs a, int tz_first, int tx_first, 
 
   const Grid &g = a.g;
   const int tid = threadIdx.x;
-  const int nitems = a.batch * ntiles;
-  const int stride = gridDim.x;   // round-robin item order (see fwd_step_kernel)
+  // Work is dealt round-robin in units of (tile, shot group): CTA b takes units b, b + gridDim.x, ... and, inside a
+  // unit, the shots of the group one after the other.  With acc_group == 1 a unit is one (tile, shot) item, shot
+  // fastest -- the order of the other step kernels.  With larger groups the CTAs walk the shots in step, each on its
+  // own tile, so that at any instant they still read neighbouring tiles of the same few shots (contiguous HBM pages).
+  const int G = GROUPED ? a.acc_group : 1;
+  const int ngrp = (a.batch + G - 1) / G;
+  const int nunits = ntiles * ngrp;
+  const int stride = gridDim.x;
+  constexpr int TAIL_OFF = NS * RSTAGE_BYTES + NSV * SV_BYTES + FRM_BYTES + (NS + 1) * (int)sizeof(TileDesc) + (NS + 1) * 8;
+  int *pst = reinterpret_cast<int *>(base + TAIL_OFF);   // producer's position {unit, shot within the unit's group}: its lane only
+  float *s_acc = reinterpret_cast<float *>(base + (TAIL_OFF + 8 + 15) / 16 * 16);   // [G_COUNT][NOWN] quads (acc_group > 1 only)
+  int n_my = 0;   // items of this CTA
+  for (int u = blockIdx.x; u < nunits; u += stride) {
+    const int uo = a.order ? nunits - 1 - u : u;
+    n_my += min(G, a.batch - (uo % ngrp) * G);
+  }
   const int fin = a.cur_f ? S_FB : S_FA, fout = a.cur_f ? S_FA : S_FB;
   const int ain = a.cur_a ? S_AB : S_AA;
   const int P = g.P;
@@ -106,16 +125,22 @@ rev_image_kernel(const __grid_constant__ BwdArgs a, int tz_first, int tx_first, 
   }
   __syncthreads();
 
-  auto produce = [&](int item, int stage, int ds, bool first = false) {
-    const int io = a.order ? nitems - 1 - item : item;       // reverse launches run descending, adjoint launches ascending
-    const int t = io / a.batch, shot = io - t * a.batch;      // shot fastest: the shots of a tile share its coefficients
+  // producer: next item of this CTA (only the producer lane calls it, in sequence; p_u < nunits on entry)
+  auto produce = [&](int stage, int ds, bool first = false) {
+    int p_u = pst[0], p_j = pst[1];
+    const int uo = a.order ? nunits - 1 - p_u : p_u;         // reverse launches run descending, adjoint launches ascending
+    const int t = uo / ngrp, grp = uo - t * ngrp;             // group fastest: the shots of a tile share its coefficients
+    const int len = min(G, a.batch - grp * G);
+    const int shot = grp * G + (a.order ? len - 1 - p_j : p_j);
     const int z0 = (tz_first + t % ntz) * TILE_Z, x0 = (tx_first + t / ntz) * TILE_X;
     const int sz = a.st.src_z[shot], sx = a.st.src_x[shot];
     TileDesc d;
     d.soff = (long long)shot * S_COUNT * pl + (long long)x0 * P + z0;
     d.moff = x0 * P + z0;
-    d.z0 = z0; d.x0 = x0; d.shot = shot; d.tile = t; d.sz = sz; d.sx = sx; d.r0 = d.r1 = 0;
-    int fl = 0;
+    d.z0 = z0; d.x0 = x0; d.shot = shot; d.tile = t; d.sz = sz; d.sx = sx; d.r0 = grp; d.r1 = 0;
+    int fl = (p_j == 0 ? TF_ACC_FIRST : 0) | (p_j == len - 1 ? TF_ACC_LAST : 0);
+    if (++p_j == len) { p_j = 0; p_u += stride; }
+    pst[0] = p_u; pst[1] = p_j;
     // every tile whose owner cells or their +-4 halo can touch the ring (the old launch's frame_tile test)
     if (!(z0 - 4 > g.zlo - 1 + g.f_in && z0 + TILE_Z + 3 < g.zhi + 1 - g.f_in && x0 - 2 > g.xlo - 1 + g.f_in &&
           x0 + TILE_X + 1 < g.xhi + 1 - g.f_in))
@@ -136,12 +161,14 @@ rev_image_kernel(const __grid_constant__ BwdArgs a, int tz_first, int tx_first, 
 #if FWI_L2PF
     // operands of the owner quads that are fetched with direct loads: adjoint fields and imaging accumulators -> L2
     tma_prefetch_3d(&a.tm.o5, z0, x0 + XM, shot * S_COUNT + ain);
-    tma_prefetch_3d(&a.tm.g4, z0, x0 + XM, shot * G_COUNT);
+    if (fl & TF_ACC_FIRST) tma_prefetch_3d(&a.tm.g4, z0, x0 + XM, grp * G_COUNT);
 #endif
   };
-  if (tid == PRODUCER_TID)
+  if (tid == PRODUCER_TID) {
+    pst[0] = blockIdx.x; pst[1] = 0;
     for (int s = 0; s < NS; s++)
-      if (blockIdx.x + s * stride < nitems) produce(blockIdx.x + s * stride, s, s, s == 0);
+      if (pst[0] < nunits) produce(s, s, s == 0);
+  }
   __syncthreads();   // the first descriptors are visible: per-item global loads may start before the TMA data lands
   pdl_wait();
   pdl_launch_dependents();
@@ -157,14 +184,17 @@ rev_image_kernel(const __grid_constant__ BwdArgs a, int tz_first, int tx_first, 
   const int gx_max = g.nx + XM - 1;
 
   int stage = 0, phase = 0, nb = 0, ds = 0, kdone = 0;
-  for (int item = blockIdx.x; item < nitems; item += stride) {
+  for (int item = 0; item < n_my; item++) {
     const TileDesc d = sdesc[ds];   // written by the producer >= 1 block barrier ago
     const int gz = d.z0 - 4 + 4 * q, gx = d.x0 - 2 + c;
     const bool inb = (unsigned)gx < (unsigned)g.nx && (unsigned)gz < (unsigned)g.zlive;
     const bool owner = inner && inb;
     const long long toff = d.soff + ((long long)(c - 2) * P + 4 * q - 4);
     float *sq = a.state + g.origin + toff;                                       // + slot * pl
-    float *acc = a.gacc + g.origin + (long long)d.shot * (G_COUNT - S_COUNT) * pl + toff;   // shot * G_COUNT * pl + cell
+    // accumulator slot of the shot's group: group * G_COUNT * pl + cell
+    float *acc = a.gacc + g.origin + ((long long)d.r0 * G_COUNT - (long long)d.shot * S_COUNT) * pl + toff;
+    const bool acc_first = d.flags & TF_ACC_FIRST, acc_last = d.flags & TF_ACC_LAST;
+    float *my_acc = s_acc + 4 * ((q - 1) + (TILE_Z / 4) * (c - 2));   // owner quads only; planes 4 * NOWN floats apart
     const float *mq = a.m.ldt + ((long long)min(gx, gx_max) * P + gz);
     const bool colbox = gx >= g.xlo && gx <= g.xhi;
     bool bx[4];   // cell inside the inner box (reconstruction / imaging region)
@@ -188,6 +218,15 @@ rev_image_kernel(const __grid_constant__ BwdArgs a, int tz_first, int tx_first, 
 #pragma unroll
         for (int f = 0; f < 3; f++) cp_async16(my_frm + f * 4 * NFRM, frm + (F_SZZ + f) * g.f_len);
       }
+    }
+
+    const bool wr = owner && in_rect;
+    const bool colrho = gx >= g.xlo && gx <= g.xhi + 1;   // the x+1 spray also lands in column xhi + 1 (SURVEY.md Q2)
+    const bool rowbox = gz + 3 >= g.zlo && gz <= g.zhi;
+    if (GROUPED && acc_first && wr) {   // the group's accumulator slot -> this thread's shared slots (LDGSTS, no registers)
+#pragma unroll
+      for (int k = 0; k < 3; k++) cp_async16(my_acc + k * 4 * NOWN, acc + k * pl);
+      if (rowbox && colrho) cp_async16(my_acc + G_RHO * 4 * NOWN, acc + G_RHO * pl);
     }
 
     // global operands of the velocity half, requested before waiting for the ring: buoyancies, adjoint velocities.
@@ -241,9 +280,6 @@ rev_image_kernel(const __grid_constant__ BwdArgs a, int tz_first, int tx_first, 
     }
     // g_a of the cell right above the quad: from the thread above in the same half-warp (all 32 lanes take part)
     const float ga_up = __shfl_up_sync(0xffffffffu, ga.v[3], 1, 16);
-    const bool wr = owner && in_rect;
-    const bool colrho = gx >= g.xlo && gx <= g.xhi + 1;   // the x+1 spray also lands in column xhi + 1 (SURVEY.md Q2)
-    const bool rowbox = gz + 3 >= g.zlo && gz <= g.zhi;
     F4 grho = zero4();   // this step's density term of the quad, gathered
     if (wr && rowbox && colrho) {
       // g_b of column x-1 (zero outside the box): D-z(sxz) + D+x(sxx) one column to the left
@@ -283,11 +319,14 @@ rev_image_kernel(const __grid_constant__ BwdArgs a, int tz_first, int tx_first, 
     if (wr) {
       ldt = ld4(mq); l2mdt = ld4(mq + pl); amudt = ld4(mq + 2 * pl);
       za = ld4s(sq + (ain + F_SZZ) * pl); xa = ld4s(sq + (ain + F_SXX) * pl); xza = ld4s(sq + (ain + F_SXZ) * pl);
-      gl = ld4s(acc + G_LAM * pl); gm = ld4s(acc + G_MU * pl); gs = ld4s(acc + G_MUS * pl);
-      if (rowbox && colrho) gd = ld4s(acc + G_RHO * pl);
+      if (!GROUPED) {
+        gl = ld4s(acc + G_LAM * pl); gm = ld4s(acc + G_MU * pl); gs = ld4s(acc + G_MUS * pl);
+        if (rowbox && colrho) gd = ld4s(acc + G_RHO * pl);
+      }
     }
+    if (GROUPED && acc_first) cp_async_wait_all();   // (thread-private slots: no barrier needed for them)
     __syncthreads();  // s_v is complete; nobody reads ring slot `stage` any more
-    if (tid == PRODUCER_TID && item + NS * stride < nitems) produce(item + NS * stride, stage, ds == 0 ? NS : ds - 1);
+    if (tid == PRODUCER_TID && pst[0] < nunits) produce(stage, ds == 0 ? NS : ds - 1);
 
     // ---- sigma^{it} = sigma^{it+1} - source - stress(v^{it}) on the owner quads; lambda / mu imaging (el_stress.cu:90-124) ----
     if (wr) {
@@ -311,6 +350,9 @@ rev_image_kernel(const __grid_constant__ BwdArgs a, int tz_first, int tx_first, 
             sxx.v[kk] = (kk == ks) ? (float)((double)sxx.v[kk] - axx) : sxx.v[kk];
           }
         }
+        if (GROUPED) {   // running sums of the group's earlier shots (or the slot's contents, copied at the top of the item)
+          gl = ld4(my_acc + G_LAM * 4 * NOWN); gm = ld4(my_acc + G_MU * 4 * NOWN); gs = ld4(my_acc + G_MUS * 4 * NOWN);
+        }
 #pragma unroll
         for (int kk = 0; kk < 4; kk++) {
           if (bx[kk]) {
@@ -330,14 +372,22 @@ rev_image_kernel(const __grid_constant__ BwdArgs a, int tz_first, int tx_first, 
             gs.v[kk] += -xza.v[kk] * e * (q_rdt * amudt.v[kk] * amudt.v[kk]);
           }
         }
-        st4(acc + G_LAM * pl, gl);
-        st4(acc + G_MU * pl, gm);
-        st4(acc + G_MUS * pl, gs);
+        if (!GROUPED || acc_last) {
+          st4(acc + G_LAM * pl, gl);
+          st4(acc + G_MU * pl, gm);
+          st4(acc + G_MUS * pl, gs);
+        } else {
+          st4(my_acc + G_LAM * 4 * NOWN, gl);
+          st4(my_acc + G_MU * 4 * NOWN, gm);
+          st4(my_acc + G_MUS * 4 * NOWN, gs);
+        }
       }
       if (rowbox && colrho) {
+        if (GROUPED) gd = ld4(my_acc + G_RHO * 4 * NOWN);
 #pragma unroll
         for (int kk = 0; kk < 4; kk++) gd.v[kk] += grho.v[kk];
-        st4(acc + G_RHO * pl, gd);
+        if (!GROUPED || acc_last) st4(acc + G_RHO * pl, gd);
+        else st4(my_acc + G_RHO * 4 * NOWN, gd);
       }
       if (fq >= 0) {  // to_bnd(sigma) (libCUFD.cu:403)
         szz = ld4(my_frm);
@@ -1380,7 +1430,10 @@ __global__ void __launch_bounds__(NCOMPUTE, CTAS_PER_SM) bwd_step_kernel(const _
 
 // -1: pick the reverse kernel build by working-set size; 0 / 1: force the double-buffered / LEAN build
 std::atomic<int> g_rev_lean_force{-1};
+std::atomic<int> g_acc_group_force{0};   // 0: automatic (reverse_acc_group)
+bool reverse_is_lean(const Grid &g, int batch);
 void set_rev_lean(int v) { g_rev_lean_force.store(v, std::memory_order_relaxed); }
+void set_acc_group(int v) { g_acc_group_force.store(v, std::memory_order_relaxed); }
 
 size_t reverse_smem_bytes() { return REV_SMEM; }
 
@@ -1399,8 +1452,10 @@ void launch_backward_merged(const BwdArgs &a_in, cudaStream_t s) {
 
 void configure_backward_kernels() {
   cudaFuncSetAttribute(bwd_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MRG_SMEM);
-  cudaFuncSetAttribute(rev_image_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rev_smem<false>());
-  cudaFuncSetAttribute(rev_image_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rev_smem<true>());
+  cudaFuncSetAttribute(rev_image_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rev_smem<false>());
+  cudaFuncSetAttribute(rev_image_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rev_smem<true>());
+  cudaFuncSetAttribute(rev_image_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rev_smem<false>() + RACC_BYTES);
+  cudaFuncSetAttribute(rev_image_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rev_smem<true>() + RACC_BYTES);
   cudaFuncSetAttribute(adj_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ADJ_SMEM);
 }
 
@@ -1421,16 +1476,44 @@ void launch_reverse_imaging(const BwdArgs &a_in, cudaStream_t s) {
   const int tz0 = max(g.zlo - 2, 0) / TILE_Z, tz1 = min(g.zhi + 2, g.nz - 1) / TILE_Z;
   const int tx0 = max(g.xlo - 2, 0) / TILE_X, tx1 = min(g.xhi + 2, g.nx - 1) / TILE_X;
   const int ntz = tz1 - tz0 + 1, ntx = tx1 - tx0 + 1;
-  const int nitems = a.batch * ntz * ntx;
-  const int blocks = nitems < sm_count() * CTAS_PER_SM ? nitems : sm_count() * CTAS_PER_SM;
-  // working set of one launch = forward + adjoint fields and accumulators of every box cell of the batch; beyond a few
-  // L2 capacities the kernel is bound by its streams and wants the larger L1 (see rev_smem)
-  const double working_set = 100.0 * a.batch * (double)(g.zhi - g.zlo + 1) * (g.xhi - g.xlo + 1);
+  if (a.acc_group < 1) a.acc_group = 1;
+  if (a.acc_group > a.batch) a.acc_group = a.batch;
+  const int nunits = ((a.batch + a.acc_group - 1) / a.acc_group) * ntz * ntx;
+  const int blocks = nunits < sm_count() * CTAS_PER_SM ? nunits : sm_count() * CTAS_PER_SM;
+  const bool lean = reverse_is_lean(g, a.batch);
+  if (a.acc_group > 1) {
+    if (lean) launch_step(rev_image_kernel<true, true>, blocks, NCOMPUTE, rev_smem<true>() + RACC_BYTES, s, a, tz0, tx0, ntz, ntz * ntx);
+    else launch_step(rev_image_kernel<false, true>, blocks, NCOMPUTE, rev_smem<false>() + RACC_BYTES, s, a, tz0, tx0, ntz, ntz * ntx);
+  } else {
+    if (lean) launch_step(rev_image_kernel<true, false>, blocks, NCOMPUTE, rev_smem<true>(), s, a, tz0, tx0, ntz, ntz * ntx);
+    else launch_step(rev_image_kernel<false, false>, blocks, NCOMPUTE, rev_smem<false>(), s, a, tz0, tx0, ntz, ntz * ntx);
+  }
+}
+
+// working set of one launch = forward + adjoint fields and accumulators of every box cell of the batch; beyond a few
+// L2 capacities the kernel is bound by its streams and wants the larger L1 (see rev_smem)
+bool reverse_is_lean(const Grid &g, int batch) {
+  const double working_set = 100.0 * batch * (double)(g.zhi - g.zlo + 1) * (g.xhi - g.xlo + 1);
   const int force = g_rev_lean_force.load(std::memory_order_relaxed);   // A/B switch (fwi_b200_set_option)
-  if (force >= 0 ? force == 1 : (REV_LEAN_AUTO && working_set > 512e6))
-    launch_step(rev_image_kernel<true>, blocks, NCOMPUTE, rev_smem<true>(), s, a, tz0, tx0, ntz, ntz * ntx);
-  else
-    launch_step(rev_image_kernel<false>, blocks, NCOMPUTE, rev_smem<false>(), s, a, tz0, tx0, ntz, ntz * ntx);
+  return force >= 0 ? force == 1 : (REV_LEAN_AUTO && working_set > 512e6);
+}
+
+// Shots per accumulator slot of the reverse kernel (BwdArgs::acc_group).  Grouping pays where the kernel is bound by
+// its HBM streams (the LEAN regime: C3 8 shots 450 -> 357 us, 25 shots 1476 -> 1158 us per launch); where the fields
+// stay in L2 (C2) the whole gradient does not change and a slot per shot is kept.  Measured optimum 8 - 13 shots per
+// group (C3, 25 shots: 5 -> 1180, 9 -> 1158, 13 -> 1164, 25 -> 1222 us): groups of at most 12, evenly sized, and more of
+// them when a launch would otherwise have fewer than 6 rounds of (tile, group) units.
+int reverse_acc_group(const Grid &g, int batch) {
+  const int force = g_acc_group_force.load(std::memory_order_relaxed);
+  if (force >= 1) return force < batch ? force : batch;
+  if (!reverse_is_lean(g, batch)) return 1;
+  const int tz0 = max(g.zlo - 2, 0) / TILE_Z, tz1 = min(g.zhi + 2, g.nz - 1) / TILE_Z;
+  const int tx0 = max(g.xlo - 2, 0) / TILE_X, tx1 = min(g.xhi + 2, g.nx - 1) / TILE_X;
+  const long long ntiles = (long long)(tz1 - tz0 + 1) * (tx1 - tx0 + 1);
+  const long long want = 6LL * sm_count() * CTAS_PER_SM;
+  long long ngrp = (batch + 11) / 12;
+  while (ntiles * ngrp < want && ngrp < batch) ngrp++;
+  return (int)((batch + ngrp - 1) / ngrp);
 }
 
 }  // namespace fwi

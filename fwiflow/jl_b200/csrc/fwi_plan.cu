@@ -497,6 +497,9 @@ void run_locked(fwi_b200_plan &pl, int calc_id, cudaStream_t s) {
   fa.pr.z = pl.zprof.p + g.P; fa.pr.x = pl.xprof.p; fa.pr.nxp = g.nx + 2 * XM;
   BwdArgs ba{};
   ba.g = g; ba.m = m; ba.pr = fa.pr; ba.tm = pl.tm;
+  // shots per imaging-accumulator slot (the merged backward kernel keeps a slot per shot)
+  const int nb_max = std::min(pl.batch, pl.group);
+  ba.acc_group = g_merged_bwd.load(std::memory_order_relaxed) ? 1 : reverse_acc_group(g, nb_max);
 
   if (with_adj) {
     CUDA_OK(cudaMemsetAsync(pl.gacc.p, 0, pl.gacc.bytes(), s));
@@ -602,7 +605,7 @@ void run_locked(fwi_b200_plan &pl, int calc_id, cudaStream_t s) {
     pl.launches++;
   }
   if (with_adj) {
-    launch_finalize(g, pl.gacc.p, std::min(pl.batch, pl.group), m.mu, pl.misfit_half.p, pl.result.p, pl.layout, s);
+    launch_finalize(g, pl.gacc.p, (nb_max + ba.acc_group - 1) / ba.acc_group, m.mu, pl.misfit_half.p, pl.result.p, pl.layout, s);
     pl.launches++;
   } else if (if_res) {
     CUDA_OK(cudaMemcpyAsync(pl.result.p + 3LL * g.nz * g.nx, pl.misfit_half.p, sizeof(float), cudaMemcpyDeviceToDevice, s));
@@ -973,6 +976,7 @@ extern "C" int fwi_b200_plan_time_kernel(fwi_b200_plan *pl, int which, int iters
     BwdArgs ba{};
     ba.g = g; ba.m = fa.m; ba.pr = fa.pr; ba.tm = pl->tm; ba.st = fa.st; ba.state = pl->state.p; ba.res = pl->res_tr.p;
     ba.frames = pl->frames.p; ba.gacc = pl->gacc.p; ba.stf_grad = pl->stf_grad.p; ba.batch = nb;
+    ba.acc_group = which == 2 ? reverse_acc_group(g, nb) : 1;
     cudaEvent_t e0, e1;
     CUDA_OK(cudaEventCreate(&e0));
     CUDA_OK(cudaEventCreate(&e1));
@@ -1414,6 +1418,10 @@ extern "C" int fwi_b200_set_option(const char *name, int value) {
     if (!name) throw Error(FWI_B200_ERR_ARG, "set_option: null name");
     const std::string k(name);
     if (k == "rev_lean") set_rev_lean(value);
+    else if (k == "acc_group") {   // shots per accumulator slot of the reverse step: 0 automatic, 1 a slot per shot, k forced
+      if (value < 0) throw Error(FWI_B200_ERR_ARG, "set_option: acc_group must be >= 0");
+      set_acc_group(value);
+    }
     else if (k == "merged_bwd") g_merged_bwd.store(value != 0, std::memory_order_relaxed);
     else if (k == "frame_ring") {   // takes effect for plans created afterwards
       if (value != 2 && value != 5) throw Error(FWI_B200_ERR_ARG, "set_option: frame_ring must be 2 or 5");

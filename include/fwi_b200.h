@@ -126,7 +126,10 @@ int fwi_b200_para_info(const char *para_fname, int *out);
  * DRAM bytes but measured slower: latency-bound).  "frame_ring": depth of the boundary ring saved per
  * time step for the reverse-time reconstruction, for plans created afterwards: 2 (default) the two cells outside the
  * inner box that the stencils of the box cells read, 5 the reference's ring (Boundary.cu:17-27: those two plus three
- * box cells); same gradients to 2e-5, 2.1x the frame bytes. */
+ * box cells); same gradients to 2e-5, 2.1x the frame bytes.  "acc_group": shots of a launch that share one imaging
+ * accumulator slot in the reverse step (the CTA of a tile takes them one after the other and keeps the sums in shared
+ * memory): 0 (default) chosen by working-set size -- groups of <= 12 on the DRAM-bound grids, 1 elsewhere --, k >= 1
+ * forced; same gradients up to the order of the float sums (1e-6), deterministic for a given value. */
 int fwi_b200_set_option(const char *name, int value);
 
 /* Host-only: the device layout this library derives from a parameter file (no GPU needed).

@@ -11,6 +11,8 @@ iters = int(sys.argv[3]) if len(sys.argv) > 3 else 200
 c = synthetic.case_c2(nshots=nshots, nSteps=64) if case == "c2" else synthetic.case_c3(nshots=nshots, nSteps=64)
 para = c.write_files(tempfile.mkdtemp(prefix="kt_"))
 ids = np.arange(nshots, dtype=np.int32)
+if "FWI_ACC" in os.environ:      # shots per accumulator slot of the reverse step (0 automatic, 1 a slot per shot)
+    ops.set_option("acc_group", int(os.environ["FWI_ACC"]))
 p = ops.Plan(para, ids)
 p.set_stf(c.stf); p.set_model(*c.moduli("true")); p.run(2); print('obs ok', flush=True); p.write_obs_files()
 p.set_model(*c.moduli("init")); p.load_obs_files(); p.run(1); print('grad ok', flush=True)

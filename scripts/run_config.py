@@ -12,6 +12,8 @@ from fwiflow.jl_b200 import ops, synthetic
 case, nshots, nsteps = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
 if "FWI_RING" in os.environ:        # depth of the saved boundary ring: 5 (reference) or 2 (thin)
     ops.set_option("frame_ring", int(os.environ["FWI_RING"]))
+if "FWI_ACC" in os.environ:         # shots per accumulator slot of the reverse step (0 automatic, 1 a slot per shot)
+    ops.set_option("acc_group", int(os.environ["FWI_ACC"]))
 if "FWI_MERGED" in os.environ:      # A/B: backward loop as one merged launch per time index (1) or two launches (0)
     ops.set_option("merged_bwd", int(os.environ["FWI_MERGED"]))
 mk = {"c2": synthetic.case_c2, "c3": synthetic.case_c3, "c5": synthetic.case_c5}[case]
@@ -35,7 +37,7 @@ assert abs(ms * 1e-3 - wall) < 0.05 * wall + 5e-3, (ms, wall)   # the events bra
 free1, _ = torch.cuda.mem_get_info()
 j, gl, gm, gd, gs = p.result()
 cells = c.nz_pad * c.nx_pad
-print(json.dumps({"merged_bwd": os.environ.get("FWI_MERGED", "default"), "frame_ring": os.environ.get("FWI_RING", "default"), "config": case, "grid": [c.nz_pad, c.nx_pad], "shots": nshots, "nSteps": nsteps, "batch": p.batch,
+print(json.dumps({"acc_group": os.environ.get("FWI_ACC", "default"), "merged_bwd": os.environ.get("FWI_MERGED", "default"), "frame_ring": os.environ.get("FWI_RING", "default"), "config": case, "grid": [c.nz_pad, c.nx_pad], "shots": nshots, "nSteps": nsteps, "batch": p.batch,
                   "gradient_s": ms / 1e3, "forward_only_s": t_obs, "shot_gradients_per_s": nshots / (ms / 1e3),
                   "cell_updates_per_s": 2.0 * nshots * cells * (nsteps - 1) / (ms / 1e3),
                   "hbm_used_gb": (total - free1) / 1e9, "misfit": j,

@@ -338,6 +338,36 @@ def test_high_level_api(ops):
     assert fd == pytest.approx(an, rel=0.1)
 
 
+def test_shot_groups_share_an_accumulator_slot(ops):
+    """Reverse step with the imaging accumulators of a tile kept in shared memory across the shots of a group
+    (set_option("acc_group", k)): the same gradients as one slot per shot, up to the order of the float sums.  Ragged
+    groups (5 shots in groups of 2 and 3), one group for the whole batch, both builds of the kernel."""
+    from fwiflow.jl_b200 import synthetic
+    c = synthetic.case_small(name="groups", nz=120, nx=90, nshots=5, nSteps=220)     # 3 x 4 reverse tiles
+    para = c.write_files(tempfile.mkdtemp())
+    ids = list(range(len(c.stf)))
+    lam, mu, rho = c.moduli("true")
+    lam0, mu0, rho0 = c.moduli("init")
+    ops.fwi_obs_op(lam, mu, rho, c.stf, 0, ids, para)
+    try:
+        ops.set_option("acc_group", 1)
+        ref = ops.fwi_op_and_grad(lam0, mu0, rho0, c.stf, 0, ids, para)
+        for lean in (0, 1):
+            ops.set_option("rev_lean", lean)
+            for k in (2, 3, len(ids)):
+                ops.set_option("acc_group", k)
+                got = ops.fwi_op_and_grad(lam0, mu0, rho0, c.stf, 0, ids, para)
+                assert got[0] == ref[0]
+                for a, b in zip(got[1:4], ref[1:4]):
+                    assert rel(a, b) <= 1e-5, (lean, k)
+                assert np.array_equal(got[4], ref[4])          # grad_stf does not go through the accumulators
+                again = ops.fwi_op_and_grad(lam0, mu0, rho0, c.stf, 0, ids, para)
+                assert all(np.array_equal(a, b) for a, b in zip(got[1:4], again[1:4]))   # deterministic
+    finally:
+        ops.set_option("acc_group", 0)
+        ops.set_option("rev_lean", -1)
+
+
 @pytest.mark.parametrize("is_masked", [False, True])
 def test_velocity_front_end_on_the_device(ops, is_masked):
     """fwi_b200_plan_set_velocities / _get_velocity_gradients: symmetric padding, mask blend,
