@@ -66,7 +66,15 @@ def ncu_traffic():
     """dram bytes per launch of the hot kernels from the committed ncu captures (profiles/traffic.json):
     {"c2": {kernel: bytes at 30 shots}, "c3": {kernel: bytes at 8 shots}}."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
-    return json.load(open(p)) if os.path.exists(p) else {}
+    if not os.path.exists(p):
+        return {}
+    try:
+        raw = json.load(open(p))
+    except (OSError, ValueError):
+        return {}
+    # per config: kernel name -> bytes; notes, shot counts and anything else that is not a number is left out
+    return {cfg: {k: float(v) for k, v in d.items() if isinstance(v, (int, float)) and not k.startswith("_")}
+            for cfg, d in raw.items() if isinstance(d, dict)}
 
 
 class ClockSampler:

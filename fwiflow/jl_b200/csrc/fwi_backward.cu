@@ -106,11 +106,11 @@ rev_image_kernel(const __grid_constant__ BwdArgs a, int tz_first, int tx_first, 
   constexpr int TAIL_OFF = NS * RSTAGE_BYTES + NSV * SV_BYTES + FRM_BYTES + (NS + 1) * (int)sizeof(TileDesc) + (NS + 1) * 8;
   int *pst = reinterpret_cast<int *>(base + TAIL_OFF);   // producer's position {unit, shot within the unit's group}: its lane only
   float *s_acc = reinterpret_cast<float *>(base + (TAIL_OFF + 8 + 15) / 16 * 16);   // [G_COUNT][NOWN] quads (acc_group > 1 only)
-  int n_my = 0;   // items of this CTA
-  for (int u = blockIdx.x; u < nunits; u += stride) {
-    const int uo = a.order ? nunits - 1 - u : u;
-    n_my += min(G, a.batch - (uo % ngrp) * G);
-  }
+  // GROUPED: units are claimed from a counter in global memory (a.unit_counter) instead of being dealt statically, so
+  // that the units in flight are always ~gridDim.x consecutive ones however far the CTAs drift apart over the launch;
+  // the loop below ends on a sentinel descriptor.  Otherwise: static round-robin, item count known up front.
+  const bool dyn = GROUPED && a.unit_counter != nullptr;
+  const int n_my = GROUPED ? 0 : (nunits - (int)blockIdx.x + stride - 1) / stride;   // (!GROUPED: a unit is one item)
   const int fin = a.cur_f ? S_FB : S_FA, fout = a.cur_f ? S_FA : S_FB;
   const int ain = a.cur_a ? S_AB : S_AA;
   const int P = g.P;
@@ -128,6 +128,10 @@ rev_image_kernel(const __grid_constant__ BwdArgs a, int tz_first, int tx_first, 
   // producer: next item of this CTA (only the producer lane calls it, in sequence; p_u < nunits on entry)
   auto produce = [&](int stage, int ds, bool first = false) {
     int p_u = pst[0], p_j = pst[1];
+    if (GROUPED && p_u >= nunits) {   // nothing left: sentinel (the ring slot is not armed, nobody waits on it)
+      sdesc[ds].tile = -1;
+      return;
+    }
     const int uo = a.order ? nunits - 1 - p_u : p_u;         // reverse launches run descending, adjoint launches ascending
     const int t = uo / ngrp, grp = uo - t * ngrp;             // group fastest: the shots of a tile share its coefficients
     const int len = min(G, a.batch - grp * G);
@@ -139,7 +143,7 @@ rev_image_kernel(const __grid_constant__ BwdArgs a, int tz_first, int tx_first, 
     d.moff = x0 * P + z0;
     d.z0 = z0; d.x0 = x0; d.shot = shot; d.tile = t; d.sz = sz; d.sx = sx; d.r0 = grp; d.r1 = 0;
     int fl = (p_j == 0 ? TF_ACC_FIRST : 0) | (p_j == len - 1 ? TF_ACC_LAST : 0);
-    if (++p_j == len) { p_j = 0; p_u += stride; }
+    if (++p_j == len) { p_j = 0; p_u = dyn ? atomicAdd(a.unit_counter, 1) : p_u + stride; }
     pst[0] = p_u; pst[1] = p_j;
     // every tile whose owner cells or their +-4 halo can touch the ring (the old launch's frame_tile test)
     if (!(z0 - 4 > g.zlo - 1 + g.f_in && z0 + TILE_Z + 3 < g.zhi + 1 - g.f_in && x0 - 2 > g.xlo - 1 + g.f_in &&
@@ -151,7 +155,7 @@ rev_image_kernel(const __grid_constant__ BwdArgs a, int tz_first, int tx_first, 
     sdesc[ds] = d;
     unsigned char *sb = base + stage * RSTAGE_BYTES;
     const int p0 = shot * S_COUNT + fin;
-    if (first) pdl_wait();   // everything above reads static tables only
+    if (first && !dyn) pdl_wait();   // everything above reads static tables only
     mbar_arrive_expect_tx(&full[stage], RSTAGE_BYTES);
     tma_load_3d(sb, &a.tm.sw, z0 - 8, x0 - 4 + XM, p0 + F_SZZ, &full[stage]);
     tma_load_3d(sb + RW_BYTES, &a.tm.vn, z0 - 4, x0 - 2 + XM, p0 + F_VZ, &full[stage]);
@@ -165,9 +169,15 @@ rev_image_kernel(const __grid_constant__ BwdArgs a, int tz_first, int tx_first, 
 #endif
   };
   if (tid == PRODUCER_TID) {
-    pst[0] = blockIdx.x; pst[1] = 0;
+    if (dyn) {   // the counter belongs to the previous reverse launch until every earlier grid has completed
+      pdl_wait();
+      pst[0] = atomicAdd(a.unit_counter, 1);
+    } else {
+      pst[0] = blockIdx.x;
+    }
+    pst[1] = 0;
     for (int s = 0; s < NS; s++)
-      if (pst[0] < nunits) produce(s, s, s == 0);
+      if (GROUPED || pst[0] < nunits) produce(s, s, s == 0);
   }
   __syncthreads();   // the first descriptors are visible: per-item global loads may start before the TMA data lands
   pdl_wait();
@@ -184,8 +194,9 @@ rev_image_kernel(const __grid_constant__ BwdArgs a, int tz_first, int tx_first, 
   const int gx_max = g.nx + XM - 1;
 
   int stage = 0, phase = 0, nb = 0, ds = 0, kdone = 0;
-  for (int item = 0; item < n_my; item++) {
+  for (int item = 0; GROUPED || item < n_my; item++) {
     const TileDesc d = sdesc[ds];   // written by the producer >= 1 block barrier ago
+    if (GROUPED && d.tile < 0) break;
     const int gz = d.z0 - 4 + 4 * q, gx = d.x0 - 2 + c;
     const bool inb = (unsigned)gx < (unsigned)g.nx && (unsigned)gz < (unsigned)g.zlive;
     const bool owner = inner && inb;
@@ -326,7 +337,7 @@ rev_image_kernel(const __grid_constant__ BwdArgs a, int tz_first, int tx_first, 
     }
     if (GROUPED && acc_first) cp_async_wait_all();   // (thread-private slots: no barrier needed for them)
     __syncthreads();  // s_v is complete; nobody reads ring slot `stage` any more
-    if (tid == PRODUCER_TID && pst[0] < nunits) produce(stage, ds == 0 ? NS : ds - 1);
+    if (tid == PRODUCER_TID && (GROUPED || pst[0] < nunits)) produce(stage, ds == 0 ? NS : ds - 1);
 
     // ---- sigma^{it} = sigma^{it+1} - source - stress(v^{it}) on the owner quads; lambda / mu imaging (el_stress.cu:90-124) ----
     if (wr) {
@@ -406,6 +417,10 @@ rev_image_kernel(const __grid_constant__ BwdArgs a, int tz_first, int tx_first, 
     nb ^= 1;
     if (++ds == NS + 1) ds = 0;
     if (++stage == NS) { stage = 0; phase ^= 1; }
+  }
+  if (dyn && tid == PRODUCER_TID) {   // the last CTA to get here rewinds the counter for the next reverse launch
+    __threadfence();
+    if (atomicInc(reinterpret_cast<unsigned int *>(a.unit_counter) + 1, gridDim.x - 1) == gridDim.x - 1) a.unit_counter[0] = 0;
   }
 }
 
@@ -1499,11 +1514,17 @@ bool reverse_is_lean(const Grid &g, int batch) {
 }
 
 // Shots per accumulator slot of the reverse kernel (BwdArgs::acc_group).  Grouping pays where the kernel is bound by
-// its HBM streams (the LEAN regime: C3 8 shots 450 -> 357 us, 25 shots 1476 -> 1158 us per launch); where the fields
-// stay in L2 (C2) the whole gradient does not change and a slot per shot is kept.  Measured optimum 8 - 13 shots per
-// group (C3, 25 shots: 5 -> 1180, 9 -> 1158, 13 -> 1164, 25 -> 1222 us): groups of at most 12, evenly sized, and more of
-// them when a launch would otherwise have fewer than 6 rounds of (tile, group) units.
-int reverse_acc_group(const Grid &g, int batch) {
+// its HBM streams (the LEAN regime); where the fields stay in L2 (C2) the whole gradient does not change and a slot per
+// shot is kept.  Per launch, C3 grid / C5 grid (8 shots), us:
+//                                   C3 8 shots   C3 25 shots   C5 8 shots
+//   one slot per shot                  450          1476          4584
+//   groups, units dealt round-robin    357 (8)      1158 (9), 1222 (25)     3823 (4), 4064 (8)
+//   groups, units claimed dynamically  351 (8)      1077 (9), 1049 (25)     3730 (4), 3476 (8)
+// Dealt statically, the CTAs drift apart over the rounds of a launch, each at its own shot of its own tile, and the
+// accesses scatter over HBM pages -- the longer the launch, the more (C5: 139 rounds); claimed from a counter, the
+// units in flight are always ~148 consecutive tiles.  Dynamic: the whole batch is one group (at most 32 shots);
+// static: groups of at most 12.  Either way more groups when a launch would have fewer than 6 rounds of units.
+int reverse_acc_group(const Grid &g, int batch, bool dyn) {
   const int force = g_acc_group_force.load(std::memory_order_relaxed);
   if (force >= 1) return force < batch ? force : batch;
   if (!reverse_is_lean(g, batch)) return 1;
@@ -1511,7 +1532,8 @@ int reverse_acc_group(const Grid &g, int batch) {
   const int tx0 = max(g.xlo - 2, 0) / TILE_X, tx1 = min(g.xhi + 2, g.nx - 1) / TILE_X;
   const long long ntiles = (long long)(tz1 - tz0 + 1) * (tx1 - tx0 + 1);
   const long long want = 6LL * sm_count() * CTAS_PER_SM;
-  long long ngrp = (batch + 11) / 12;
+  const int gmax = dyn ? 32 : 12;
+  long long ngrp = (batch + gmax - 1) / gmax;
   while (ntiles * ngrp < want && ngrp < batch) ngrp++;
   return (int)((batch + ngrp - 1) / ngrp);
 }

@@ -147,6 +147,8 @@ struct BwdArgs {
   int cur_f;           // forward-field buffer holding state it+1
   int cur_a;           // adjoint buffer holding the pre-update adjoint state
   int order;           // item order of this launch (0 ascending, 1 descending)
+  int *unit_counter;   // reverse step with shot groups: {next unit, CTAs done} in global memory, zero between launches
+                       // (nullptr: units are dealt round-robin)
   int acc_group;       // reverse step: shots that share one accumulator slot of gacc (reverse_acc_group; 1 = a slot per shot)
   int indep;           // adjoint step only: the launch before it in the stream is the reverse step of the same time
                        // index, whose output it does not touch -> no wait in the prologue (see adj_step_kernel)
@@ -159,7 +161,7 @@ void launch_forward_step(const FwdArgs &a, bool save_frames, cudaStream_t s);
 void launch_reverse_imaging(const BwdArgs &a, cudaStream_t s);
 // shots per accumulator slot the reverse step should use for this grid and batch (the caller passes it in
 // BwdArgs::acc_group and sums ceil(batch / acc_group) slots in launch_finalize); set_acc_group: 0 automatic, k forced
-int reverse_acc_group(const Grid &g, int batch);
+int reverse_acc_group(const Grid &g, int batch, bool dynamic_units);
 void set_acc_group(int v);
 // adjoint step: source_grad, adjoint velocity, residual injection, adjoint stress
 void launch_adjoint_step(const BwdArgs &a, cudaStream_t s);

@@ -98,6 +98,7 @@ struct fwi_b200_plan {
   DevBuf<int> src_z, src_x, rec_ptr, rec_loc, rec_id;
   DevBuf<float> win;          // [group][3][max_nrec] win_start | win_end | weights (para if_win)
   DevBuf<float> stf, stf_grad, j_shot, misfit_half, result;
+  DevBuf<int> unit_counter;   // reverse step: dynamic unit claim {next unit, CTAs done}
   DevBuf<double> partial;
   int partial_per_shot = 0;
   size_t trace_stride = 0;  // max_nrec * nSteps
@@ -132,7 +133,7 @@ struct fwi_b200_plan {
     state.release(); gacc.release(); frames.release(); syn_tr.release(); res_tr.release();
     obs_rt.release(); syn_rt.release(); res_rt.release(); obs_cond_rt.release();
     src_z.release(); src_x.release(); rec_ptr.release(); rec_loc.release(); rec_id.release(); win.release();
-    stf.release(); stf_grad.release(); j_shot.release(); misfit_half.release(); result.release();
+    stf.release(); stf_grad.release(); j_shot.release(); misfit_half.release(); result.release(); unit_counter.release();
     partial.release();
     if (stream) cudaStreamDestroy(stream);
   }
@@ -160,6 +161,9 @@ namespace {
 // depth of the saved boundary ring: 5 = the reference's (2 cells outside + 3 inside the box), 2 = the two outside cells
 std::atomic<int> g_frame_ring{FWI_FRAME_RING};
 // 1: backward loop = one merged launch per time index (bwd_step_kernel); 0: reverse + adjoint launches (A/B, set_option)
+#ifndef FWI_DYN_UNITS
+#define FWI_DYN_UNITS 1
+#endif
 std::atomic<int> g_merged_bwd{FWI_MERGED_BWD};
 
 int round_up(int v, int m) { return (v + m - 1) / m * m; }
@@ -481,6 +485,16 @@ void settle_obs_load(fwi_b200_plan &pl) {
   for (int i = 0; i < pl.group; i++) pl.obs_set[i] = pl.loader_code == 0 ? 1 : 0;
 }
 
+// counter pair of the reverse step's dynamic unit claim (zero whenever no reverse launch is in flight: the last CTA of a
+// launch rewinds it); nullptr when the option is off
+static std::atomic<int> g_dyn_units{FWI_DYN_UNITS};
+static int *unit_counter_of(fwi_b200_plan &pl, cudaStream_t s) {
+  if (!g_dyn_units.load(std::memory_order_relaxed)) return nullptr;
+  if (!pl.unit_counter.p) pl.unit_counter.alloc(2);
+  CUDA_OK(cudaMemsetAsync(pl.unit_counter.p, 0, 2 * sizeof(int), s));   // (also heals the pair after an aborted run)
+  return pl.unit_counter.p;
+}
+
 void run_locked(fwi_b200_plan &pl, int calc_id, cudaStream_t s) {
   const Grid &g = pl.g;
   if (calc_id < 0 || calc_id > 2) throw Error(FWI_B200_ERR_ARG, "invalid calc_id " + std::to_string(calc_id));
@@ -499,7 +513,8 @@ void run_locked(fwi_b200_plan &pl, int calc_id, cudaStream_t s) {
   ba.g = g; ba.m = m; ba.pr = fa.pr; ba.tm = pl.tm;
   // shots per imaging-accumulator slot (the merged backward kernel keeps a slot per shot)
   const int nb_max = std::min(pl.batch, pl.group);
-  ba.acc_group = g_merged_bwd.load(std::memory_order_relaxed) ? 1 : reverse_acc_group(g, nb_max);
+  ba.acc_group = g_merged_bwd.load(std::memory_order_relaxed) ? 1 : reverse_acc_group(g, nb_max, g_dyn_units.load(std::memory_order_relaxed) != 0);
+  ba.unit_counter = unit_counter_of(pl, s);
 
   if (with_adj) {
     CUDA_OK(cudaMemsetAsync(pl.gacc.p, 0, pl.gacc.bytes(), s));
@@ -679,6 +694,7 @@ extern "C" int fwi_b200_plan_create(fwi_b200_plan **out, const char *para_fname,
 extern "C" void fwi_b200_plan_destroy(fwi_b200_plan *plan) { delete plan; }
 
 static void finish_model_locked(fwi_b200_plan *pl);
+
 
 static void plan_set_model_impl(fwi_b200_plan *pl, const double *Lambda, const double *Mu, const double *Den) {
   if (!pl || !Lambda || !Mu || !Den) throw Error(FWI_B200_ERR_ARG, "set_model: null pointer");
@@ -976,7 +992,8 @@ extern "C" int fwi_b200_plan_time_kernel(fwi_b200_plan *pl, int which, int iters
     BwdArgs ba{};
     ba.g = g; ba.m = fa.m; ba.pr = fa.pr; ba.tm = pl->tm; ba.st = fa.st; ba.state = pl->state.p; ba.res = pl->res_tr.p;
     ba.frames = pl->frames.p; ba.gacc = pl->gacc.p; ba.stf_grad = pl->stf_grad.p; ba.batch = nb;
-    ba.acc_group = which == 2 ? reverse_acc_group(g, nb) : 1;
+    ba.acc_group = which == 2 ? reverse_acc_group(g, nb, g_dyn_units.load(std::memory_order_relaxed) != 0) : 1;
+    ba.unit_counter = unit_counter_of(*pl, s);
     cudaEvent_t e0, e1;
     CUDA_OK(cudaEventCreate(&e0));
     CUDA_OK(cudaEventCreate(&e1));
@@ -1418,6 +1435,7 @@ extern "C" int fwi_b200_set_option(const char *name, int value) {
     if (!name) throw Error(FWI_B200_ERR_ARG, "set_option: null name");
     const std::string k(name);
     if (k == "rev_lean") set_rev_lean(value);
+    else if (k == "dyn_units") g_dyn_units.store(value != 0, std::memory_order_relaxed);
     else if (k == "acc_group") {   // shots per accumulator slot of the reverse step: 0 automatic, 1 a slot per shot, k forced
       if (value < 0) throw Error(FWI_B200_ERR_ARG, "set_option: acc_group must be >= 0");
       set_acc_group(value);

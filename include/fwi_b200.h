@@ -129,7 +129,9 @@ int fwi_b200_para_info(const char *para_fname, int *out);
  * box cells); same gradients to 2e-5, 2.1x the frame bytes.  "acc_group": shots of a launch that share one imaging
  * accumulator slot in the reverse step (the CTA of a tile takes them one after the other and keeps the sums in shared
  * memory): 0 (default) chosen by working-set size -- groups of <= 12 on the DRAM-bound grids, 1 elsewhere --, k >= 1
- * forced; same gradients up to the order of the float sums (1e-6), deterministic for a given value. */
+ * forced; same gradients up to the order of the float sums (1e-6), deterministic for a given value.  "dyn_units": 1
+ * (default) the reverse step's (tile, shot group) units are claimed from a counter in device memory, 0 dealt
+ * round-robin (same results; measured slower on long launches). */
 int fwi_b200_set_option(const char *name, int value);
 
 /* Host-only: the device layout this library derives from a parameter file (no GPU needed).

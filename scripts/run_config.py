@@ -12,6 +12,8 @@ from fwiflow.jl_b200 import ops, synthetic
 case, nshots, nsteps = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
 if "FWI_RING" in os.environ:        # depth of the saved boundary ring: 5 (reference) or 2 (thin)
     ops.set_option("frame_ring", int(os.environ["FWI_RING"]))
+if "FWI_DYN" in os.environ:         # reverse step with shot groups: units claimed dynamically (1) or dealt round-robin (0)
+    ops.set_option("dyn_units", int(os.environ["FWI_DYN"]))
 if "FWI_ACC" in os.environ:         # shots per accumulator slot of the reverse step (0 automatic, 1 a slot per shot)
     ops.set_option("acc_group", int(os.environ["FWI_ACC"]))
 if "FWI_MERGED" in os.environ:      # A/B: backward loop as one merged launch per time index (1) or two launches (0)

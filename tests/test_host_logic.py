@@ -345,3 +345,20 @@ def test_json_unicode_paths(lib_built):
     with pytest.raises(ops.FwiError) as ei:
         ops.para_info(bad)
     assert ei.value.code == -3
+
+
+def test_bench_reads_the_committed_ncu_traffic_file():
+    """bench.py multiplies the entries of profiles/traffic.json; notes and shot counts in that file must not reach it."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    t = bench.ncu_traffic()
+    assert set(t) >= {"c2", "c3"}
+    for cfg in ("c2", "c3"):
+        assert {"fwd_step_kernel<save_frames>", "adj_step_kernel", "rev_image_kernel"} <= set(t[cfg])
+        assert all(isinstance(v, float) and v > 0 for v in t[cfg].values())
+    # whole-gradient byte count of the C2 bench step: 60 + 32 f, 60 + 64 f per cell, 64 per box cell, per time index
+    c = synthetic.case_c2(nshots=2, nSteps=8)
+    b = bench.whole_gradient_alg_bytes(c, 30, 2000)
+    assert 1.1e12 < b < 1.3e12
