@@ -22,7 +22,7 @@ mk = {"c2": synthetic.case_c2, "c3": synthetic.case_c3, "c5": synthetic.case_c5}
 c = mk(nshots=nshots, nSteps=nsteps)
 para = c.write_files(tempfile.mkdtemp(prefix=f"cfg_{case}_"))
 ids = np.arange(nshots, dtype=np.int32)
-p = ops.Plan(para, ids)
+p = ops.Plan(para, ids, max_batch=int(os.environ.get("FWI_BATCH", "0")))   # FWI_BATCH: shots per launch (0: chosen by the plan)
 p.set_stf(c.stf); p.set_model(*c.moduli("true"))
 t0 = time.time(); p.run(2); t_obs = time.time() - t0
 p.write_obs_files(); p.set_model(*c.moduli("init")); p.load_obs_files()
