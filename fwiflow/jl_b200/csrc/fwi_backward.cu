@@ -74,7 +74,11 @@ template <bool LEAN> constexpr size_t rev_smem() {
 // Shot groups (BwdArgs::acc_group > 1): the imaging accumulators of a tile stay in shared memory while the CTA takes
 // the shots of the group one after the other -- one accumulator slot per GROUP in HBM, read at the group's first shot
 // and written at its last, instead of 32 B per cell, shot and time index.
-constexpr int RACC_BYTES = G_COUNT * NOWN * 16 + 32;
+// Same build: the density term g_b of a quad is handed to the thread one column to the right through shared memory
+// (one quad per thread; double-buffered unless LEAN, whose "velocity tile free" wait also orders these writes) instead of
+// being evaluated a second time by that thread.
+constexpr int RACC_ONLY = G_COUNT * NOWN * 16 + 32;
+template <bool LEAN> constexpr int racc_bytes() { return RACC_ONLY + (LEAN ? 1 : 2) * NCOMPUTE * 16; }
 enum : int { TF_ACC_FIRST = 64, TF_ACC_LAST = 128 };
 constexpr size_t REV_SMEM = rev_smem<false>();
 static_assert(RW_BYTES % 128 == 0 && RV_BYTES % 128 == 0, "TMA destination alignment");
@@ -106,6 +110,7 @@ rev_image_kernel(const __grid_constant__ BwdArgs a, int tz_first, int tx_first, 
   constexpr int TAIL_OFF = NS * RSTAGE_BYTES + NSV * SV_BYTES + FRM_BYTES + (NS + 1) * (int)sizeof(TileDesc) + (NS + 1) * 8;
   int *pst = reinterpret_cast<int *>(base + TAIL_OFF);   // producer's position {unit, shot within the unit's group}: its lane only
   float *s_acc = reinterpret_cast<float *>(base + (TAIL_OFF + 8 + 15) / 16 * 16);   // [G_COUNT][NOWN] quads (acc_group > 1 only)
+  float *s_gb_base = s_acc + G_COUNT * NOWN * 4;                                      // [1 or 2][NCOMPUTE] quads (GROUPED only)
   // GROUPED: units are claimed from a counter in global memory (a.unit_counter) instead of being dealt statically, so
   // that the units in flight are always ~gridDim.x consecutive ones however far the CTAs drift apart over the launch;
   // the loop below ends on a sentinel descriptor.  Otherwise: static round-robin, item count known up front.
@@ -249,11 +254,15 @@ rev_image_kernel(const __grid_constant__ BwdArgs a, int tz_first, int tx_first, 
     F4 vza = zero4(), vxa = zero4(), vxaL = zero4(), bybL = zero4();
     const bool above = q == 0 && c >= 2 && c < TILE_X + 2 && inb;   // halo quad right above an owner quad
     if (owner || above) vza = ld4s(sq + (ain + F_VZ) * pl);
-    if (owner) {
+    if (GROUPED) {   // g_b of column x-1 comes from the thread of that column: the halo column left of the tile computes it too
+      const bool leftcol = c == 1 && q >= 1 && q <= TILE_Z / 4 && inb;
+      if (owner || leftcol) vxa = ld4s(sq + (ain + F_VX) * pl);
+    } else if (owner) {
       vxa = ld4s(sq + (ain + F_VX) * pl);
       vxaL = ld4s(sq + (ain + F_VX) * pl - P);
       bybL = ld4(mq + 4 * pl - P);
     }
+    float *s_gb = s_gb_base + (LEAN ? 0 : nb) * (NCOMPUTE * 4) + 4 * tid;
     mbar_wait(&full[stage], phase);
 
     const unsigned char *sb = base + stage * RSTAGE_BYTES;
@@ -292,7 +301,17 @@ rev_image_kernel(const __grid_constant__ BwdArgs a, int tz_first, int tx_first, 
     // g_a of the cell right above the quad: from the thread above in the same half-warp (all 32 lanes take part)
     const float ga_up = __shfl_up_sync(0xffffffffu, ga.v[3], 1, 16);
     F4 grho = zero4();   // this step's density term of the quad, gathered
-    if (wr && rowbox && colrho) {
+    if (GROUPED) {
+      st4(s_gb, gb);   // read by the thread one column to the right after the block barrier
+      if (wr && rowbox && colrho) {
+#pragma unroll
+        for (int kk = 0; kk < 4; kk++) {
+          const bool rowin = (unsigned)(gz + kk - g.zlo) <= (unsigned)(g.zhi - g.zlo);
+          const float up = kk == 0 ? ga_up : ga.v[kk - 1];
+          grho.v[kk] = rowin ? (ga.v[kk] + gb.v[kk]) + up : 0.0f;   // + g_b(z, x-1) after the barrier
+        }
+      }
+    } else if (wr && rowbox && colrho) {
       // g_b of column x-1 (zero outside the box): D-z(sxz) + D+x(sxx) one column to the left
       float ebL[4] = {0.f, 0.f, 0.f, 0.f};
       if (gx - 1 >= g.xlo && gx - 1 <= g.xhi) {
@@ -394,7 +413,12 @@ rev_image_kernel(const __grid_constant__ BwdArgs a, int tz_first, int tx_first, 
         }
       }
       if (rowbox && colrho) {
-        if (GROUPED) gd = ld4(my_acc + G_RHO * 4 * NOWN);
+        if (GROUPED) {
+          gd = ld4(my_acc + G_RHO * 4 * NOWN);
+          const F4 gbl = ld4(s_gb - 64);   // g_b of the quad one column to the left (zero outside the box)
+#pragma unroll
+          for (int kk = 0; kk < 4; kk++) grho.v[kk] += gbl.v[kk];
+        }
 #pragma unroll
         for (int kk = 0; kk < 4; kk++) gd.v[kk] += grho.v[kk];
         if (!GROUPED || acc_last) st4(acc + G_RHO * pl, gd);
@@ -1469,8 +1493,8 @@ void configure_backward_kernels() {
   cudaFuncSetAttribute(bwd_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MRG_SMEM);
   cudaFuncSetAttribute(rev_image_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rev_smem<false>());
   cudaFuncSetAttribute(rev_image_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rev_smem<true>());
-  cudaFuncSetAttribute(rev_image_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rev_smem<false>() + RACC_BYTES);
-  cudaFuncSetAttribute(rev_image_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rev_smem<true>() + RACC_BYTES);
+  cudaFuncSetAttribute(rev_image_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rev_smem<false>() + racc_bytes<false>());
+  cudaFuncSetAttribute(rev_image_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rev_smem<true>() + racc_bytes<true>());
   cudaFuncSetAttribute(adj_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ADJ_SMEM);
 }
 
@@ -1497,8 +1521,8 @@ void launch_reverse_imaging(const BwdArgs &a_in, cudaStream_t s) {
   const int blocks = nunits < sm_count() * CTAS_PER_SM ? nunits : sm_count() * CTAS_PER_SM;
   const bool lean = reverse_is_lean(g, a.batch);
   if (a.acc_group > 1) {
-    if (lean) launch_step(rev_image_kernel<true, true>, blocks, NCOMPUTE, rev_smem<true>() + RACC_BYTES, s, a, tz0, tx0, ntz, ntz * ntx);
-    else launch_step(rev_image_kernel<false, true>, blocks, NCOMPUTE, rev_smem<false>() + RACC_BYTES, s, a, tz0, tx0, ntz, ntz * ntx);
+    if (lean) launch_step(rev_image_kernel<true, true>, blocks, NCOMPUTE, rev_smem<true>() + racc_bytes<true>(), s, a, tz0, tx0, ntz, ntz * ntx);
+    else launch_step(rev_image_kernel<false, true>, blocks, NCOMPUTE, rev_smem<false>() + racc_bytes<false>(), s, a, tz0, tx0, ntz, ntz * ntx);
   } else {
     if (lean) launch_step(rev_image_kernel<true, false>, blocks, NCOMPUTE, rev_smem<true>(), s, a, tz0, tx0, ntz, ntz * ntx);
     else launch_step(rev_image_kernel<false, false>, blocks, NCOMPUTE, rev_smem<false>(), s, a, tz0, tx0, ntz, ntz * ntx);

@@ -363,9 +363,22 @@ def test_shot_groups_share_an_accumulator_slot(ops):
                 assert np.array_equal(got[4], ref[4])          # grad_stf does not go through the accumulators
                 again = ops.fwi_op_and_grad(lam0, mu0, rho0, c.stf, 0, ids, para)
                 assert all(np.array_equal(a, b) for a, b in zip(got[1:4], again[1:4]))   # deterministic
+        # two sequential batches (3 + 2 shots) with groups of 2: the second batch fills fewer slots than the first;
+        # units dealt round-robin instead of claimed from the device counter give the same sums
+        for dyn in (1, 0):
+            ops.set_option("dyn_units", dyn)
+            ops.set_option("acc_group", 2)
+            p = ops.Plan(para, ids, max_batch=3)
+            p.set_model(lam0, mu0, rho0); p.set_stf(c.stf); p.load_obs_files(); p.run(1)
+            j, gl, gm, gd, gs = p.result()
+            p.close()
+            assert p.batch == 3 and j == pytest.approx(ref[0], rel=1e-6)
+            for a, b in zip((gl, gm, gd), ref[1:4]):
+                assert rel(a, b) <= 1e-5, dyn
     finally:
         ops.set_option("acc_group", 0)
         ops.set_option("rev_lean", -1)
+        ops.set_option("dyn_units", 1)
 
 
 @pytest.mark.parametrize("is_masked", [False, True])
