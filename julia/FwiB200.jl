@@ -126,3 +126,53 @@ function cufd_colmajor_b200(calc_id::Integer, λ::Matrix{Float64}, μ::Matrix{Fl
     fwi_error(rc)
     misfit[], gλ, gμ, gρ, permutedims(gs)
 end
+
+# ---- resident plan: velocities in, velocity gradients out (what compute_loss_with_stf + gradients(loss, cp) do in
+# TensorFlow around the op, src/FWI.jl:156-205, src/Utils.jl:221-227, on the device) ------------------------------------
+"device-resident evaluation context of one (para file, gpu, shot group): observations, source functions, wavefield and
+frame buffers stay on the GPU between L-BFGS evaluations"
+mutable struct PlanB200
+    h::Ptr{Cvoid}
+    nz::Int; nx::Int; nsteps::Int
+end
+
+function PlanB200(para::String, gpu_id::Integer, shot_ids::Vector{Int32}, stf::AbstractMatrix{Float64})
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    fwi_error(ccall((:fwi_b200_plan_create, LIBFWI), Cint, (Ref{Ptr{Cvoid}}, Cstring, Cint, Cint, Ptr{Cint}, Cint),
+                    h, para, gpu_id, length(shot_ids), shot_ids, 0))
+    info = para_info_b200(para)
+    p = PlanB200(h[], info[1], info[2], info[3])
+    finalizer(close_b200, p)
+    fwi_error(ccall((:fwi_b200_plan_set_layout, LIBFWI), Cint, (Ptr{Cvoid}, Cint), p.h, 1))   # Julia matrices as they are
+    fwi_error(ccall((:fwi_b200_plan_load_obs_files, LIBFWI), Cint, (Ptr{Cvoid},), p.h))        # Data/Shot<id>.bin, once
+    size(stf, 2) == p.nsteps || error("fwi_b200: stf has $(size(stf, 2)) samples per row; the parameter file says $(p.nsteps)")
+    fwi_error(ccall((:fwi_b200_plan_set_stf, LIBFWI), Cint, (Ptr{Cvoid}, Ptr{Cdouble}), p.h, rowmajor(stf)))
+    p
+end
+
+function close_b200(p::PlanB200)
+    p.h == C_NULL || ccall((:fwi_b200_plan_destroy, LIBFWI), Cvoid, (Ptr{Cvoid},), p.h)
+    p.h = C_NULL
+    nothing
+end
+
+"(misfit, g_cp, g_cs, g_ρ) on the padded grid for cp, cs, ρ given unpadded (nz - 2 nPml - nPad, nx - 2 nPml) or padded
+(nz, nx); refs = (cp_ref, cs_ref, ρ_ref) of the same size unless is_masked (src/FWI.jl:174-176)"
+function misfit_and_gradient_b200(p::PlanB200, cp::Matrix{Float64}, cs::Matrix{Float64}, ρ::Matrix{Float64};
+                                  refs = nothing, is_masked::Bool = false)
+    padded = size(cp) == (p.nz, p.nx)
+    size(cs) == size(cp) == size(ρ) || error("fwi_b200: cp, cs, ρ differ in size")
+    is_masked || refs !== nothing || error("fwi_b200: refs = (cp_ref, cs_ref, ρ_ref) is required unless is_masked")
+    r = is_masked ? (C_NULL, C_NULL, C_NULL) : map(a -> pointer(a), refs)
+    GC.@preserve refs begin
+        fwi_error(ccall((:fwi_b200_plan_set_velocities, LIBFWI), Cint,
+                        (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Cint, Cint),
+                        p.h, cp, cs, ρ, r[1], r[2], r[3], is_masked ? 1 : 0, padded ? 1 : 0))
+    end
+    fwi_error(ccall((:fwi_b200_plan_run, LIBFWI), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Cint), p.h, 1, C_NULL, 1))
+    misfit = Ref{Cdouble}(0.0)
+    g_cp = zeros(p.nz, p.nx); g_cs = zeros(p.nz, p.nx); g_ρ = zeros(p.nz, p.nx)
+    fwi_error(ccall((:fwi_b200_plan_get_velocity_gradients, LIBFWI), Cint,
+                    (Ptr{Cvoid}, Ref{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}), p.h, misfit, g_cp, g_cs, g_ρ))
+    misfit[], g_cp, g_cs, g_ρ
+end

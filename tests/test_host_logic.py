@@ -221,7 +221,10 @@ def test_julia_binding_matches_the_header():
     jl = open(os.path.join(root, "julia", "FwiB200.jl")).read()
     calls = re.findall(r"ccall\(\(:(fwi_b200_\w+), LIBFWI\), (\w+),\s*\(([^)]*)\)", jl)
     assert len(calls) >= 6
-    jmap = {"Ref{Cdouble}": "f64p", "Ptr{Cdouble}": "f64p", "Cint": "int", "Ptr{Cint}": "i32p", "Cstring": "str"}
+    jmap = {"Ref{Cdouble}": "f64p", "Ptr{Cdouble}": "f64p", "Cint": "int", "Ptr{Cint}": "i32p", "Cstring": "str",
+            "Ptr{Cvoid}": "ptr", "Ref{Ptr{Cvoid}}": "ptr"}
+    assert {"fwi_b200_plan_create", "fwi_b200_plan_set_velocities", "fwi_b200_plan_get_velocity_gradients",
+            "fwi_b200_plan_run"} <= {c[0] for c in calls}
     for name, ret, types in calls:
         assert name in protos, name
         jt = [t.strip() for t in types.split(",") if t.strip()]
