@@ -468,17 +468,23 @@ constexpr int ASTAGE_BYTES = AS_PAD + AV_BYTES;
 constexpr int APHI_BYTES = 4 * SCOLS * SPITCH * 4;               // new phi of the region (tiles touching the CPML)
 constexpr int AINJ_BYTES = SCOLS * SPITCH * 4;                   // residual injection table
 constexpr int ANB = ADJ_DB ? 2 : 1;                               // buffers of the phi / injection tiles
+#ifndef ADJ_SV1
+#define ADJ_SV1 1   // 1: the new-adjoint-velocity tile is single-buffered too (ordered by the same arrive / wait pair as the phi
+                    // and injection tiles: its first write of an item comes after the wait, its last read before the arrive);
+                    // 16 KB more L1: adj C3 292.5 -> 289.0 us (8 shots), 933.8 -> 923.6 us (25), C2 57.9 -> 57.7 us
+#endif
+constexpr int ANV = (ADJ_SV1 && ADJ_SPLIT && !ADJ_DB) ? 1 : 2;    // buffers of the adjoint-velocity tile
 constexpr size_t ADJ_SMEM =
-    (size_t)ANS * ASTAGE_BYTES + 2 * AV_BYTES + ANB * (APHI_BYTES + AINJ_BYTES) + (ANS + 1) * sizeof(TileDesc) + (ANS + 1) * 8 + 128;
+    (size_t)ANS * ASTAGE_BYTES + ANV * AV_BYTES + ANB * (APHI_BYTES + AINJ_BYTES) + (ANS + 1) * sizeof(TileDesc) + (ANS + 1) * 8 + 128;
 static_assert(AV_BYTES % 128 == 0, "TMA destination alignment");
 
 __global__ void __launch_bounds__(NCOMPUTE, CTAS_PER_SM) adj_step_kernel(const __grid_constant__ BwdArgs a) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char *base = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
   float *s_v_base = reinterpret_cast<float *>(base + ANS * ASTAGE_BYTES);                         // [2][2][SCOLS][SPITCH]
-  float *s_phi_base = reinterpret_cast<float *>(base + ANS * ASTAGE_BYTES + 2 * AV_BYTES);                      // [ANB][4][SCOLS][SPITCH]
-  float *s_inj_base = reinterpret_cast<float *>(base + ANS * ASTAGE_BYTES + 2 * AV_BYTES + ANB * APHI_BYTES);   // [ANB][SCOLS][SPITCH]
-  unsigned char *tail = base + ANS * ASTAGE_BYTES + 2 * AV_BYTES + ANB * (APHI_BYTES + AINJ_BYTES);
+  float *s_phi_base = reinterpret_cast<float *>(base + ANS * ASTAGE_BYTES + ANV * AV_BYTES);                      // [ANB][4][SCOLS][SPITCH]
+  float *s_inj_base = reinterpret_cast<float *>(base + ANS * ASTAGE_BYTES + ANV * AV_BYTES + ANB * APHI_BYTES);   // [ANB][SCOLS][SPITCH]
+  unsigned char *tail = base + ANS * ASTAGE_BYTES + ANV * AV_BYTES + ANB * (APHI_BYTES + AINJ_BYTES);
   TileDesc *sdesc = reinterpret_cast<TileDesc *>(tail);                                          // [ANS + 1]
   uint64_t *full = reinterpret_cast<uint64_t *>(tail + (ANS + 1) * sizeof(TileDesc));
 
@@ -594,7 +600,7 @@ __global__ void __launch_bounds__(NCOMPUTE, CTAS_PER_SM) adj_step_kernel(const _
     const unsigned char *sb = base + stage * ASTAGE_BYTES;
     const float *sa = reinterpret_cast<const float *>(sb);              // [3][VCOLS][VPITCH]: adjoint szz sxx sxz
     const float *sva = reinterpret_cast<const float *>(sb + AS_PAD);    // [2][SCOLS][SPITCH]: adjoint vz vx
-    float *s_v = s_v_base + nb * (AV_BYTES / 4);
+    float *s_v = s_v_base + (ANV == 1 ? 0 : nb) * (AV_BYTES / 4);
     float *s_phi = s_phi_base + (ADJ_DB ? nb : 0) * (APHI_BYTES / 4);
     float *s_inj = s_inj_base + (ADJ_DB ? nb : 0) * (AINJ_BYTES / 4);
 
