@@ -409,6 +409,19 @@ def test_velocity_front_end_on_the_device(ops, is_masked):
             assert rel(a, b) <= 1e-6
             if not is_masked:
                 assert np.all(a[fwi.mask == 0] == 0)
+    # a grid smaller than the absorbing layer: the symmetric extension reflects more than once (np.pad "symmetric")
+    nzs, nxs = 21, 27
+    small = FWI(nz=nzs, nx=nxs, dz=20.0, dx=20.0, nSteps=120, dt=0.002, f0=6.0, ind_src_x=[5, 20], ind_src_z=[12, 12],
+                ind_rec_x=np.arange(2, 25), ind_rec_z=np.full(23, 12))
+    cps = 2500.0 + 40.0 * rng.random((nzs, nxs)); css = cps / np.sqrt(3.0); rhos = 2200.0 + 50.0 * rng.random((nzs, nxs))
+    compute_observation(small, cps, css, rhos, sourceGene(6.0, 120, 0.002))
+    cps2 = cps * (1.0 + 0.02 * rng.random(cps.shape))
+    kws = dict(is_masked=is_masked, cp_ref=cps, cs_ref=css, rho_ref=rhos)
+    ref_s = compute_misfit_and_gradient(small, cps2, css, rhos, sourceGene(6.0, 120, 0.002), **kws)
+    got_s = compute_misfit_and_gradient_resident(small, cps2, css, rhos, sourceGene(6.0, 120, 0.002), **kws)
+    assert ref_s[0] > 0 and got_s[0] == pytest.approx(ref_s[0], rel=1e-6)
+    for a, b in zip(got_s[1:], ref_s[1:]):
+        assert rel(a, b) <= 1e-6
     # the second evaluation reuses the plan, the observations and the source functions
     assert len(fwi._resident_plans) == 1
     again = compute_misfit_and_gradient_resident(fwi, cp2, cs2, rho, stf, shot_ids=[1, 3], **kw)
