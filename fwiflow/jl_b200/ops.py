@@ -181,7 +181,11 @@ def timelapse(surveys, stf, gpu_ids, shot_ids):
 
 
 def set_option(name, value):
-    """Developer A/B switches of the library (fwi_b200_set_option)."""
+    """Developer A/B switches of the library (fwi_b200_set_option; include/fwi_b200.h has the details):
+    "rev_lean" (-1 auto / 0 / 1), "merged_bwd" (0 / 1), "frame_ring" (2 / 5, plans created afterwards),
+    "acc_group" (0 auto, k shots per imaging-accumulator slot of the reverse step), "dyn_units" (1 / 0: the reverse
+    step's work units claimed from a device counter / dealt round-robin).  All of them leave the results unchanged up
+    to the order of float sums."""
     check(_lib.lib().fwi_b200_set_option(str(name).encode(), int(value)))
 
 
