@@ -87,3 +87,45 @@ def test_reconstruction_matches_forward_inside_box():
     P = c.nPml
     box = (slice(P, c.nz_pad - c.nPad - P), slice(P, c.nx_pad - P))
     assert np.isfinite(r["snap_back"]).all() and np.abs(r["snap_back"][box]).max() > 0
+
+
+def test_front_end_restatement_of_the_tensorflow_graph():
+    """oracle/front_end.py (padding / mask / velocity_to_moduli / chain rule around the op, src/FWI.jl:45-49,165-205,
+    src/Utils.jl:221-227): two independent statements of SYMMETRIC padding agree (index arithmetic vs np.pad, also for
+    pads longer than the array), the mask matches its definition, and the chain rule is the derivative of the forward
+    maps (central differences in double)."""
+    from oracle import front_end as fe
+    rng = np.random.default_rng(5)
+    for nz0, nx0, nPml, nPad in ((37, 53, 32, 27), (7, 5, 32, 25), (21, 27, 13, 6), (1, 3, 4, 3)):
+        a = rng.random((nz0, nx0))
+        ref = np.pad(a, ((nPml, nPml + nPad), (nPml, nPml)), mode="symmetric")
+        assert np.array_equal(fe.padding(a, nPml, nPad), ref)
+    m = fe.mask(40, 60, 32, 24)
+    assert m.shape == (128, 124) and m.sum() == 30 * 60 and m[42:72, 32:92].all() and not m[32:42].any()
+    # chain rule vs central differences of J(cp, cs, rho) = sum(w_l lam + w_m mu + w_d rho_masked)
+    nz0, nx0, nPml, nPad = 12, 9, 4, 3
+    cp = 2500.0 + 100.0 * rng.random((nz0, nx0)); cs = 1400.0 + 80.0 * rng.random((nz0, nx0)); rho = 2200.0 + 50.0 * rng.random((nz0, nx0))
+    refs = (cp * 1.01, cs * 0.99, rho * 1.02)
+    shape = (nz0 + 2 * nPml + nPad, nx0 + 2 * nPml)
+    wl, wm, wd = rng.random(shape), rng.random(shape), rng.random(shape)
+    for is_masked in (False, True):
+        cp_p, cs_p, rho_p = (fe.padding(x, nPml, nPad) for x in (cp, cs, rho))      # differentiate w.r.t. padded inputs
+
+        def J(cpp, csp, rhop):
+            lam, mu, den, _, _ = fe.front_end(cpp, csp, rhop, nPml, nPad, is_masked, refs, shape_padded=shape)
+            return float(np.sum(wl * lam + wm * mu + wd * den))
+        _, _, _, vel, msk = fe.front_end(cp_p, cs_p, rho_p, nPml, nPad, is_masked, refs, shape_padded=shape)
+        g = fe.chain_rule(vel, wl, wm, wd, msk, is_masked)
+        for k, (x, eps) in enumerate(((cp_p, 1e-2), (cs_p, 1e-2), (rho_p, 1e-2))):
+            for (z, xx) in ((0, 0), (nPml + 10, nPml + 2), (nPml + 11, nPml + 5), (shape[0] - 1, shape[1] - 1), (nPml + 3, nPml + 3)):
+                args = [cp_p.copy(), cs_p.copy(), rho_p.copy()]
+                args[k][z, xx] += eps; jp = J(*args)
+                args[k][z, xx] -= 2 * eps; jm = J(*args)
+                fd = (jp - jm) / (2 * eps)
+                assert fd == pytest.approx(g[k][z, xx], rel=1e-6, abs=1e-9), (is_masked, k, z, xx)
+    # the product's host mirror (fwiflow/jl_b200/utils.py) says the same
+    from fwiflow.jl_b200 import utils
+    assert np.array_equal(utils.symmetric_pad(cp, 4, 3), fe.padding(cp, 4, 3))
+    lam_u, mu_u = utils.velocity_to_moduli(cp, cs, rho)
+    lam_o, mu_o = fe.velocity_to_moduli(cp, cs, rho)
+    assert np.array_equal(lam_u, lam_o) and np.array_equal(mu_u, mu_o)

@@ -401,6 +401,15 @@ def test_velocity_front_end_on_the_device(ops, is_masked):
     cp2 = cp * (1.0 + 0.03 * rng.random(cp.shape)); cs2 = cs * (1.0 - 0.02 * rng.random(cp.shape))
     kw = dict(is_masked=is_masked, cp_ref=cp, cs_ref=cs, rho_ref=rho)
     ref = compute_misfit_and_gradient(fwi, cp2, cs2, rho, stf, shot_ids=[1, 3], **kw)
+    # the checker proper: oracle/front_end.py (numpy restatement of the TensorFlow graph around the op, independent of
+    # the product's host mirror) -> host-buffer op -> oracle chain rule
+    from oracle import front_end as fe
+    lam_o, mu_o, rho_o, vel_o, mask_o = fe.front_end(cp2, cs2, rho, fwi.nPml, fwi.nPad, is_masked, (cp, cs, rho))
+    stf_rows = np.repeat(np.atleast_2d(stf), 3, axis=0)
+    j_o, gl_o, gm_o, gd_o, _ = ops.fwi_op_and_grad(lam_o, mu_o, rho_o, stf_rows, 0, [0, 2], fwi.para_path)
+    orc = (j_o, *fe.chain_rule(vel_o, gl_o, gm_o, gd_o, mask_o, is_masked))
+    assert ref[0] == pytest.approx(orc[0], rel=1e-6) and all(rel(a, b) <= 1e-6 for a, b in zip(ref[1:], orc[1:]))
+    ref = orc
     for models in ((cp2, cs2, rho), padding(fwi, cp2, cs2, rho)):          # unpadded (device pads) and padded inputs
         got = compute_misfit_and_gradient_resident(fwi, *models, stf, shot_ids=[1, 3], **kw)
         assert got[0] == pytest.approx(ref[0], rel=1e-6)
