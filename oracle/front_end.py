@@ -2,6 +2,12 @@
 velocity-space interface, and of the derivative TensorFlow's autodiff takes through it.  Checker for
 fwi_b200_plan_set_velocities / fwi_b200_plan_get_velocity_gradients; the product never imports this.
 
+PARITY UNPINNED against the reference itself for this file: the reference's front end is Julia + TensorFlow, neither of
+which runs in this image, and the reference's tests hold no golden vectors for it.  What pins it instead: np.pad's
+"symmetric" mode as a second statement of tf.pad SYMMETRIC, the mask's definition, and central differences of its own
+forward maps for the chain rule (tests/test_oracle_golden.py).  (The propagator oracle, oracle/fwi_oracle.cpp, IS pinned
+against the reference's own op: tests/golden/.)
+
   padding            /root/reference/src/FWI.jl:193-205   tf.pad(cp, [nPml (nPml+nPad); nPml nPml], "SYMMETRIC")
   mask               /root/reference/src/FWI.jl:45-49     ones inside the absorbing layers, minus 10 rows under the top one
   mask blend         /root/reference/src/FWI.jl:174-176   cp .* mask + cp_ref .* mask_neg
